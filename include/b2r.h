@@ -1,0 +1,148 @@
+/* b2r -- B200 exact vector-retrieval engine: the C ABI (drop-in boundary).
+ *
+ * This is what a binding on the reference side would call instead of the
+ * chromadb.Collection methods that app/utils/embedder.py reaches through
+ * `self.collection` (reference file:line cited per entry point below).  Plain C:
+ * pointers and sizes only, no torch / C++ types.  All entry points are thread-safe
+ * (one host mutex per handle; every call does cudaSetDevice, because the reference
+ * calls the store from asyncio.to_thread worker threads, embedder.py:517,595).
+ *
+ * Conventions
+ *   - every function returns a b2r_status (0 = ok); b2r_last_error() gives the
+ *     message for the calling thread's last failure.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - data pointers marked "host or device" are classified with
+ *     cudaPointerGetAttributes.  With device pointers a call only enqueues work on
+ *     `stream`; with host pointers it copies (cudaMemcpyAsync on `stream`) and, for
+ *     outputs, synchronises the stream before returning.
+ *   - row numbers are dense insertion indices starting at 0 (the host keeps
+ *     row <-> Chroma id).  Rows are never reused; delete/upsert tombstone.
+ *   - there is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef B2R_H_
+#define B2R_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_ABI_VERSION 1
+
+typedef struct b2r_index *b2r_handle;
+
+typedef enum {
+    B2R_OK = 0,
+    B2R_EINVAL = 1,      /* bad argument / dimension mismatch -> ValueError upstream */
+    B2R_ECUDA = 2,       /* CUDA runtime failure              -> RuntimeError        */
+    B2R_ENOMEM = 3,      /* device allocation failed                                */
+    B2R_EUNSUPPORTED = 4 /* k or dim outside what the kernels are built for         */
+} b2r_status;
+
+/* Chroma `hnsw:space` (collection metadata; default l2 -- embedder.py:179-182 passes
+ * no space, the committed chroma_db/ says cosine).  Distances returned:
+ *   L2     sum (q-x)^2            COSINE  1 - q^.x^  (both normalised at ingest/query)
+ *   IP     1 - q.x                                                                   */
+typedef enum { B2R_SPACE_L2 = 0, B2R_SPACE_COSINE = 1, B2R_SPACE_IP = 2 } b2r_space;
+
+/* create flags */
+#define B2R_FLAG_NO_F32_MASTER 1u /* keep only the packed bf16 rows: the corpus *is* its
+                                     bf16 rounding, re-rank and get_rows read that.     */
+
+/* Row filter (Chroma `where`, embedder.py:543,599).  The host evaluates the clause on
+ * its metadata tables and hands the device either a type-code mask (fast path for
+ * {"type": ...}) or a general allow bitmap.  Tombstoned rows never match.             */
+typedef struct {
+    uint64_t type_mask;         /* bit c set = rows with type_code c pass; ~0 = all    */
+    const uint32_t *allow_bits; /* NULL, or ceil(rows/32) words, host or device:
+                                   bit (r&31) of word r>>5 set = row r passes          */
+} b2r_filter;
+
+typedef struct {
+    int32_t dim, dim_padded, space;
+    uint32_t flags;
+    int64_t rows;          /* rows appended so far (live + tombstoned)                */
+    int64_t live;          /* rows not tombstoned                                     */
+    int64_t capacity;      /* rows the current allocation holds                       */
+    int64_t bytes_device;  /* HBM held by this handle                                 */
+    int64_t n_queries;     /* queries answered                                        */
+    int64_t n_exact_fallbacks; /* queries whose bf16 candidate certificate failed and
+                                  were recomputed by the exact fp64 scan (only counted
+                                  on calls with host outputs)                          */
+    int32_t sm_count, device;
+} b2r_stats;
+
+int b2r_abi_version(void);
+const char *b2r_last_error(void);
+
+/* replaces chromadb.Client(...).create_collection / get_collection
+ * (app/utils/embedder.py:170-183).  capacity_rows is a reservation hint (grows x2). */
+int b2r_create(int dim, int space, int64_t capacity_rows, int device, uint32_t flags,
+               b2r_handle *out);
+/* replaces client.delete_collection (app/utils/embedder.py:669-672) */
+int b2r_destroy(b2r_handle h);
+/* drop all rows, keep the allocation (delete_all_documents, embedder.py:658-688) */
+int b2r_clear(b2r_handle h);
+int b2r_reserve(b2r_handle h, int64_t capacity_rows);
+
+/* replaces the vector half of collection.add / upsert (app/utils/embedder.py:517-523):
+ * x is [n, dim] fp32 row-major, host or device.  Fused on device: (cosine) L2
+ * normalise, bf16 pack, fp32 master store, per-row -|x|^2/2 for l2.  type_code is n
+ * bytes (values 0..62), host or device, or NULL (= 0).  Rows become visible to every
+ * later call on the same stream.  *first_row_out = row number given to x[0].        */
+int b2r_ingest_f32(b2r_handle h, const float *x, int64_t n, const uint8_t *type_code,
+                   int64_t *first_row_out, void *stream);
+
+/* replaces the vector half of collection.delete (app/utils/embedder.py:639-642) and the
+ * overwrite half of upsert: rows (host array) stop matching any query.               */
+int b2r_tombstone(b2r_handle h, const int64_t *rows, int64_t n, void *stream);
+
+/* replaces collection.query(query_embeddings, n_results, where)
+ * (app/utils/embedder.py:595-601, 900-905): q is [nq, dim] fp32 (host or device),
+ * k = n_results.  Outputs, host or device (all three the same kind):
+ *   out_rows  [nq, k] int64, ascending distance, ties -> lower row; padded with -1
+ *   out_dist  [nq, k] fp32 distance in the collection's space; padded with +inf
+ *   out_count [nq]    int32 = min(k, rows passing the filter)
+ * Exact: identical rows to an fp64 brute force over the stored rows.                 */
+int b2r_query(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
+              int64_t *out_rows, float *out_dist, int32_t *out_count, void *stream);
+/* same, plus the fp64 distances the ordering was decided on (out_dist64 [nq,k] or NULL);
+ * the cross-shard merge needs them to stay exact.                                    */
+int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
+                 int64_t *out_rows, float *out_dist, double *out_dist64, int32_t *out_count,
+                 void *stream);
+
+/* replaces collection.get(ids, include=['embeddings']) (app/utils/embedder.py:887-891):
+ * the stored fp32 rows (normalised in cosine space, as hnswlib stores them).         */
+int b2r_get_rows_f32(b2r_handle h, const int64_t *rows, int64_t n, float *out, void *stream);
+
+/* replaces collection.count() (app/utils/embedder.py:700): live rows               */
+int64_t b2r_count(b2r_handle h);
+int b2r_get_stats(b2r_handle h, b2r_stats *out);
+
+/* Row-sharded corpus (one process per GPU): rows reported by b2r_query are
+ * row_base + local row, so every shard can answer in global row numbers.            */
+int b2r_set_row_base(b2r_handle h, int64_t row_base);
+
+/* Cross-shard merge: after an allgather of every rank's local b2r_query_ex result, pick
+ * the global top-k per query.  in_rows [nshards,nq,k] int64 (global rows, -1 = pad),
+ * in_dist64 [nshards,nq,k] fp64, in_count [nshards,nq]; all device pointers.
+ * Order: (fp64 distance, global row) -- the same total order a single shard uses.
+ * No reference counterpart: the reference is single-process.                        */
+int b2r_merge_shards(const int64_t *in_rows, const double *in_dist64, const int32_t *in_count,
+                     int nshards, int nq, int k, int64_t *out_rows, float *out_dist,
+                     int32_t *out_count, int device, void *stream);
+
+/* Diagnostics used by bench.py: run only the scoring/selection kernel selected by
+ * `path` on device-resident prepared inputs, so it can be timed alone.
+ *   path 0 = automatic (what b2r_query picks), 1 = warp-shuffle scan, 2 = tcgen05,
+ *   3 = exact fp64 scan.                                                            */
+int b2r_set_path(b2r_handle h, int path);
+/* number of kernel launches issued by this handle since creation                    */
+int64_t b2r_launch_count(b2r_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2R_H_ */

@@ -1,0 +1,399 @@
+"""Drop-in for the duck-typed Chroma client/collection the reference holds in
+``EmbeddingManager.client`` / ``.collection``.
+
+Reference seam: ``chromadb.Client(...)`` + ``get_collection`` /
+``create_collection(name, metadata)`` / ``delete_collection`` (app/utils/embedder.py:170-183,
+669-678) and the collection methods ``add`` (:518), ``query`` (:596, :901), ``get`` (:632, :888),
+``delete`` (:640), ``count`` (:700) -- same keyword arguments, same result shapes (nested lists
+per query for ``query``, flat lists for ``get``), Chroma's error behaviour for bad input.
+
+Vectors, scoring, selection and the exact re-rank live on the GPU behind the C ABI
+(include/b2r.h); ids, documents and metadata dicts stay in host tables keyed by the dense row
+number the device reports.  No CPU fallback exists: constructing a collection without the CUDA
+library or without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+import threading
+
+import numpy as np
+
+from . import _lib
+from .where import MetaTable, pack_bits
+
+logger = logging.getLogger(__name__)
+
+_INCLUDE_QUERY = ("metadatas", "documents", "distances")
+_INCLUDE_GET = ("metadatas", "documents")
+_VALID_INCLUDE = {"metadatas", "documents", "distances", "embeddings"}
+
+
+def _torch():
+    import sys
+    return sys.modules.get("torch")
+
+
+class _Matrix:
+    """A [n, d] fp32 row-major matrix somewhere (host numpy or CUDA torch) + its raw pointer."""
+
+    def __init__(self, x, what="embeddings"):
+        t = _torch()
+        self.keep = None
+        self.stream = 0
+        if t is not None and isinstance(x, t.Tensor):
+            if x.dim() == 1:
+                x = x[None]
+            if x.dim() != 2:
+                raise ValueError(f"{what} must be a 2-D [n, dim] array")
+            x = x.detach().to(dtype=t.float32).contiguous()
+            self.keep, self.n, self.d, self.ptr = x, int(x.shape[0]), int(x.shape[1]), x.data_ptr()
+            self.is_cuda = x.is_cuda
+            if x.is_cuda:
+                self.device = x.device.index if x.device.index is not None else t.cuda.current_device()
+                self.stream = t.cuda.current_stream(x.device).cuda_stream
+            return
+        try:
+            a = np.asarray(x, dtype=np.float32)
+        except (ValueError, TypeError) as e:
+            raise ValueError(f"{what} must be a list of equal-length float vectors: {e}") from None
+        if a.ndim == 1 and a.size and not isinstance(x[0], (list, tuple, np.ndarray)):
+            a = a[None]
+        if a.ndim != 2:
+            raise ValueError(f"{what} must be a 2-D [n, dim] array")
+        a = np.ascontiguousarray(a)
+        self.keep, self.n, self.d, self.ptr, self.is_cuda = a, int(a.shape[0]), int(a.shape[1]), a.ctypes.data, False
+
+
+class B200Collection:
+    """Exact GPU collection with ``chromadb.Collection``'s add/upsert/query/get/delete/count."""
+
+    def __init__(self, name="multimodal_rag", metadata=None, *, device=0, capacity=0,
+                 keep_f32_master=True, dimension=None):
+        self.name = name
+        self.metadata = dict(metadata) if metadata else None
+        space = (metadata or {}).get("hnsw:space", "l2")          # Chroma's default space
+        if space not in _lib.SPACE_CODE:
+            raise ValueError(f"hnsw:space must be one of {sorted(_lib.SPACE_CODE)}, got {space!r}")
+        self.space = space
+        self.device = int(device)
+        self._capacity = int(capacity)
+        self._flags = 0 if keep_f32_master else _lib.FLAG_NO_F32_MASTER
+        self._lib = _lib.load()
+        self._h = None
+        self._dim = None
+        self._lock = threading.RLock()
+        self._ids: list[str] = []
+        self._docs: list = []
+        self._alive = np.zeros(0, dtype=bool)
+        self._row_of: dict[str, int] = {}
+        self._meta = MetaTable()
+        if dimension is not None:
+            self._open(int(dimension))
+
+    # ---- handle --------------------------------------------------------------------
+    def _open(self, dim: int):
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.b2r_create(dim, _lib.SPACE_CODE[self.space], self._capacity, self.device,
+                                        self._flags, ctypes.byref(h)), "b2r_create")
+        self._h, self._dim = h, dim
+
+    def close(self):
+        with self._lock:
+            if self._h is not None:
+                self._lib.b2r_destroy(self._h)
+                self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def dimension(self):
+        return self._dim
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ---- validation ------------------------------------------------------------------
+    def _validate_batch(self, ids, embeddings, metadatas, documents):
+        if ids is None or isinstance(ids, str):
+            ids = [ids] if isinstance(ids, str) else ids
+        if not isinstance(ids, (list, tuple)):
+            raise ValueError("Expected ids to be a list of str")
+        n = len(ids)
+        for i in ids:
+            if not isinstance(i, str) or not i:
+                raise ValueError(f"Expected ID to be a non-empty str, got {i!r}")
+        if len(set(ids)) != n:
+            seen, dup = set(), []
+            for i in ids:
+                if i in seen:
+                    dup.append(i)
+                seen.add(i)
+            raise ValueError(f"Expected IDs to be unique, found duplicates of: {', '.join(dup[:5])}")
+        if embeddings is None:
+            raise ValueError("embeddings are required: this collection has no embedding function")
+        m = _Matrix(embeddings)
+        if m.n != n:
+            raise ValueError(f"Number of embeddings {m.n} must match number of ids {n}")
+        for name, lst in (("metadatas", metadatas), ("documents", documents)):
+            if lst is not None and len(lst) != n:
+                raise ValueError(f"Number of {name} {len(lst)} must match number of ids {n}")
+        if metadatas is not None:
+            for md in metadatas:
+                MetaTable.validate(md)
+        if n and self._dim is not None and m.d != self._dim:
+            raise ValueError(f"Embedding dimension {m.d} does not match collection dimensionality {self._dim}")
+        return list(ids), m
+
+    # ---- mutations -------------------------------------------------------------------
+    def _append_rows(self, ids, m: _Matrix, sel, metadatas, documents):
+        """Ingest rows `sel` (indices into the batch) and register them on the host."""
+        if not sel:
+            return
+        if self._h is None:
+            self._open(m.d)
+        metas = [None if metadatas is None else metadatas[i] for i in sel]
+        # type codes must be known before the device call; MetaTable only commits below
+        codes = np.asarray([self._meta.type_code_of(md) for md in metas], dtype=np.uint8)
+        if len(sel) == m.n:
+            ptr, keep = m.ptr, m.keep
+        elif m.is_cuda:
+            keep = m.keep[_torch().as_tensor(sel, device=m.keep.device)].contiguous()
+            ptr = keep.data_ptr()
+        else:
+            keep = np.ascontiguousarray(m.keep[sel])
+            ptr = keep.ctypes.data
+        first = ctypes.c_int64(-1)
+        _lib.check(self._lib.b2r_ingest_f32(self._h, ptr, len(sel), codes.ctypes.data, ctypes.byref(first),
+                                            m.stream), "b2r_ingest_f32")
+        assert first.value == len(self._ids), "host tables out of step with the device corpus"
+        for j, i in enumerate(sel):
+            self._row_of[ids[i]] = first.value + j
+            self._ids.append(ids[i])
+            self._docs.append(None if documents is None else documents[i])
+            self._meta.append(metas[j])
+        self._alive = np.concatenate([self._alive, np.ones(len(sel), dtype=bool)])
+
+    def _kill_rows(self, rows):
+        if not rows:
+            return
+        arr = np.asarray(rows, dtype=np.int64)
+        _lib.check(self._lib.b2r_tombstone(self._h, arr.ctypes.data, arr.shape[0], 0), "b2r_tombstone")
+        self._alive[arr] = False
+        for r in rows:
+            self._row_of.pop(self._ids[r], None)
+
+    def add(self, ids, embeddings=None, metadatas=None, documents=None):
+        """Chroma ``Collection.add``: ids already present are skipped (with a warning)."""
+        with self._lock:
+            ids, m = self._validate_batch(ids, embeddings, metadatas, documents)
+            sel = [i for i, id_ in enumerate(ids) if id_ not in self._row_of]
+            if len(sel) != len(ids):
+                logger.warning("Add of existing embedding ID(s) skipped: %d of %d", len(ids) - len(sel), len(ids))
+            self._append_rows(ids, m, sel, metadatas, documents)
+
+    def upsert(self, ids, embeddings=None, metadatas=None, documents=None):
+        """Chroma ``Collection.upsert``: existing ids are overwritten (tombstone + append)."""
+        with self._lock:
+            ids, m = self._validate_batch(ids, embeddings, metadatas, documents)
+            old = [self._row_of[i] for i in ids if i in self._row_of]
+            if self._h is None and ids:
+                self._open(m.d)
+            self._kill_rows(old)
+            self._append_rows(ids, m, list(range(len(ids))), metadatas, documents)
+
+    def delete(self, ids=None, where=None):
+        with self._lock:
+            rows = self._select_rows(ids, where)
+            self._kill_rows(rows)
+            return [self._ids[r] for r in rows]
+
+    def count(self) -> int:
+        with self._lock:
+            if self._h is None:
+                return 0
+            n = int(self._lib.b2r_count(self._h))
+            assert n == len(self._row_of), "host tables out of step with the device corpus"
+            return n
+
+    # ---- reads -----------------------------------------------------------------------
+    def _select_rows(self, ids, where):
+        if ids is not None:
+            if isinstance(ids, str):
+                ids = [ids]
+            rows = sorted(self._row_of[i] for i in ids if i in self._row_of)
+            if where:
+                mask = self._meta.mask(where)
+                rows = [r for r in rows if mask[r]]
+            return rows
+        if where:
+            mask = self._meta.mask(where) & self._alive
+        else:
+            mask = self._alive
+        return np.flatnonzero(mask).tolist()
+
+    def _fetch_rows(self, rows):
+        out = np.empty((len(rows), self._dim), dtype=np.float32)
+        if rows:
+            arr = np.asarray(rows, dtype=np.int64)
+            _lib.check(self._lib.b2r_get_rows_f32(self._h, arr.ctypes.data, arr.shape[0], out.ctypes.data, 0),
+                       "b2r_get_rows_f32")
+        return out
+
+    @staticmethod
+    def _check_include(include, allowed):
+        include = list(include)
+        for key in include:
+            if key not in _VALID_INCLUDE or key not in allowed:
+                raise ValueError(f"Expected include item to be one of {sorted(allowed)}, got {key}")
+        return include
+
+    def get(self, ids=None, where=None, limit=None, offset=None, include=_INCLUDE_GET):
+        include = self._check_include(include, {"metadatas", "documents", "embeddings"})
+        with self._lock:
+            rows = self._select_rows(ids, where)
+            if offset:
+                rows = rows[offset:]
+            if limit is not None:
+                rows = rows[:limit]
+            out = {"ids": [self._ids[r] for r in rows], "embeddings": None, "metadatas": None, "documents": None}
+            if "embeddings" in include:
+                out["embeddings"] = self._fetch_rows(rows).tolist() if rows else []
+            if "metadatas" in include:
+                out["metadatas"] = [self._meta.meta[r] for r in rows]
+            if "documents" in include:
+                out["documents"] = [self._docs[r] for r in rows]
+            return out
+
+    def _filter(self, where):
+        """where -> (B2RFilter, keep-alive object).  None when nothing can match."""
+        f = _lib.B2RFilter(type_mask=(1 << 64) - 1, allow_bits=None)
+        if not where:
+            return f, None
+        tm = self._meta.type_only_mask(where)
+        if tm is not None:
+            f.type_mask = tm
+            return f, None
+        bits = pack_bits(self._meta.mask(where))
+        f.allow_bits = bits.ctypes.data
+        return f, bits
+
+    def query_rows(self, query_embeddings, n_results=10, where=None, want_dist64=False):
+        """Device query returning numpy arrays: rows [nq,k] int64 (-1 pad), dist [nq,k] fp32,
+        count [nq] int32 (and fp64 distances when asked)."""
+        with self._lock:
+            if not isinstance(n_results, int) or isinstance(n_results, bool) or n_results <= 0:
+                raise ValueError(f"Expected n_results to be a positive integer, got {n_results}")
+            m = _Matrix(query_embeddings, "query_embeddings")
+            if m.n == 0:
+                raise ValueError("Expected query_embeddings to be a non-empty list")
+            if self._dim is not None and m.d != self._dim:
+                raise ValueError(f"Query dimension {m.d} does not match collection dimensionality {self._dim}")
+            k = n_results
+            rows = np.full((m.n, k), -1, dtype=np.int64)
+            dist = np.full((m.n, k), np.inf, dtype=np.float32)
+            cnt = np.zeros((m.n,), dtype=np.int32)
+            d64 = np.full((m.n, k), np.inf, dtype=np.float64) if want_dist64 else None
+            if self._h is None or not self._row_of:
+                return (rows, dist, cnt, d64) if want_dist64 else (rows, dist, cnt)
+            f, keep = self._filter(where)
+            _lib.check(self._lib.b2r_query_ex(self._h, m.ptr, m.n, k, ctypes.byref(f), rows.ctypes.data,
+                                              dist.ctypes.data, None if d64 is None else d64.ctypes.data,
+                                              cnt.ctypes.data, m.stream), "b2r_query")
+            del keep
+            return (rows, dist, cnt, d64) if want_dist64 else (rows, dist, cnt)
+
+    def query(self, query_embeddings=None, n_results=10, where=None, where_document=None,
+              include=_INCLUDE_QUERY, query_texts=None):
+        """Chroma ``Collection.query``: nested lists, one inner list per query, ascending
+        distance; keys not in ``include`` are None."""
+        if query_texts is not None and query_embeddings is None:
+            raise ValueError("query_texts needs an embedding function; pass query_embeddings")
+        if where_document:
+            raise NotImplementedError("where_document ($contains) is not part of the reference's hot path")
+        include = self._check_include(include, _VALID_INCLUDE)
+        with self._lock:
+            rows, dist, cnt = self.query_rows(query_embeddings, n_results, where)
+            nq = rows.shape[0]
+            live = len(self._row_of)
+            if n_results > live:
+                logger.warning("Number of requested results %d is greater than number of elements in index %d, "
+                               "updating n_results = %d", n_results, live, live)
+            res = {"ids": [], "distances": None, "metadatas": None, "documents": None, "embeddings": None}
+            for key in include:
+                res[key] = []
+            for i in range(nq):
+                rr = rows[i, : cnt[i]].tolist()
+                res["ids"].append([self._ids[r] for r in rr])
+                if res["distances"] is not None:
+                    res["distances"].append(dist[i, : cnt[i]].tolist())
+                if res["metadatas"] is not None:
+                    res["metadatas"].append([self._meta.meta[r] for r in rr])
+                if res["documents"] is not None:
+                    res["documents"].append([self._docs[r] for r in rr])
+                if res["embeddings"] is not None:
+                    res["embeddings"].append(self._fetch_rows(rr).tolist() if rr else [])
+            return res
+
+    def stats(self) -> dict:
+        with self._lock:
+            if self._h is None:
+                return {"rows": 0, "live": 0}
+            st = _lib.B2RStats()
+            _lib.check(self._lib.b2r_get_stats(self._h, ctypes.byref(st)), "b2r_get_stats")
+            out = {name: getattr(st, name) for name, _ in st._fields_}
+            out["launches"] = int(self._lib.b2r_launch_count(self._h))
+            return out
+
+    def set_path(self, path: int):
+        """Diagnostics: 0 auto, 1 warp-shuffle scan, 2 tcgen05, 3 exact fp64 scan."""
+        _lib.check(self._lib.b2r_set_path(self._h, int(path)), "b2r_set_path")
+
+
+class B200Client:
+    """The ``chromadb.Client`` trio the reference uses (app/utils/embedder.py:170-183, 669-678)."""
+
+    def __init__(self, device=0, keep_f32_master=True, default_capacity=0):
+        self.device = device
+        self.keep_f32_master = keep_f32_master
+        self.default_capacity = default_capacity
+        self._collections: dict[str, B200Collection] = {}
+        self._lock = threading.Lock()
+        _lib.load()    # fail now, loudly, if the CUDA library is absent
+
+    def create_collection(self, name, metadata=None, get_or_create=False, **kw):
+        with self._lock:
+            if name in self._collections:
+                if get_or_create:
+                    return self._collections[name]
+                raise ValueError(f"Collection {name} already exists.")
+            c = B200Collection(name, metadata, device=kw.pop("device", self.device),
+                               capacity=kw.pop("capacity", self.default_capacity),
+                               keep_f32_master=kw.pop("keep_f32_master", self.keep_f32_master), **kw)
+            self._collections[name] = c
+            return c
+
+    def get_collection(self, name):
+        with self._lock:
+            if name not in self._collections:
+                raise ValueError(f"Collection {name} does not exist.")
+            return self._collections[name]
+
+    def get_or_create_collection(self, name, metadata=None, **kw):
+        return self.create_collection(name, metadata, get_or_create=True, **kw)
+
+    def delete_collection(self, name):
+        with self._lock:
+            if name not in self._collections:
+                raise ValueError(f"Collection {name} does not exist.")
+            self._collections.pop(name).close()
+
+    def list_collections(self):
+        with self._lock:
+            return list(self._collections.values())

@@ -1,0 +1,546 @@
+// C ABI implementation (include/b2r.h): handle lifetime, HBM layout, host<->device
+// staging and kernel dispatch.  No compute happens on the host.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "engine.h"
+#include "ingest.cuh"
+
+using namespace b2r;
+
+// ---------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void b2r::set_error(const std::string &msg) { g_last_error = msg; }
+
+#define B2R_REQUIRE(cond, msg)                      \
+    do {                                            \
+        if (!(cond)) { set_error(msg); return B2R_EINVAL; } \
+    } while (0)
+
+extern "C" const char *b2r_last_error(void) { return g_last_error.c_str(); }
+extern "C" int b2r_abi_version(void) { return B2R_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------
+namespace {
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure(DevBuf &b, size_t bytes) {
+    if (b.bytes >= bytes) return B2R_OK;
+    if (b.p) { B2R_CUDA(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+    size_t want = std::max(bytes, (size_t)256);
+    want = (want + 255) & ~(size_t)255;
+    B2R_CUDA(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return B2R_OK;
+}
+void release(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// entries-per-lane of the candidate lists for a fast-path query: KP = 32*EPL >= 2k
+int epl_scored(int k) { return k <= 16 ? 1 : k <= 32 ? 2 : k <= 64 ? 4 : k <= 128 ? 8 : 0; }
+// exact path: KP >= k
+int epl_exact(int k) { return k <= 32 ? 1 : k <= 64 ? 2 : k <= 128 ? 4 : k <= 256 ? 8 : 0; }
+
+size_t row_bytes_total(const b2r_index *h) {
+    size_t b = (size_t)h->dp * 2 + 1;
+    if (h->master) b += (size_t)h->dp * 4;
+    if (h->space == B2R_SPACE_L2) b += 4;
+    return b;
+}
+
+// (re)allocate the corpus arrays for `cap` rows, preserving the first h->rows rows
+int grow(b2r_index *h, int64_t cap, cudaStream_t s) {
+    if (cap <= h->capacity) return B2R_OK;
+    cap = std::max<int64_t>(cap, 1024);
+    uint4 *corpus = nullptr; float *master = nullptr, *bias = nullptr; uint8_t *tc = nullptr;
+    const size_t cb = (size_t)cap * h->dp * 2;
+    B2R_CUDA(cudaMalloc(&corpus, cb));
+    if (!(h->flags & B2R_FLAG_NO_F32_MASTER)) {
+        cudaError_t e = cudaMalloc(&master, (size_t)cap * h->dp * 4);
+        if (e != cudaSuccess) { cudaFree(corpus); B2R_CUDA(e); }
+    }
+    if (h->space == B2R_SPACE_L2) {
+        cudaError_t e = cudaMalloc(&bias, (size_t)cap * 4);
+        if (e != cudaSuccess) { cudaFree(corpus); cudaFree(master); B2R_CUDA(e); }
+    }
+    {
+        cudaError_t e = cudaMalloc(&tc, (size_t)cap + 4);
+        if (e != cudaSuccess) { cudaFree(corpus); cudaFree(master); cudaFree(bias); B2R_CUDA(e); }
+    }
+    if (h->rows > 0) {
+        B2R_CUDA(cudaMemcpyAsync(corpus, h->corpus, (size_t)h->rows * h->dp * 2, cudaMemcpyDeviceToDevice, s));
+        if (master) B2R_CUDA(cudaMemcpyAsync(master, h->master, (size_t)h->rows * h->dp * 4, cudaMemcpyDeviceToDevice, s));
+        if (bias) B2R_CUDA(cudaMemcpyAsync(bias, h->bias, (size_t)h->rows * 4, cudaMemcpyDeviceToDevice, s));
+        B2R_CUDA(cudaMemcpyAsync(tc, h->type_code, (size_t)h->rows, cudaMemcpyDeviceToDevice, s));
+    }
+    B2R_CUDA(cudaStreamSynchronize(s));
+    cudaFree(h->corpus); cudaFree(h->master); cudaFree(h->bias); cudaFree(h->type_code);
+    h->corpus = corpus; h->master = master; h->bias = bias; h->type_code = tc;
+    h->capacity = cap;
+    return B2R_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------
+extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device, uint32_t flags,
+                          b2r_handle *out) {
+    B2R_REQUIRE(out != nullptr, "b2r_create: out is NULL");
+    *out = nullptr;
+    B2R_REQUIRE(dim >= 1 && dim <= 8192, "b2r_create: dim must be in [1, 8192]");
+    B2R_REQUIRE(space >= 0 && space <= 2, "b2r_create: unknown space");
+    B2R_REQUIRE(capacity_rows >= 0 && capacity_rows < (1ll << 32) - 64, "b2r_create: capacity out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("b2r_create: no CUDA device (this engine has no CPU fallback)");
+        return B2R_ECUDA;
+    }
+    B2R_REQUIRE(device >= 0 && device < ndev, "b2r_create: bad device ordinal");
+    B2R_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2R_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("b2r_create: kernels are built for sm_100a only, device is sm_" + std::to_string(prop.major) +
+                  std::to_string(prop.minor));
+        return B2R_EUNSUPPORTED;
+    }
+    b2r_index *h = new (std::nothrow) b2r_index();
+    if (!h) { set_error("b2r_create: host allocation failed"); return B2R_ENOMEM; }
+    h->dim = dim; h->dp = round_up(dim, 64); h->space = space; h->device = device; h->flags = flags;
+    h->sm_count = prop.multiProcessorCount;
+    int rc = B2R_OK;
+    do {
+        if (cudaMalloc(&h->max_norm2, 256) != cudaSuccess || cudaMalloc(&h->counters, 256) != cudaSuccess ||
+            cudaMalloc(&h->tickets, sizeof(unsigned) * (1 + EXACT_MAX_BATCH)) != cudaSuccess) {
+            set_error("b2r_create: cudaMalloc failed"); rc = B2R_ENOMEM; break;
+        }
+        cudaMemset(h->max_norm2, 0, 256);
+        cudaMemset(h->counters, 0, 256);
+        cudaMemset(h->tickets, 0, sizeof(unsigned) * (1 + EXACT_MAX_BATCH));
+        rc = grow(h, std::max<int64_t>(capacity_rows, 1024), 0);
+    } while (0);
+    if (rc != B2R_OK) { b2r_destroy(h); return rc; }
+    *out = h;
+    return B2R_OK;
+}
+
+extern "C" int b2r_destroy(b2r_handle h) {
+    if (!h) return B2R_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->corpus); cudaFree(h->master); cudaFree(h->bias); cudaFree(h->type_code);
+    cudaFree(h->max_norm2); cudaFree(h->counters); cudaFree(h->tickets);
+    DevBuf *bufs[] = {&h->x_stage, &h->t_stage, &h->q_raw, &h->q_prep, &h->allow, &h->rows_stage, &h->gather_out,
+                      &h->o_rows, &h->o_dist, &h->o_dist64, &h->o_count, &h->need_exact, &h->scan_lists,
+                      &h->exact_lists};
+    for (DevBuf *b : bufs) release(*b);
+    delete h;
+    return B2R_OK;
+}
+
+extern "C" int b2r_clear(b2r_handle h) {
+    B2R_REQUIRE(h, "b2r_clear: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    B2R_CUDA(cudaDeviceSynchronize());
+    h->rows = 0; h->live = 0;
+    B2R_CUDA(cudaMemset(h->max_norm2, 0, 4));
+    return B2R_OK;
+}
+
+extern "C" int b2r_reserve(b2r_handle h, int64_t capacity_rows) {
+    B2R_REQUIRE(h, "b2r_reserve: NULL handle");
+    B2R_REQUIRE(capacity_rows < (1ll << 32) - 64, "b2r_reserve: capacity out of range");
+    std::lock_guard<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    return grow(h, capacity_rows, 0);
+}
+
+extern "C" int b2r_set_row_base(b2r_handle h, int64_t row_base) {
+    B2R_REQUIRE(h, "b2r_set_row_base: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    h->row_base = row_base;
+    return B2R_OK;
+}
+
+extern "C" int b2r_set_path(b2r_handle h, int path) {
+    B2R_REQUIRE(h, "b2r_set_path: NULL handle");
+    B2R_REQUIRE(path >= 0 && path <= 3, "b2r_set_path: path must be 0..3");
+    std::lock_guard<std::mutex> g(h->mu);
+    h->path = path;
+    return B2R_OK;
+}
+
+extern "C" int64_t b2r_launch_count(b2r_handle h) { return h ? h->n_launches : 0; }
+extern "C" int64_t b2r_count(b2r_handle h) { return h ? h->live : -1; }
+
+extern "C" int b2r_get_stats(b2r_handle h, b2r_stats *out) {
+    B2R_REQUIRE(h && out, "b2r_get_stats: NULL argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    unsigned long long c[2] = {0, 0};
+    B2R_CUDA(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    std::memset(out, 0, sizeof(*out));
+    out->dim = h->dim; out->dim_padded = h->dp; out->space = h->space; out->flags = h->flags;
+    out->rows = h->rows; out->live = h->live; out->capacity = h->capacity;
+    out->bytes_device = (int64_t)(row_bytes_total(h) * (size_t)h->capacity);
+    out->n_queries = h->n_queries; out->n_exact_fallbacks = (int64_t)c[1];
+    out->sm_count = h->sm_count; out->device = h->device;
+    return B2R_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// ingest / tombstone / gather
+// ---------------------------------------------------------------------------------
+extern "C" int b2r_ingest_f32(b2r_handle h, const float *x, int64_t n, const uint8_t *type_code,
+                              int64_t *first_row_out, void *stream) {
+    B2R_REQUIRE(h, "b2r_ingest_f32: NULL handle");
+    B2R_REQUIRE(n >= 0, "b2r_ingest_f32: negative row count");
+    B2R_REQUIRE(n == 0 || x, "b2r_ingest_f32: x is NULL");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (first_row_out) *first_row_out = h->rows;
+    if (n == 0) return B2R_OK;
+    B2R_REQUIRE(h->rows + n < (1ll << 32) - 64, "b2r_ingest_f32: shard row limit (2^32) exceeded");
+    B2R_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->rows + n > h->capacity) {
+        int rc = grow(h, std::max(h->rows + n, h->capacity * 2), s);
+        if (rc != B2R_OK) return rc;
+    }
+    const float *xd = x;
+    if (!is_device_ptr(x)) {
+        int rc = ensure(h->x_stage, (size_t)n * h->dim * 4);
+        if (rc != B2R_OK) return rc;
+        B2R_CUDA(cudaMemcpyAsync(h->x_stage.p, x, (size_t)n * h->dim * 4, cudaMemcpyHostToDevice, s));
+        xd = (const float *)h->x_stage.p;
+    }
+    const uint8_t *td = type_code;
+    if (type_code && !is_device_ptr(type_code)) {
+        for (int64_t i = 0; i < n; ++i) B2R_REQUIRE(type_code[i] < B2R_TYPE_DEAD, "b2r_ingest_f32: type_code must be 0..62");
+        int rc = ensure(h->t_stage, (size_t)n);
+        if (rc != B2R_OK) return rc;
+        B2R_CUDA(cudaMemcpyAsync(h->t_stage.p, type_code, (size_t)n, cudaMemcpyHostToDevice, s));
+        td = (const uint8_t *)h->t_stage.p;
+    }
+    IngestParams p;
+    p.x = xd; p.n = n; p.d = h->dim; p.dp = h->dp; p.space = h->space;
+    p.corpus = h->corpus + (size_t)h->rows * (h->dp / 8);
+    p.master = h->master ? h->master + (size_t)h->rows * h->dp : nullptr;
+    p.bias = h->bias ? h->bias + h->rows : nullptr;
+    p.type_out = h->type_code + h->rows;
+    p.type_in = td;
+    p.max_norm2 = h->max_norm2;
+    const int wpb = INGEST_THREADS / 32;
+    int grid = (int)std::min<int64_t>((n + wpb - 1) / wpb, (int64_t)h->sm_count * 16);
+    const bool vec = (h->dim % 8 == 0) && (((uintptr_t)xd & 15) == 0);
+    if (vec) ingest_kernel<true><<<grid, INGEST_THREADS, 0, s>>>(p);
+    else ingest_kernel<false><<<grid, INGEST_THREADS, 0, s>>>(p);
+    B2R_CUDA(cudaGetLastError());
+    h->n_launches++;
+    if (xd != x || td != type_code) B2R_CUDA(cudaStreamSynchronize(s));   // staging buffers are reused
+    h->rows += n; h->live += n;
+    return B2R_OK;
+}
+
+extern "C" int b2r_tombstone(b2r_handle h, const int64_t *rows, int64_t n, void *stream) {
+    B2R_REQUIRE(h, "b2r_tombstone: NULL handle");
+    B2R_REQUIRE(n >= 0 && (n == 0 || rows), "b2r_tombstone: bad arguments");
+    if (n == 0) return B2R_OK;
+    std::lock_guard<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int64_t i = 0; i < n; ++i)
+        B2R_REQUIRE(rows[i] >= 0 && rows[i] < h->rows, "b2r_tombstone: row out of range");
+    int rc = ensure(h->rows_stage, (size_t)n * 8);
+    if (rc != B2R_OK) return rc;
+    unsigned long long before = 0, after = 0;
+    B2R_CUDA(cudaMemcpyAsync(&before, h->counters, 8, cudaMemcpyDeviceToHost, s));
+    B2R_CUDA(cudaMemcpyAsync(h->rows_stage.p, rows, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    tombstone_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->type_code, (const long long *)h->rows_stage.p, n,
+                                                                 h->rows, h->counters);
+    B2R_CUDA(cudaGetLastError());
+    h->n_launches++;
+    B2R_CUDA(cudaMemcpyAsync(&after, h->counters, 8, cudaMemcpyDeviceToHost, s));
+    B2R_CUDA(cudaStreamSynchronize(s));
+    h->live -= (int64_t)(after - before);
+    return B2R_OK;
+}
+
+extern "C" int b2r_get_rows_f32(b2r_handle h, const int64_t *rows, int64_t n, float *out, void *stream) {
+    B2R_REQUIRE(h, "b2r_get_rows_f32: NULL handle");
+    B2R_REQUIRE(n >= 0 && (n == 0 || (rows && out)), "b2r_get_rows_f32: bad arguments");
+    if (n == 0) return B2R_OK;
+    std::lock_guard<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int64_t i = 0; i < n; ++i)
+        B2R_REQUIRE(rows[i] >= 0 && rows[i] < h->rows, "b2r_get_rows_f32: row out of range");
+    int rc = ensure(h->rows_stage, (size_t)n * 8);
+    if (rc != B2R_OK) return rc;
+    B2R_CUDA(cudaMemcpyAsync(h->rows_stage.p, rows, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    const bool dev_out = is_device_ptr(out);
+    float *od = out;
+    if (!dev_out) {
+        rc = ensure(h->gather_out, (size_t)n * h->dim * 4);
+        if (rc != B2R_OK) return rc;
+        od = (float *)h->gather_out.p;
+    }
+    gather_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(h->master, h->corpus, h->dim, h->dp,
+                                                               (const long long *)h->rows_stage.p, n, h->rows, od);
+    B2R_CUDA(cudaGetLastError());
+    h->n_launches++;
+    if (!dev_out) B2R_CUDA(cudaMemcpyAsync(out, od, (size_t)n * h->dim * 4, cudaMemcpyDeviceToHost, s));
+    B2R_CUDA(cudaStreamSynchronize(s));
+    return B2R_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// query
+// ---------------------------------------------------------------------------------
+namespace {
+
+struct QueryPlan {
+    int path;       // 1 scan, 3 exact
+    int epl;        // scored-list EPL (scan) -- exact path uses epl_exact(k)
+};
+
+int launch_scan_batch(b2r_index *h, int nq, int epl, const ScanParams &base, cudaStream_t s) {
+    int q = 0;
+    while (q < nq) {
+        int grp = (nq - q >= 4 && epl <= 2) ? 4 : (nq - q >= 2 && epl <= 2) ? 2 : 1;
+        int max_grid = scan_max_grid(h->dp, grp, epl, h->sm_count);
+        if (max_grid <= 0) { set_error("b2r_query: scan kernel cannot be resident (occupancy 0)"); return B2R_ECUDA; }
+        const int tile = scan_tile_rows(h->dp);
+        int64_t tiles = (h->rows + tile - 1) / tile;
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, max_grid));
+        int rc = ensure(h->scan_lists, sizeof(KeyS) * (size_t)max_grid * 4 * 32 * epl);
+        if (rc != B2R_OK) return rc;
+        ScanParams p = base;
+        p.q0 = q;
+        p.cta_lists = (KeyS *)h->scan_lists.p;
+        B2R_CUDA(scan_launch(h->dp, grp, epl, p, grid, s));
+        h->n_launches++;
+        q += grp;
+    }
+    return B2R_OK;
+}
+
+int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const FinalizeParams &fin,
+                       const b2r_filter &f, const uint32_t *allow_dev, cudaStream_t s) {
+    const int epl = epl_exact(k);
+    int max_grid = exact_max_grid(epl, h->dp, h->sm_count);
+    if (max_grid <= 0) { set_error("b2r_query: exact kernel cannot be resident"); return B2R_ECUDA; }
+    int64_t warps_needed = std::max<int64_t>(1, (h->rows + 3) / 4);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps_needed + EXACT_WARPS - 1) / EXACT_WARPS, max_grid));
+    int rc = ensure(h->exact_lists, sizeof(KeyD) * (size_t)EXACT_MAX_BATCH * max_grid * 32 * epl);
+    if (rc != B2R_OK) return rc;
+    for (int q0 = 0; q0 < nq; q0 += EXACT_MAX_BATCH) {
+        ExactParams p;
+        p.type_code = h->type_code; p.allow_bits = allow_dev; p.type_mask = f.type_mask;
+        p.n = (unsigned)h->rows; p.q0 = q0; p.nq = std::min(EXACT_MAX_BATCH, nq - q0); p.force_all = force_all;
+        p.cta_lists = (KeyD *)h->exact_lists.p; p.tickets = h->tickets + 1;
+        p.n_fallbacks = (long long *)(h->counters + 1);
+        p.fin = fin;
+        B2R_CUDA(exact_launch(epl, p, grid, s));
+        h->n_launches++;
+    }
+    return B2R_OK;
+}
+
+}  // namespace
+
+extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
+                            int64_t *out_rows, float *out_dist, double *out_dist64, int32_t *out_count,
+                            void *stream) {
+    B2R_REQUIRE(h, "b2r_query: NULL handle");
+    B2R_REQUIRE(nq >= 1 && q, "b2r_query: need at least one query");
+    B2R_REQUIRE(k >= 1, "b2r_query: n_results must be a positive integer");
+    B2R_REQUIRE(out_rows && out_dist && out_count, "b2r_query: NULL output");
+    if (epl_exact(k) == 0) { set_error("b2r_query: k > 256 is not supported"); return B2R_EUNSUPPORTED; }
+    std::lock_guard<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool dev_out = is_device_ptr(out_rows);
+    B2R_REQUIRE(dev_out == is_device_ptr(out_dist) && dev_out == is_device_ptr(out_count) &&
+                    (!out_dist64 || dev_out == is_device_ptr(out_dist64)),
+                "b2r_query: outputs must all be host or all be device pointers");
+    b2r_filter f; f.type_mask = ~0ull; f.allow_bits = nullptr;
+    if (filter) f = *filter;
+    f.type_mask &= ~(1ull << B2R_TYPE_DEAD);
+
+    int rc;
+    // ---- stage inputs ----
+    const float *q_raw = q;
+    if (!is_device_ptr(q)) {
+        if ((rc = ensure(h->q_raw, (size_t)nq * h->dim * 4)) != B2R_OK) return rc;
+        B2R_CUDA(cudaMemcpyAsync(h->q_raw.p, q, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, s));
+        q_raw = (const float *)h->q_raw.p;
+    }
+    const uint32_t *allow_dev = f.allow_bits;
+    if (f.allow_bits && !is_device_ptr(f.allow_bits)) {
+        size_t words = (size_t)((h->rows + 31) / 32);
+        if ((rc = ensure(h->allow, std::max<size_t>(words, 1) * 4)) != B2R_OK) return rc;
+        B2R_CUDA(cudaMemcpyAsync(h->allow.p, f.allow_bits, words * 4, cudaMemcpyHostToDevice, s));
+        allow_dev = (const uint32_t *)h->allow.p;
+    }
+    if ((rc = ensure(h->q_prep, (size_t)nq * h->dp * 4)) != B2R_OK) return rc;
+    if ((rc = ensure(h->need_exact, (size_t)nq * 4)) != B2R_OK) return rc;
+    long long *o_rows = (long long *)out_rows; float *o_dist = out_dist; double *o_dist64 = out_dist64; int *o_count = out_count;
+    if (!dev_out) {
+        if ((rc = ensure(h->o_rows, (size_t)nq * k * 8)) != B2R_OK) return rc;
+        if ((rc = ensure(h->o_dist, (size_t)nq * k * 4)) != B2R_OK) return rc;
+        if ((rc = ensure(h->o_count, (size_t)nq * 4)) != B2R_OK) return rc;
+        o_rows = (long long *)h->o_rows.p; o_dist = (float *)h->o_dist.p; o_count = (int *)h->o_count.p;
+        if (out_dist64) {
+            if ((rc = ensure(h->o_dist64, (size_t)nq * k * 8)) != B2R_OK) return rc;
+            o_dist64 = (double *)h->o_dist64.p;
+        }
+    }
+
+    // ---- prepare queries (cosine: hnswlib normalisation; zero-pad to dp) ----
+    {
+        IngestParams p;
+        p.x = q_raw; p.n = nq; p.d = h->dim; p.dp = h->dp; p.space = h->space;
+        p.corpus = nullptr; p.master = (float *)h->q_prep.p; p.bias = nullptr;
+        p.type_out = nullptr; p.type_in = nullptr; p.max_norm2 = nullptr;
+        const int wpb = INGEST_THREADS / 32;
+        int grid = std::min((nq + wpb - 1) / wpb, h->sm_count * 8);
+        const bool vec = (h->dim % 8 == 0) && (((uintptr_t)q_raw & 15) == 0);
+        if (vec) ingest_kernel<true><<<grid, INGEST_THREADS, 0, s>>>(p);
+        else ingest_kernel<false><<<grid, INGEST_THREADS, 0, s>>>(p);
+        B2R_CUDA(cudaGetLastError());
+        h->n_launches++;
+    }
+
+    FinalizeParams fin;
+    fin.master = h->master; fin.corpus = h->corpus; fin.q = (const float *)h->q_prep.p;
+    fin.max_norm2 = h->max_norm2; fin.dp = h->dp; fin.space = h->space; fin.k = k;
+    fin.row_base = h->row_base; fin.out_rows = o_rows; fin.out_dist = o_dist; fin.out_dist64 = o_dist64;
+    fin.out_count = o_count; fin.need_exact = (int *)h->need_exact.p;
+    // scan: fp32 query x bf16 corpus, fp32 accumulate.  bf16 unit roundoff 2^-8 only if
+    // the exact answer is defined on the fp32 master; fp32 accumulation adds (dp+2)*2^-24.
+    fin.eps_rel = (h->master ? 0.00390625f : 0.f) + (float)(h->dp + 8) * 5.9604645e-8f;
+    fin.eps_rel *= 1.01f;
+
+    // ---- choose the scoring path ----
+    int path = h->path;
+    const int epl_s = epl_scored(k);
+    if (path == 0) path = (scan_supported(h->dp) && epl_s != 0) ? 1 : 3;
+    if (path == 2) path = 1;   // tcgen05 path not built into this library version
+    if (path == 1 && (!scan_supported(h->dp) || epl_s == 0)) path = 3;
+
+    if (h->rows == 0) {
+        // empty collection: Chroma returns empty lists; nothing to launch but the padding
+        path = 3;
+    }
+    if (path == 1) {
+        ScanParams sp;
+        sp.corpus = h->corpus; sp.bias = h->bias; sp.type_code = h->type_code; sp.allow_bits = allow_dev;
+        sp.type_mask = f.type_mask; sp.n = (unsigned)h->rows; sp.q0 = 0; sp.cta_lists = nullptr;
+        sp.ticket = h->tickets; sp.fin = fin;
+        if ((rc = launch_scan_batch(h, nq, epl_s, sp, s)) != B2R_OK) return rc;
+        if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
+    } else {
+        if ((rc = launch_exact_batch(h, nq, k, 1, fin, f, allow_dev, s)) != B2R_OK) return rc;
+    }
+    h->n_queries += nq;
+
+    if (!dev_out) {
+        B2R_CUDA(cudaMemcpyAsync(out_rows, o_rows, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
+        B2R_CUDA(cudaMemcpyAsync(out_dist, o_dist, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+        B2R_CUDA(cudaMemcpyAsync(out_count, o_count, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+        if (out_dist64) B2R_CUDA(cudaMemcpyAsync(out_dist64, o_dist64, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
+        B2R_CUDA(cudaStreamSynchronize(s));
+    } else if (q_raw != q || (f.allow_bits && allow_dev != f.allow_bits)) {
+        B2R_CUDA(cudaStreamSynchronize(s));   // host inputs were staged through reusable buffers
+    }
+    return B2R_OK;
+}
+
+extern "C" int b2r_query(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
+                         int64_t *out_rows, float *out_dist, int32_t *out_count, void *stream) {
+    return b2r_query_ex(h, q, nq, k, filter, out_rows, out_dist, nullptr, out_count, stream);
+}
+
+// ---------------------------------------------------------------------------------
+// cross-shard merge (K4)
+// ---------------------------------------------------------------------------------
+namespace {
+constexpr int MERGE_THREADS = 256;
+// one CTA per query: rank every gathered candidate by counting (<= nshards*k <= 2048)
+__global__ void __launch_bounds__(MERGE_THREADS)
+merge_shards_kernel(const long long *in_rows, const double *in_dist, const int *in_count, int nshards, int nq,
+                    int k, long long *out_rows, float *out_dist, int *out_count) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int qi = blockIdx.x;
+    const int total = nshards * k;
+    double *sd = reinterpret_cast<double *>(sm);
+    long long *sr = reinterpret_cast<long long *>(sd + total);
+    __shared__ int s_valid;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    int my_valid = 0;
+    for (int c = threadIdx.x; c < total; c += MERGE_THREADS) {
+        int sh = c / k, i = c % k;
+        bool ok = i < in_count[(size_t)sh * nq + qi];
+        size_t src = ((size_t)sh * nq + qi) * k + i;
+        sd[c] = ok ? in_dist[src] : __longlong_as_double(0x7ff0000000000000ll);
+        sr[c] = ok ? in_rows[src] : -1;
+        my_valid += ok ? 1 : 0;
+    }
+    atomicAdd(&s_valid, my_valid);
+    __syncthreads();
+    const int cnt = min(s_valid, k);
+    for (int c = threadIdx.x; c < total; c += MERGE_THREADS) {
+        const long long r = sr[c];
+        if (r < 0) continue;
+        const double d = sd[c];
+        int rank = 0;
+        for (int j = 0; j < total; ++j) {
+            const long long rj = sr[j];
+            const double dj = sd[j];
+            rank += (rj >= 0 && (dj < d || (dj == d && rj < r))) ? 1 : 0;
+        }
+        if (rank < k) {
+            out_rows[(size_t)qi * k + rank] = r;
+            out_dist[(size_t)qi * k + rank] = (float)d;
+        }
+    }
+    for (int t = cnt + threadIdx.x; t < k; t += MERGE_THREADS) {
+        out_rows[(size_t)qi * k + t] = -1;
+        out_dist[(size_t)qi * k + t] = __int_as_float(0x7f800000);
+    }
+    if (threadIdx.x == 0) out_count[qi] = cnt;
+}
+}  // namespace
+
+extern "C" int b2r_merge_shards(const int64_t *in_rows, const double *in_dist64, const int32_t *in_count,
+                                int nshards, int nq, int k, int64_t *out_rows, float *out_dist,
+                                int32_t *out_count, int device, void *stream) {
+    B2R_REQUIRE(in_rows && in_dist64 && in_count && out_rows && out_dist && out_count, "b2r_merge_shards: NULL argument");
+    B2R_REQUIRE(nshards >= 1 && nq >= 1 && k >= 1, "b2r_merge_shards: bad sizes");
+    B2R_REQUIRE((size_t)nshards * k <= 8192, "b2r_merge_shards: nshards*k must be <= 8192");
+    B2R_CUDA(cudaSetDevice(device));
+    size_t smem = (size_t)nshards * k * 16;
+    B2R_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_shards_kernel<<<nq, MERGE_THREADS, smem, (cudaStream_t)stream>>>(
+        (const long long *)in_rows, in_dist64, in_count, nshards, nq, k, (long long *)out_rows, out_dist, out_count);
+    B2R_CUDA(cudaGetLastError());
+    return B2R_OK;
+}

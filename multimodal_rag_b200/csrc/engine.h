@@ -1,0 +1,71 @@
+// Host-side engine state behind the C ABI (include/b2r.h) and the launcher interfaces
+// each kernel translation unit exports.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/b2r.h"
+#include "common.cuh"
+#include "finalize.cuh"
+#include "scan.cuh"
+#include "exact.cuh"
+
+namespace b2r {
+
+void set_error(const std::string &msg);
+
+#define B2R_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            b2r::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+            return _e == cudaErrorMemoryAllocation ? B2R_ENOMEM : B2R_ECUDA;                \
+        }                                                                                   \
+    } while (0)
+
+// ---- launchers implemented in the kernel TUs ----
+// returns false when no kernel is built for (dp, nq_group, epl)
+bool scan_supported(int dp);
+// max CTAs that can be co-resident for this instantiation (0 if unsupported)
+int scan_max_grid(int dp, int nq_group, int epl, int sm_count);
+cudaError_t scan_launch(int dp, int nq_group, int epl, const ScanParams &p, int grid, cudaStream_t s);
+int scan_tile_rows(int dp);
+
+int exact_max_grid(int epl, int dp, int sm_count);
+cudaError_t exact_launch(int epl, const ExactParams &p, int grid, cudaStream_t s);
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace b2r
+
+struct b2r_index {
+    int dim = 0, dp = 0, space = 0, device = 0;
+    uint32_t flags = 0;
+    int64_t rows = 0, live = 0, capacity = 0;
+    int64_t row_base = 0;
+    int sm_count = 0;
+    int path = 0;
+    int64_t n_queries = 0, n_launches = 0;
+
+    // corpus (device)
+    uint4 *corpus = nullptr;        // bf16 [capacity, dp]
+    float *master = nullptr;        // fp32 [capacity, dp] unless B2R_FLAG_NO_F32_MASTER
+    float *bias = nullptr;          // [capacity], l2 only
+    uint8_t *type_code = nullptr;   // [capacity]
+    float *max_norm2 = nullptr;     // scalar
+    unsigned long long *counters = nullptr;   // [0] = rows killed by tombstone, [1] = exact fallbacks
+
+    // scratch (device), grown on demand
+    b2r::DevBuf x_stage, t_stage, q_raw, q_prep, allow, rows_stage, gather_out;
+    b2r::DevBuf o_rows, o_dist, o_dist64, o_count, need_exact;
+    b2r::DevBuf scan_lists, exact_lists;
+    unsigned *tickets = nullptr;    // [1 + EXACT_MAX_BATCH]
+
+    std::mutex mu;
+};

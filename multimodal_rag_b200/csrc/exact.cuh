@@ -1,0 +1,104 @@
+// K5: exact fp64 scan.  Reads the stored fp32 rows (or the bf16 rows when the handle
+// keeps no fp32 master), accumulates every distance in fp64 and selects on
+// (distance, row) directly, so its answer needs no certificate.  It is the always-correct
+// fallback for queries whose bf16 candidate certificate failed (need_exact[q] != 0), and
+// the forced path for tests (mode 1 = every query).  One query at a time, whole grid.
+#pragma once
+#include "common.cuh"
+#include "finalize.cuh"
+
+namespace b2r {
+
+constexpr int EXACT_THREADS = FIN_THREADS;
+constexpr int EXACT_WARPS = EXACT_THREADS / 32;
+constexpr int EXACT_MAX_BATCH = 64;
+
+struct ExactParams {
+    const uint8_t *type_code;
+    const uint32_t *allow_bits;
+    unsigned long long type_mask;
+    unsigned n;
+    int q0, nq;                   // queries [q0, q0+nq) of the batch; nq <= EXACT_MAX_BATCH
+    int force_all;                // 1: ignore need_exact and redo every query
+    KeyD *cta_lists;              // [EXACT_MAX_BATCH][gridDim.x][KP]: one slot per query, never reused in a launch
+    unsigned *tickets;            // [EXACT_MAX_BATCH]
+    long long *n_fallbacks;       // device counter (may be nullptr)
+    FinalizeParams fin;
+};
+
+template <int EPL>
+__global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactParams p) {
+    constexpr int KP = 32 * EPL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dp = p.fin.dp;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KeyD *sm_keys = reinterpret_cast<KeyD *>(smem_raw);                 // [EXACT_WARPS][KP]
+    KeyD *sm_misc = sm_keys + EXACT_WARPS * KP;                         // [4]
+    float *sm_q = reinterpret_cast<float *>(sm_misc + 4);              // [dp]
+    __shared__ unsigned s_ticket;
+
+    for (int qs = 0; qs < p.nq; ++qs) {
+        const int qi = p.q0 + qs;
+        KeyD *my_lists = p.cta_lists + (size_t)qs * gridDim.x * KP;
+        if (!p.force_all && __ldcg(&p.fin.need_exact[qi]) == 0) continue;   // CTA-uniform
+        __syncthreads();
+        for (int i = threadIdx.x; i < dp; i += EXACT_THREADS) sm_q[i] = p.fin.q[(size_t)qi * dp + i];
+        __syncthreads();
+
+        WarpList<KeyD, EPL> wl; wl.init();
+        const unsigned gw = blockIdx.x * EXACT_WARPS + warp, nw = gridDim.x * EXACT_WARPS;
+        for (unsigned row = gw; row < p.n; row += nw) {
+            if (!row_passes(row, p.type_code, p.type_mask, p.allow_bits)) continue;   // warp-uniform
+            double d = exact_distance_warp(p.fin, sm_q, row, lane);
+            wl.offer(KeyD::make(d, row), lane);
+        }
+        wl.store(sm_keys + warp * KP, lane);
+        __syncthreads();
+        if (warp == 0) {
+            for (int w = 1; w < EXACT_WARPS; ++w) wl.merge_sorted(sm_keys + w * KP, KP, lane);
+            wl.store(my_lists + (size_t)blockIdx.x * KP, lane);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[qs], 1u);
+        __syncthreads();
+        if (s_ticket == gridDim.x - 1) {
+            // ---- last CTA for this query: fold all CTA lists, emit ----
+            __threadfence();
+            WarpList<KeyD, EPL> m; m.init();
+            for (unsigned li = warp; li < gridDim.x; li += EXACT_WARPS) {
+                const KeyD *src = my_lists + (size_t)li * KP;
+                for (int i = 0; i < KP; ++i) {
+                    KeyD kk;
+                    kk.d = __ldcg(&src[i].d); kk.row = __ldcg(&src[i].row);
+                    if (!kk.valid() || !m.accepts(kk)) break;
+                    m.insert(kk, lane);
+                }
+            }
+            m.store(sm_keys + warp * KP, lane);
+            __syncthreads();
+            if (warp == 0) {
+                for (int w = 1; w < EXACT_WARPS; ++w) m.merge_sorted(sm_keys + w * KP, KP, lane);
+                m.store(sm_keys, lane);
+            }
+            if (threadIdx.x == 0) sm_misc[0] = KeyD::worst();
+            __syncthreads();
+            int nvalid = 0;
+            for (int i = 0; i < KP; ++i) nvalid += sm_keys[i].valid() ? 1 : 0;
+            emit_sorted(p.fin, qi, sm_keys, nvalid, &sm_misc[0]);
+            if (threadIdx.x == 0) {
+                p.tickets[qs] = 0u;
+                if (!p.force_all && p.n_fallbacks) atomicAdd((unsigned long long *)p.n_fallbacks, 1ull);
+                p.fin.need_exact[qi] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+inline size_t exact_smem_bytes(int EPL, int dp) {
+    const int KP = 32 * EPL;
+    return sizeof(KeyD) * (EXACT_WARPS * KP + 4) + sizeof(float) * dp;
+}
+
+}  // namespace b2r

@@ -1,0 +1,172 @@
+// Last-CTA epilogue shared by the scoring kernels: merge the per-CTA candidate lists,
+// re-rank the KP survivors exactly (fp64 accumulate over the stored fp32 rows), prove
+// that no row outside the candidate set can belong to the top-k (certificate), and
+// write Chroma-ordered results.  Runs in ONE CTA of FIN_THREADS threads.
+#pragma once
+#include "common.cuh"
+
+namespace b2r {
+
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_WARPS = FIN_THREADS / 32;
+
+struct FinalizeParams {
+    const float *master;        // [rows, dp] fp32 stored rows, or nullptr (bf16-only corpus)
+    const uint4 *corpus;        // [rows, dp] bf16 stored rows
+    const float *q;             // [nq, dp] fp32 prepared queries (normalised for cosine)
+    const float *max_norm2;     // device scalar: max |x|^2 over stored rows (bf16-rounded or fp32)
+    int dp, space, k;
+    long long row_base;         // added to local rows on output (shard offset)
+    long long *out_rows;        // [nq, k]
+    float *out_dist;            // [nq, k]
+    double *out_dist64;         // [nq, k] or nullptr
+    int *out_count;             // [nq]
+    int *need_exact;            // [nq]: 1 = certificate failed, exact scan must redo it
+    float eps_rel;              // |score_scan - score_exact| <= eps_rel * |q| * max|x| (+ small abs term)
+};
+
+// exact distance between prepared query and stored row, fp64 accumulation, whole warp
+__device__ __forceinline__ double exact_distance_warp(const FinalizeParams &p, const float *qv,
+                                                      unsigned row, int lane) {
+    double acc = 0.0;
+    const int dp = p.dp;
+    if (p.master) {
+        const float4 *xr = reinterpret_cast<const float4 *>(p.master + (size_t)row * dp);
+        const float4 *q4 = reinterpret_cast<const float4 *>(qv);
+        for (int c = lane; c < dp / 4; c += 32) {
+            float4 x = __ldcg(xr + c);
+            float4 q = q4[c];
+            if (p.space == 0) {
+                double a = (double)q.x - (double)x.x, b = (double)q.y - (double)x.y;
+                double cc = (double)q.z - (double)x.z, d = (double)q.w - (double)x.w;
+                acc = fma(a, a, acc); acc = fma(b, b, acc); acc = fma(cc, cc, acc); acc = fma(d, d, acc);
+            } else {
+                acc = fma((double)q.x, (double)x.x, acc); acc = fma((double)q.y, (double)x.y, acc);
+                acc = fma((double)q.z, (double)x.z, acc); acc = fma((double)q.w, (double)x.w, acc);
+            }
+        }
+    } else {
+        const uint4 *xr = p.corpus + (size_t)row * (dp / 8);
+        for (int c = lane; c < dp / 8; c += 32) {
+            uint4 w = __ldcg(xr + c);
+            const float *qq = qv + c * 8;
+            unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double x0 = (double)bf16lo(ww[i]), x1 = (double)bf16hi(ww[i]);
+                double q0 = (double)qq[2 * i], q1 = (double)qq[2 * i + 1];
+                if (p.space == 0) {
+                    double a = q0 - x0, b = q1 - x1;
+                    acc = fma(a, a, acc); acc = fma(b, b, acc);
+                } else {
+                    acc = fma(q0, x0, acc); acc = fma(q1, x1, acc);
+                }
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    return p.space == 0 ? acc : 1.0 - acc;
+}
+
+// Sort `n` exact keys held in smem (ex[0..n)) by rank computation and emit results.
+// Called by all FIN_THREADS threads.  Returns (via smem slot) nothing; writes outputs.
+__device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, const KeyD *ex, int n,
+                                            KeyD *kth_out /* smem, rank k-1 entry or worst */) {
+    const int k = p.k;
+    const int cnt = n < k ? n : k;
+    for (int t = threadIdx.x; t < n; t += FIN_THREADS) {
+        KeyD me = ex[t];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += KeyD::better(ex[j], me) ? 1 : 0;
+        if (rank < k) {
+            p.out_rows[(size_t)qi * k + rank] = p.row_base + (long long)me.row;
+            p.out_dist[(size_t)qi * k + rank] = (float)me.d;
+            if (p.out_dist64) p.out_dist64[(size_t)qi * k + rank] = me.d;
+        }
+        if (rank == k - 1) *kth_out = me;
+    }
+    for (int t = cnt + threadIdx.x; t < k; t += FIN_THREADS) {
+        p.out_rows[(size_t)qi * k + t] = -1;
+        p.out_dist[(size_t)qi * k + t] = __int_as_float(0x7f800000);
+        if (p.out_dist64) p.out_dist64[(size_t)qi * k + t] = __longlong_as_double(0x7ff0000000000000ll);
+    }
+    if (threadIdx.x == 0) p.out_count[qi] = cnt;
+}
+
+// Merge nlists rank-ordered KeyS lists of length KP (global memory, written by other
+// CTAs -> read with ld.cg), re-rank, certify, emit.  smem: sm_keys[FIN_WARPS*KP] KeyS,
+// sm_ex[KP] KeyD, sm_q[dp] float, sm_misc[4] KeyD.
+template <int EPL>
+__device__ void finalize_scored_query(const FinalizeParams &p, int qi, const KeyS *lists, int nlists,
+                                      size_t list_stride /* keys between consecutive lists */,
+                                      KeyS *sm_keys, KeyD *sm_ex, float *sm_q, KeyD *sm_misc) {
+    constexpr int KP = 32 * EPL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int i = threadIdx.x; i < p.dp; i += FIN_THREADS) sm_q[i] = p.q[(size_t)qi * p.dp + i];
+
+    // ---- stage 1: every warp folds its share of the lists ----
+    WarpList<KeyS, EPL> wl; wl.init();
+    for (int base = warp; base < nlists; base += FIN_WARPS * 32) {
+        int mine = base + lane * FIN_WARPS;                       // list whose head this lane probes
+        KeyS head = KeyS::worst();
+        if (mine < nlists) head.v = __ldcg(&lists[(size_t)mine * list_stride].v);
+        unsigned pending = __ballot_sync(FULL_MASK, head.valid() && wl.accepts(head));
+        while (pending) {
+            int src_lane = __ffs(pending) - 1;
+            pending &= pending - 1;
+            int li = base + src_lane * FIN_WARPS;
+            const KeyS *src = lists + (size_t)li * list_stride;
+            for (int i = 0; i < KP; ++i) {
+                KeyS kk; kk.v = __ldcg(&src[i].v);
+                if (!kk.valid() || !wl.accepts(kk)) break;
+                wl.insert(kk, lane);
+            }
+        }
+    }
+    wl.store(sm_keys + warp * KP, lane);
+    __syncthreads();
+    // ---- stage 2: warp 0 folds the other warps' lists ----
+    if (warp == 0) {
+        for (int w = 1; w < FIN_WARPS; ++w) wl.merge_sorted(sm_keys + w * KP, KP, lane);
+        wl.store(sm_keys, lane);
+    }
+    __syncthreads();
+    int nvalid = 0;
+    for (int i = 0; i < KP; ++i) nvalid += sm_keys[i].valid() ? 1 : 0;   // tiny, uniform
+
+    // ---- stage 3: exact re-rank, one warp per candidate ----
+    for (int c = warp; c < nvalid; c += FIN_WARPS) {
+        unsigned row = sm_keys[c].row();
+        double d = exact_distance_warp(p, sm_q, row, lane);
+        if (lane == 0) sm_ex[c] = KeyD::make(d, row);
+    }
+    if (threadIdx.x == 0) sm_misc[0] = KeyD::worst();
+    __syncthreads();
+    emit_sorted(p, qi, sm_ex, nvalid, &sm_misc[0]);
+    __syncthreads();
+
+    // ---- stage 4: certificate ----
+    if (threadIdx.x < 32) {
+        int flag = 0;
+        if (nvalid == KP) {   // otherwise every passing row of the shard is already a candidate
+            // every row outside the list scored <= T in the scan; its exact score is <= T + eps
+            float T = sm_keys[KP - 1].score();
+            double qn2 = 0.0;
+            for (int i = lane; i < p.dp; i += 32) qn2 = fma((double)sm_q[i], (double)sm_q[i], qn2);
+            qn2 = warp_sum(qn2);
+            double xn = sqrt((double)*p.max_norm2), qn = sqrt(qn2);
+            double eps = (double)p.eps_rel * qn * xn + 1e-6 * (0.5 * xn * xn + qn * xn) + 1e-30;
+            KeyD kth = sm_misc[0];
+            double s_k;
+            if (!kth.valid()) s_k = -1e300;                       // fewer than k results: cannot happen with nvalid==KP>=k
+            else if (p.space == 0) s_k = 0.5 * (qn2 - kth.d);
+            else s_k = 1.0 - kth.d;
+            flag = (s_k - eps > (double)T) ? 0 : 1;
+        }
+        if (lane == 0) p.need_exact[qi] = flag;
+    }
+    __syncthreads();
+}
+
+}  // namespace b2r

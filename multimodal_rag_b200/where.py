@@ -1,0 +1,201 @@
+"""Host-side metadata tables and Chroma `where` evaluation.
+
+Chroma 0.4.22 resolves `where` in its sqlite metadata segment into a set of allowed ids
+before the vector search (reference call sites: app/utils/embedder.py:543,599 `filter_dict`
+-> `collection.query(where=...)`, and :633 `collection.get(where={"doc_id": ...})`).  Here the
+metadata lives in dictionary-encoded columns (one int32 code per row per key) so a clause is
+a look-up table over the distinct values of a key, applied with one numpy gather; the
+result is either a type-code mask (the `{"type": ...}` fast path, evaluated inside the scan
+kernel from a 1-byte/row code) or a packed allow bitmap handed to the device.
+
+Grammar: {key: v} | {key: {"$eq|$ne|$gt|$gte|$lt|$lte": v}} | {key: {"$in|$nin": [...]}} |
+{"$and"|"$or": [clause, ...]}.  A missing key never matches; values only compare within a
+kind (str / number / bool).
+"""
+from __future__ import annotations
+
+import operator
+
+import numpy as np
+
+TYPE_KEY = "type"
+MAX_TYPE_CODES = 62          # device type codes 1..61 name values, 0 = no value, 62 = overflow
+TYPE_NONE, TYPE_OVERFLOW = 0, 62
+
+_CMP = {"$eq": operator.eq, "$ne": operator.ne, "$gt": operator.gt, "$gte": operator.ge,
+        "$lt": operator.lt, "$lte": operator.le}
+
+
+def _kind(v) -> int:
+    if isinstance(v, bool):
+        return 2
+    if isinstance(v, (int, float)):
+        return 1
+    if isinstance(v, str):
+        return 0
+    raise ValueError(f"metadata values must be str, int, float or bool, got {type(v).__name__}")
+
+
+class _Column:
+    """Dictionary-encoded column: codes[row] = index into values, -1 = key absent."""
+
+    def __init__(self, nrows: int):
+        self.codes = np.full(max(nrows, 16), -1, dtype=np.int32)
+        self.n = nrows
+        self.values: list = []
+        self.kinds: list[int] = []
+        self.index: dict = {}
+
+    def _grow(self, n):
+        if n > self.codes.shape[0]:
+            new = np.full(max(n, 2 * self.codes.shape[0]), -1, dtype=np.int32)
+            new[: self.n] = self.codes[: self.n]
+            self.codes = new
+
+    def set(self, row: int, v):
+        self._grow(row + 1)
+        self.n = max(self.n, row + 1)
+        key = (_kind(v), v)
+        c = self.index.get(key)
+        if c is None:
+            c = len(self.values)
+            self.index[key] = c
+            self.values.append(v)
+            self.kinds.append(key[0])
+        self.codes[row] = c
+
+    def lut_mask(self, nrows: int, pred) -> np.ndarray:
+        lut = np.zeros(len(self.values) + 1, dtype=bool)       # last slot = absent key
+        for c, (v, kd) in enumerate(zip(self.values, self.kinds)):
+            lut[c] = bool(pred(v, kd))
+        codes = self.codes[: self.n]
+        out = np.zeros(nrows, dtype=bool)
+        out[: self.n] = lut[codes]                               # -1 -> last slot (False)
+        return out
+
+
+class MetaTable:
+    """Per-collection metadata store (row-aligned with the device corpus)."""
+
+    def __init__(self):
+        self.nrows = 0
+        self.cols: dict[str, _Column] = {}
+        self.meta: list[dict | None] = []       # original dicts, returned verbatim by query/get
+        self.type_codes: dict[str, int] = {}    # value of the `type` key -> device code
+        self.type_overflow = False              # more distinct type values than device codes
+
+    def type_code_of(self, meta: dict | None) -> int:
+        if not meta or TYPE_KEY not in meta or not isinstance(meta[TYPE_KEY], str):
+            return TYPE_NONE
+        v = meta[TYPE_KEY]
+        c = self.type_codes.get(v)
+        if c is None:
+            if len(self.type_codes) + 1 < TYPE_OVERFLOW:
+                c = self.type_codes[v] = len(self.type_codes) + 1
+            else:
+                c, self.type_overflow = TYPE_OVERFLOW, True
+        return c
+
+    @staticmethod
+    def validate(meta):
+        if meta is None:
+            return
+        if not isinstance(meta, dict):
+            raise ValueError(f"Expected metadata to be a dict, got {type(meta).__name__}")
+        for k, v in meta.items():
+            if not isinstance(k, str):
+                raise ValueError("Expected metadata key to be a str")
+            _kind(v)
+
+    def append(self, meta: dict | None) -> int:
+        """Adds one row; returns its device type code."""
+        row = self.nrows
+        self.nrows += 1
+        self.meta.append(meta)
+        if meta:
+            for k, v in meta.items():
+                col = self.cols.get(k)
+                if col is None:
+                    col = self.cols[k] = _Column(0)
+                col.set(row, v)
+        return self.type_code_of(meta)
+
+    def clear(self):
+        self.__init__()
+
+    # ---- where ----------------------------------------------------------------
+    def mask(self, where: dict | None) -> np.ndarray | None:
+        """bool[nrows] of rows matching `where` (None = no restriction)."""
+        if not where:
+            return None
+        return self._eval(where)
+
+    def _eval(self, where) -> np.ndarray:
+        if not isinstance(where, dict) or len(where) != 1:
+            raise ValueError(f"Expected where to have exactly one operator, got {where}")
+        (key, cond), = where.items()
+        if key in ("$and", "$or"):
+            if not isinstance(cond, (list, tuple)) or len(cond) < 1:
+                raise ValueError(f"Expected where value for {key} to be a non-empty list")
+            parts = [self._eval(w) for w in cond]
+            out = parts[0].copy()
+            for p in parts[1:]:
+                out = (out & p) if key == "$and" else (out | p)
+            return out
+        if key.startswith("$"):
+            raise ValueError(f"Expected where operator to be one of $and, $or, got {key}")
+        if not isinstance(cond, dict):
+            cond = {"$eq": cond}
+        if len(cond) != 1:
+            raise ValueError(f"Expected operator expression to have exactly one operator, got {cond}")
+        (op, val), = cond.items()
+        col = self.cols.get(key)
+        if op in ("$in", "$nin"):
+            if not isinstance(val, (list, tuple)) or not val:
+                raise ValueError(f"Expected where value for {op} to be a non-empty list")
+            wanted = {(_kind(v), v) for v in val}
+            if col is None:
+                return np.zeros(self.nrows, dtype=bool)
+            hit = lambda v, kd: (kd, v) in wanted
+            pred = hit if op == "$in" else (lambda v, kd: not hit(v, kd))
+            return col.lut_mask(self.nrows, pred)
+        if op not in _CMP:
+            raise ValueError(f"Expected where operator to be one of {sorted(_CMP)} or $in/$nin, got {op}")
+        vk = _kind(val)
+        if op in ("$gt", "$gte", "$lt", "$lte") and vk != 1:
+            raise ValueError(f"Expected operand value to be an int or a float for operator {op}")
+        if col is None:
+            return np.zeros(self.nrows, dtype=bool)
+        fn = _CMP[op]
+        return col.lut_mask(self.nrows, lambda v, kd: kd == vk and fn(v, val))
+
+    def type_only_mask(self, where: dict | None) -> int | None:
+        """If `where` only constrains the `type` key by equality / $in on string values that all
+        have a device code, return the 64-bit type mask; else None (caller uses a bitmap)."""
+        if not where or len(where) != 1 or TYPE_KEY not in where:
+            return None
+        if self.type_overflow:
+            return None
+        cond = where[TYPE_KEY]
+        if not isinstance(cond, dict):
+            cond = {"$eq": cond}
+        if len(cond) != 1:
+            return None
+        (op, val), = cond.items()
+        vals = [val] if op == "$eq" else list(val) if op == "$in" and isinstance(val, (list, tuple)) else None
+        if vals is None or not all(isinstance(v, str) for v in vals):
+            return None
+        m = 0
+        for v in vals:
+            c = self.type_codes.get(v)
+            if c is not None:
+                m |= 1 << c
+        return m
+
+
+def pack_bits(mask: np.ndarray) -> np.ndarray:
+    """bool[n] -> uint32[ceil(n/32)], bit (r & 31) of word r >> 5 (include/b2r.h b2r_filter)."""
+    n = mask.shape[0]
+    padded = np.zeros(((n + 31) // 32) * 32, dtype=bool)
+    padded[:n] = mask
+    return np.packbits(padded, bitorder="little").view("<u4").copy()
