@@ -334,6 +334,7 @@ int launch_scan_batch(b2r_index *h, int nq, int epl, const ScanParams &base, cud
         ScanParams p = base;
         p.q0 = q;
         p.cta_lists = (KeyS *)h->scan_lists.p;
+        p.stage_keys = scan_stage_keys(epl, grid);
         B2R_CUDA(scan_launch(h->dp, grp, epl, p, grid, s));
         h->n_launches++;
         q += grp;

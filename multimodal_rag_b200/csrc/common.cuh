@@ -41,6 +41,11 @@ struct KeyS {
     __device__ __forceinline__ static KeyS shfl_up(const KeyS &a, int d) {
         KeyS k; k.v = __shfl_up_sync(FULL_MASK, a.v, d); return k;
     }
+    __device__ __forceinline__ static KeyS shfl_xor(const KeyS &a, int m) {
+        KeyS k; k.v = __shfl_xor_sync(FULL_MASK, a.v, m); return k;
+    }
+    // read a key another CTA wrote (L2, never L1)
+    __device__ __forceinline__ static KeyS load_cg(const KeyS *p) { KeyS k; k.v = __ldcg(&p->v); return k; }
 };
 
 // exact fp64 distance (smaller = better) + row; order (distance asc, row asc).
@@ -58,6 +63,12 @@ struct KeyD {
     }
     __device__ __forceinline__ static KeyD shfl_up(const KeyD &a, int dl) {
         KeyD k; k.d = __shfl_up_sync(FULL_MASK, a.d, dl); k.row = __shfl_up_sync(FULL_MASK, a.row, dl); return k;
+    }
+    __device__ __forceinline__ static KeyD shfl_xor(const KeyD &a, int m) {
+        KeyD k; k.d = __shfl_xor_sync(FULL_MASK, a.d, m); k.row = __shfl_xor_sync(FULL_MASK, a.row, m); return k;
+    }
+    __device__ __forceinline__ static KeyD load_cg(const KeyD *p) {
+        KeyD k; k.d = __ldcg(&p->d); k.row = __ldcg(&p->row); return k;
     }
 };
 
@@ -113,6 +124,45 @@ struct WarpList {
             if (!k.valid() || !accepts(k)) break;
             insert(k, lane);
         }
+    }
+    // Bitonic top-KP merge with a full rank-ordered list of KP keys (worst() padded).
+    // c[r] = best(a[r], b[KP-1-r]) is bitonic and holds the KP best of the union; log2(KP)
+    // compare-exchange stages re-sort it.  Cross-lane stages use shuffles, the rest registers.
+    template <bool CG>
+    __device__ __forceinline__ void merge_bitonic(const K *src, int lane) {
+        constexpr int KP = 32 * EPL;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const K *p = src + (KP - 1 - (lane * EPL + e));
+            K b = CG ? K::load_cg(p) : *p;
+            if (K::better(b, key[e])) key[e] = b;
+        }
+        resort_bitonic(lane);
+    }
+    __device__ __forceinline__ void resort_bitonic(int lane) {
+        constexpr int KP = 32 * EPL;
+#pragma unroll
+        for (int s = KP / 2; s >= 1; s >>= 1) {
+            if (s >= EPL) {
+                const int ls = s / EPL;
+                const bool keep_best = (lane & ls) == 0;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    K o = K::shfl_xor(key[e], ls);
+                    bool ob = K::better(o, key[e]);
+                    if (ob == keep_best) key[e] = o;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    if ((e & s) == 0) {
+                        K a = key[e], b = key[e + s];
+                        if (K::better(b, a)) { key[e] = b; key[e + s] = a; }
+                    }
+                }
+            }
+        }
+        thr = K::shfl(key[EPL - 1], 31);
     }
 };
 

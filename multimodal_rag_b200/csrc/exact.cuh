@@ -52,12 +52,9 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
             double d = exact_distance_warp(p.fin, sm_q, row, lane);
             wl.offer(KeyD::make(d, row), lane);
         }
-        wl.store(sm_keys + warp * KP, lane);
         __syncthreads();
-        if (warp == 0) {
-            for (int w = 1; w < EXACT_WARPS; ++w) wl.merge_sorted(sm_keys + w * KP, KP, lane);
-            wl.store(my_lists + (size_t)blockIdx.x * KP, lane);
-        }
+        cta_tree_merge<KeyD, EPL>(wl, sm_keys, warp, lane);
+        if (warp == 0) wl.store(my_lists + (size_t)blockIdx.x * KP, lane);
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[qs], 1u);
@@ -68,19 +65,11 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
             WarpList<KeyD, EPL> m; m.init();
             for (unsigned li = warp; li < gridDim.x; li += EXACT_WARPS) {
                 const KeyD *src = my_lists + (size_t)li * KP;
-                for (int i = 0; i < KP; ++i) {
-                    KeyD kk;
-                    kk.d = __ldcg(&src[i].d); kk.row = __ldcg(&src[i].row);
-                    if (!kk.valid() || !m.accepts(kk)) break;
-                    m.insert(kk, lane);
-                }
+                const KeyD head = KeyD::load_cg(src);
+                if (head.valid() && m.accepts(head)) m.template merge_bitonic<true>(src, lane);
             }
-            m.store(sm_keys + warp * KP, lane);
             __syncthreads();
-            if (warp == 0) {
-                for (int w = 1; w < EXACT_WARPS; ++w) m.merge_sorted(sm_keys + w * KP, KP, lane);
-                m.store(sm_keys, lane);
-            }
+            cta_tree_merge<KeyD, EPL>(m, sm_keys, warp, lane);
             if (threadIdx.x == 0) sm_misc[0] = KeyD::worst();
             __syncthreads();
             int nvalid = 0;

@@ -1,4 +1,7 @@
 // Instantiations + launch table for K5 (exact.cuh).
+#include <map>
+#include <tuple>
+
 #include "engine.h"
 
 namespace b2r {
@@ -16,12 +19,22 @@ exact_fn lookup(int epl) {
 }  // namespace
 
 int exact_max_grid(int epl, int dp, int sm_count) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    auto key = std::make_tuple(dev, epl, dp);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second * sm_count;
     exact_fn f = lookup(epl);
     if (!f) return 0;
     size_t smem = exact_smem_bytes(epl, dp);
-    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    // the attribute is per function (per epl), not per dp: raise it to the largest dp the ABI accepts
+    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem_bytes(epl, 8192)) != cudaSuccess) return 0;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, EXACT_THREADS, smem) != cudaSuccess) return 0;
+    cache[key] = per_sm;
     return per_sm * sm_count;
 }
 

@@ -93,45 +93,56 @@ __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, con
     if (threadIdx.x == 0) p.out_count[qi] = cnt;
 }
 
+// Tree-merge the per-warp lists of a CTA: after the call warp 0 holds the CTA's best KP and
+// has stored them rank-ordered at sm[0, KP).  sm must hold FIN_WARPS*KP keys.  All threads call.
+template <class K, int EPL>
+__device__ __forceinline__ void cta_tree_merge(WarpList<K, EPL> &wl, K *sm, int warp, int lane) {
+    constexpr int KP = 32 * EPL;
+#pragma unroll
+    for (int half = FIN_WARPS / 2; half >= 1; half >>= 1) {
+        if (warp >= half && warp < 2 * half) wl.store(sm + warp * KP, lane);
+        __syncthreads();
+        if (warp < half) wl.template merge_bitonic<false>(sm + (warp + half) * KP, lane);
+        __syncthreads();
+    }
+    if (warp == 0) wl.store(sm, lane);
+    __syncthreads();
+}
+
 // Merge nlists rank-ordered KeyS lists of length KP (global memory, written by other
-// CTAs -> read with ld.cg), re-rank, certify, emit.  smem: sm_keys[FIN_WARPS*KP] KeyS,
-// sm_ex[KP] KeyD, sm_q[dp] float, sm_misc[4] KeyD.
+// CTAs -> read with ld.cg), re-rank, certify, emit.  The lists are staged through shared
+// memory with coalesced loads (one DRAM/L2 latency per chunk instead of one per list).
+// smem: stage[stage_keys] KeyS (stage_keys a multiple of KP, >= FIN_WARPS*KP), sm_ex[KP] KeyD,
+// sm_q[dp] float, sm_misc[4] KeyD.
 template <int EPL>
 __device__ void finalize_scored_query(const FinalizeParams &p, int qi, const KeyS *lists, int nlists,
                                       size_t list_stride /* keys between consecutive lists */,
-                                      KeyS *sm_keys, KeyD *sm_ex, float *sm_q, KeyD *sm_misc) {
+                                      KeyS *stage, int stage_keys, KeyD *sm_ex, float *sm_q, KeyD *sm_misc) {
     constexpr int KP = 32 * EPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    KeyS *sm_keys = stage;
 
     for (int i = threadIdx.x; i < p.dp; i += FIN_THREADS) sm_q[i] = p.q[(size_t)qi * p.dp + i];
 
-    // ---- stage 1: every warp folds its share of the lists ----
+    // ---- stage 1: every warp folds its share of the lists, chunk by chunk ----
     WarpList<KeyS, EPL> wl; wl.init();
-    for (int base = warp; base < nlists; base += FIN_WARPS * 32) {
-        int mine = base + lane * FIN_WARPS;                       // list whose head this lane probes
-        KeyS head = KeyS::worst();
-        if (mine < nlists) head.v = __ldcg(&lists[(size_t)mine * list_stride].v);
-        unsigned pending = __ballot_sync(FULL_MASK, head.valid() && wl.accepts(head));
-        while (pending) {
-            int src_lane = __ffs(pending) - 1;
-            pending &= pending - 1;
-            int li = base + src_lane * FIN_WARPS;
-            const KeyS *src = lists + (size_t)li * list_stride;
-            for (int i = 0; i < KP; ++i) {
-                KeyS kk; kk.v = __ldcg(&src[i].v);
-                if (!kk.valid() || !wl.accepts(kk)) break;
-                wl.insert(kk, lane);
-            }
+    const int lists_per_chunk = stage_keys / KP;
+    for (int c0 = 0; c0 < nlists; c0 += lists_per_chunk) {
+        const int nl = min(lists_per_chunk, nlists - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nl * KP; i += FIN_THREADS) {
+            const int li = i / KP, r = i % KP;
+            stage[i] = KeyS::load_cg(lists + (size_t)(c0 + li) * list_stride + r);
+        }
+        __syncthreads();
+        for (int li = warp; li < nl; li += FIN_WARPS) {
+            const KeyS head = stage[li * KP];
+            if (head.valid() && wl.accepts(head)) wl.template merge_bitonic<false>(stage + li * KP, lane);
         }
     }
-    wl.store(sm_keys + warp * KP, lane);
     __syncthreads();
-    // ---- stage 2: warp 0 folds the other warps' lists ----
-    if (warp == 0) {
-        for (int w = 1; w < FIN_WARPS; ++w) wl.merge_sorted(sm_keys + w * KP, KP, lane);
-        wl.store(sm_keys, lane);
-    }
-    __syncthreads();
+    // ---- stage 2: fold the warps ----
+    cta_tree_merge<KeyS, EPL>(wl, stage, warp, lane);
     int nvalid = 0;
     for (int i = 0; i < KP; ++i) nvalid += sm_keys[i].valid() ? 1 : 0;   // tiny, uniform
 

@@ -27,6 +27,7 @@ struct ScanParams {
     int q0;                       // first query of this launch (index into fin.q / outputs)
     KeyS *cta_lists;              // [gridDim.x][NQ][KP]
     unsigned *ticket;
+    int stage_keys;               // KeyS slots of shared staging for the finalize (multiple of KP, >= 8*KP)
     FinalizeParams fin;
 };
 
@@ -115,18 +116,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_topk_kernel(const ScanParam
         }
     }
 
-    // ---- CTA merge: warp qi folds all warps' lists for query qi ----
-    KeyS *sm_keys = reinterpret_cast<KeyS *>(smem_raw);              // [SCAN_WARPS][KP] (reused per query)
+    // ---- CTA merge: tree-fold the warps' lists of each query, publish the CTA list ----
+    KeyS *stage = reinterpret_cast<KeyS *>(smem_raw);                // [stage_keys]
     __shared__ unsigned s_ticket;
+#pragma unroll
     for (int qi = 0; qi < NQ; ++qi) {
+        cta_tree_merge<KeyS, EPL>(wl[qi], stage, warp, lane);
+        if (warp == 0) wl[qi].store(p.cta_lists + ((size_t)blockIdx.x * NQ + qi) * KP, lane);
         __syncthreads();
-        wl[qi].store(sm_keys + warp * KP, lane);
-        __syncthreads();
-        if (warp == 0) {
-            WarpList<KeyS, EPL> m = wl[qi];
-            for (int w = 1; w < SCAN_WARPS; ++w) m.merge_sorted(sm_keys + w * KP, KP, lane);
-            m.store(p.cta_lists + ((size_t)blockIdx.x * NQ + qi) * KP, lane);
-        }
     }
     __threadfence();
     __syncthreads();
@@ -136,18 +133,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_topk_kernel(const ScanParam
 
     // ---- last CTA: finalize every query of this launch ----
     __threadfence();
-    KeyD *sm_ex = reinterpret_cast<KeyD *>(smem_raw + sizeof(KeyS) * FIN_WARPS * KP);
+    KeyD *sm_ex = reinterpret_cast<KeyD *>(smem_raw + sizeof(KeyS) * (size_t)p.stage_keys);
     KeyD *sm_misc = sm_ex + KP;
     float *sm_q = reinterpret_cast<float *>(sm_misc + 4);
     for (int qi = 0; qi < NQ; ++qi)
         finalize_scored_query<EPL>(p.fin, p.q0 + qi, p.cta_lists + (size_t)qi * KP, gridDim.x,
-                                   (size_t)NQ * KP, sm_keys, sm_ex, sm_q, sm_misc);
+                                   (size_t)NQ * KP, stage, p.stage_keys, sm_ex, sm_q, sm_misc);
     if (threadIdx.x == 0) *p.ticket = 0u;
 }
 
-inline size_t scan_smem_bytes(int EPL, int dp) {
+// shared staging for the finalize: all CTA lists of one query if they fit in 64 KB
+inline int scan_stage_keys(int EPL, int grid) {
     const int KP = 32 * EPL;
-    return sizeof(KeyS) * FIN_WARPS * KP + sizeof(KeyD) * (KP + 4) + sizeof(float) * dp;
+    long long want = (long long)grid * KP;
+    if (want < FIN_WARPS * KP) want = FIN_WARPS * KP;
+    if (want > 8192) want = 8192;
+    return (int)want;
+}
+inline size_t scan_smem_bytes(int EPL, int dp, int stage_keys) {
+    const int KP = 32 * EPL;
+    return sizeof(KeyS) * (size_t)stage_keys + sizeof(KeyD) * (KP + 4) + sizeof(float) * dp;
 }
 
 }  // namespace b2r

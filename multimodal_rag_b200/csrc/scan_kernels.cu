@@ -1,5 +1,8 @@
 // Instantiations + launch table for K2 (scan.cuh).  Split from the API translation unit
 // so the build can compile kernel families in parallel.
+#include <map>
+#include <tuple>
+
 #include "engine.h"
 
 namespace b2r {
@@ -75,19 +78,30 @@ scan_fn lookup(int dp, int nq, int epl) {
 bool scan_supported(int dp) { return shape_of(dp).lpr != 0; }
 
 int scan_max_grid(int dp, int nq, int epl, int sm_count) {
+    // sized for the largest staging area (8192 keys) so the grid never exceeds residency
+    // occupancy is a property of the instantiation: query the runtime once per (dp, nq, epl)
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int, int>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    auto key = std::make_tuple(dev, dp, nq, epl);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second * sm_count;
     scan_fn f = lookup(dp, nq, epl);
     if (!f) return 0;
-    size_t smem = scan_smem_bytes(epl, dp);
+    size_t smem = scan_smem_bytes(epl, dp, 8192);
     if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, SCAN_THREADS, smem) != cudaSuccess) return 0;
+    cache[key] = per_sm;
     return per_sm * sm_count;
 }
 
 cudaError_t scan_launch(int dp, int nq, int epl, const ScanParams &p, int grid, cudaStream_t s) {
     scan_fn f = lookup(dp, nq, epl);
     if (!f) return cudaErrorInvalidValue;
-    size_t smem = scan_smem_bytes(epl, dp);
+    size_t smem = scan_smem_bytes(epl, dp, p.stage_keys);
     f<<<grid, SCAN_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
