@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Headline benchmark: queries/sec at 1M x 384-d, top_k=5 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 256] [--impl reference]
+
+A *step* is one pass of the hot path over one batch of `--batch` synthetic unit-norm queries:
+prepare (normalise) -> score against the resident corpus -> select -> exact re-rank -> results.
+  value   device-resident inputs and outputs, CUDA events on the launching stream
+  e2e     the same through the C ABI with HOST buffers (pinned query batch in, ids / distances /
+          counts out), host<->device copies and the final stream sync inside the timed region
+  N > 1   one process per GPU (torchrun).  The 1M-row corpus is replicated and the query stream
+          is sharded (each rank answers its own batches, no data-path collective) -> weak
+          scaling of queries/sec; the row-sharded + NCCL all_gather + merge path (north_star's
+          100M layout) is timed beside it with a fixed 1M-row shard per GPU and reported under
+          "sharded".
+  --impl reference   the CPU arm: the oracle's C restatement of the reference's exhaustive
+          distance arithmetic (hnswlib L2Sqr / InnerProduct, fp32 accumulate) on all host cores.
+          The reference's real stack (chromadb 0.4.22 -> chroma-hnswlib 0.7.3) is not in this
+          image, so this is kind="port".
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ROWS, DIM, TOP_K = 1_000_000, 384, 5
+METRIC, UNIT = "queries/sec @1Mx384-d top_k=5", "queries/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"],
+                "bf16_tflops_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------
+def cpu_corpus(n, d, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    X = np.empty((n, d), dtype=np.float32)
+    step = 1 << 17
+    for s in range(0, n, step):
+        X[s:s + step] = rng.standard_normal((min(step, n - s), d), dtype=np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    return X
+
+
+def cpu_port_qps(X, Q, k, steps, warmup=0):
+    """Oracle C port, fp32 accumulate, all OpenMP threads.  Returns (qps, seconds/step, threads)."""
+    from oracle import c_oracle
+    for _ in range(warmup):
+        c_oracle.topk(X, Q, k, "cosine", acc64=False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c_oracle.topk(X, Q, k, "cosine", acc64=False)
+    dt = (time.perf_counter() - t0) / steps
+    return Q.shape[0] / dt, dt, c_oracle.threads()
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import c_oracle
+    c_oracle.build()
+    sample_q = min(args.batch, 32)          # bounded sample of the batch so K+W steps end in minutes
+    X = cpu_corpus(N_ROWS, DIM, 0xC0FFEE)
+    Q = cpu_corpus(sample_q, DIM, 0xBEEF)
+    qps, dt, threads = cpu_port_qps(X, Q, TOP_K, max(1, args.steps), max(0, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{N_ROWS}x{DIM} fp32 corpus, batch {args.batch}, top_k={TOP_K}, cosine",
+                   "rows": N_ROWS, "dim": DIM, "batch": args.batch, "top_k": TOP_K},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"full {N_ROWS}-row corpus, {sample_q} of the {args.batch} queries per step, "
+                                   "exhaustive fp32 scan (oracle/exact_topk.c, OpenMP)"},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from multimodal_rag_b200 import _lib
+    from multimodal_rag_b200.sharded import DeviceShard
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    nq, k, K, W = args.batch, TOP_K, args.steps, max(args.warmup, 3)
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- corpus: synthetic unit-norm rows, generated on the device, ingested through K1 ----
+    def build_shard(seed, row_base):
+        sh = DeviceShard(DIM, "cosine", capacity=N_ROWS, row_base=row_base, device=local_rank)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        step = 1 << 18
+        for s in range(0, N_ROWS, step):
+            m = min(step, N_ROWS - s)
+            x = torch.nn.functional.normalize(torch.randn(m, DIM, generator=g, device=dev), dim=1)
+            sh.ingest(x)
+        torch.cuda.synchronize()
+        return sh
+
+    shard = build_shard(0xC0FFEE, 0)          # replicated corpus: same seed on every rank
+    gq = torch.Generator(device=dev).manual_seed(0xBEEF + rank)
+    n_batches = 4                              # rotate query batches so no step repeats its predecessor
+    Qd = [torch.nn.functional.normalize(torch.randn(nq, DIM, generator=gq, device=dev), dim=1) for _ in range(n_batches)]
+    Qh = [q.cpu().pin_memory() for q in Qd]
+    out = shard.alloc_out(nq, k)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device(i, sh=shard, o=out, q=None):
+        q = Qd[i % n_batches] if q is None else q
+        _lib.check(lib.b2r_query(sh.h, q.data_ptr(), nq, k, None, o["rows"].data_ptr(), o["dist"].data_ptr(),
+                                 o["cnt"].data_ptr(), stream), "b2r_query")
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- value: device-resident in/out ----
+    for i in range(W):
+        step_device(i)
+    launches0 = lib.b2r_launch_count(shard.h)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_device, K)
+    gpu_launches = int(lib.b2r_launch_count(shard.h) - launches0)
+    ms_step = ms_total / K
+    value = world * nq * K / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant (scoring) kernel: CUDA events around its launches ----
+    _lib.check(lib.b2r_set_kernel_timing(shard.h, 1))
+    tot, cnt = ctypes.c_double(), ctypes.c_int64()
+    _lib.check(lib.b2r_kernel_time_ms(shard.h, ctypes.byref(tot), ctypes.byref(cnt), 1))
+    for i in range(K):
+        step_device(i)
+    torch.cuda.synchronize()
+    _lib.check(lib.b2r_kernel_time_ms(shard.h, ctypes.byref(tot), ctypes.byref(cnt), 1))
+    _lib.check(lib.b2r_set_kernel_timing(shard.h, 0))
+    kern_ms_per_step = tot.value / K
+    launches_per_step = cnt.value / K
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers through the C ABI ----
+    h_rows = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    h_dist = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    h_cnt = torch.empty((nq,), dtype=torch.int32).pin_memory()
+
+    def step_host(i):
+        q = Qh[i % n_batches]
+        _lib.check(lib.b2r_query(shard.h, q.data_ptr(), nq, k, None, h_rows.data_ptr(), h_dist.data_ptr(),
+                                 h_cnt.data_ptr(), stream), "b2r_query")
+
+    for i in range(W):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step_host(i)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
+    e2e = world * nq * K / e2e_s
+    assert int(h_cnt.min()) == k
+
+    # ---- batch-1 scan (the HBM-bound headline of north_star), same corpus ----
+    q1 = [q[:1].contiguous() for q in Qd]
+    o1 = shard.alloc_out(1, k)
+
+    def step_b1(i):
+        q = q1[i % n_batches]
+        _lib.check(lib.b2r_query(shard.h, q.data_ptr(), 1, k, None, o1["rows"].data_ptr(), o1["dist"].data_ptr(),
+                                 o1["cnt"].data_ptr(), stream), "b2r_query")
+
+    K1 = max(K, 50)
+    for i in range(10):
+        step_b1(i)
+    ms_b1 = timed(step_b1, K1) / K1
+    _lib.check(lib.b2r_set_kernel_timing(shard.h, 1))
+    _lib.check(lib.b2r_kernel_time_ms(shard.h, ctypes.byref(tot), ctypes.byref(cnt), 1))
+    for i in range(K1):
+        step_b1(i)
+    torch.cuda.synchronize()
+    _lib.check(lib.b2r_kernel_time_ms(shard.h, ctypes.byref(tot), ctypes.byref(cnt), 1))
+    _lib.check(lib.b2r_set_kernel_timing(shard.h, 0))
+    b1_kern_ms = tot.value / max(1, cnt.value)
+    corpus_bytes = N_ROWS * DIM * 2
+    batch1 = {"qps": world * 1e3 / ms_b1, "us_per_query": ms_b1 * 1e3,
+              "roofline": {"bound": "hbm", "achieved": corpus_bytes / (b1_kern_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                           "unit": "GB/s", "frac": corpus_bytes / (b1_kern_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                           "kernel_us": b1_kern_ms * 1e3, "peak_src": pk["src"]}}
+
+    # ---- row-sharded path (N > 1): 1M-row shard per GPU, all_gather + merge ----
+    sharded = None
+    if world > 1:
+        shard.close()
+        sh2 = DeviceShard(DIM, "cosine", capacity=N_ROWS, row_base=rank * N_ROWS, device=local_rank)
+        g = torch.Generator(device=dev).manual_seed(0xC0FFEE + 1 + rank)
+        for s in range(0, N_ROWS, 1 << 18):
+            m = min(1 << 18, N_ROWS - s)
+            sh2.ingest(torch.nn.functional.normalize(torch.randn(m, DIM, generator=g, device=dev), dim=1))
+        gq2 = torch.Generator(device=dev).manual_seed(0xBEEF)       # replicated queries
+        Q2 = [torch.nn.functional.normalize(torch.randn(nq, DIM, generator=gq2, device=dev), dim=1) for _ in range(n_batches)]
+        o2 = sh2.alloc_out(nq, k)
+
+        def step_sharded(i):
+            sh2.query_device(Q2[i % n_batches], k, o2)
+
+        for i in range(W):
+            step_sharded(i)
+        ms_sh = timed(step_sharded, K)
+        sharded = {"rows_total": world * N_ROWS, "rows_per_gpu": N_ROWS, "qps": nq * K / (ms_sh * 1e-3),
+                   "ms_per_step": ms_sh / K, "collective": "nccl all_gather of [nq,k] x (int64 row, fp64 dist, int32 count)",
+                   "bytes_gathered_per_step": world * nq * (k * 16 + 4)}
+        sh2.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import c_oracle
+        c_oracle.build()
+        Xh = cpu_corpus(N_ROWS, DIM, 0xC0FFEE)
+        sample_q = min(nq, 32)
+        Qs = Qh[0][:sample_q].numpy()
+        qps_c, dt_c, thr = cpu_port_qps(Xh, Qs, k, 2, 0)
+        cpu = {"value": qps_c, "unit": UNIT, "cores": thr, "kind": "port",
+               "sample": f"full {N_ROWS}-row fp32 corpus, {sample_q} of the {nq} queries, 2 passes, "
+                         "exhaustive fp32 scan (oracle/exact_topk.c, OpenMP)"}
+        try:
+            from oracle import exact_oracle as eo
+            t0 = time.perf_counter()
+            eo.topk_bruteforce_f32(Qs, Xh, k, "cosine")
+            cpu["numpy_sgemm_qps"] = sample_q / (time.perf_counter() - t0)
+        except Exception as e:                                  # noqa: BLE001
+            cpu["numpy_sgemm_qps"] = f"failed: {e}"
+
+    flops = 2.0 * nq * N_ROWS * DIM
+    achieved_gbs = corpus_bytes * launches_per_step / (kern_ms_per_step * 1e-3) / 1e9 if kern_ms_per_step else 0.0
+    roof = {"bound": "hbm", "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved_gbs / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
+            "kernel": "scan_topk_kernel" if launches_per_step > 1.5 else "gemm_topk_kernel",
+            "launches_per_step": launches_per_step, "kernel_ms_per_step": kern_ms_per_step,
+            "algorithmic_bytes_per_launch": corpus_bytes, "flops_per_step": flops,
+            "tflops_per_step": flops / (kern_ms_per_step * 1e-3) / 1e12 if kern_ms_per_step else 0.0,
+            "tensor_peak_tflops": pk["bf16_tflops"]}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"configs[1]: {N_ROWS}x{DIM} bf16 corpus (+fp32 master for the exact re-rank), "
+                               f"batch {nq}, top_k={k}, cosine, 1xB200 per replica",
+                   "rows": N_ROWS, "dim": DIM, "batch": nq, "top_k": k, "space": "cosine",
+                   "l2_policy": "corpus (768 MB) is larger than L2 (126 MB); query batches rotate",
+                   "parallelism": "corpus replicated, queries sharded" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nq * DIM * 4,
+                "d2h_bytes_per_step": nq * k * 12 + nq * 4},
+        "gpu_launches": gpu_launches, "roofline": roof, "batch1": batch1, "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if sharded is not None:
+        line["sharded"] = sharded
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

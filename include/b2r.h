@@ -141,6 +141,11 @@ int b2r_merge_shards(const int64_t *in_rows, const double *in_dist64, const int3
 int b2r_set_path(b2r_handle h, int path);
 /* number of kernel launches issued by this handle since creation                    */
 int64_t b2r_launch_count(b2r_handle h);
+/* When enabled, every scoring-kernel launch (scan / tcgen05 / forced exact) is bracketed by
+ * CUDA events on the caller's stream; b2r_kernel_time_ms waits for them and returns the
+ * accumulated device time and launch count (reset != 0 clears the accumulators).      */
+int b2r_set_kernel_timing(b2r_handle h, int enable);
+int b2r_kernel_time_ms(b2r_handle h, double *total_ms, int64_t *launches, int reset);
 
 #ifdef __cplusplus
 }

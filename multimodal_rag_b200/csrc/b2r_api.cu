@@ -150,6 +150,8 @@ extern "C" int b2r_destroy(b2r_handle h) {
                       &h->o_rows, &h->o_dist, &h->o_dist64, &h->o_count, &h->need_exact, &h->scan_lists,
                       &h->exact_lists};
     for (DevBuf *b : bufs) release(*b);
+    for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete h;
     return B2R_OK;
 }
@@ -188,6 +190,30 @@ extern "C" int b2r_set_path(b2r_handle h, int path) {
 }
 
 extern "C" int64_t b2r_launch_count(b2r_handle h) { return h ? h->n_launches : 0; }
+
+extern "C" int b2r_set_kernel_timing(b2r_handle h, int enable) {
+    B2R_REQUIRE(h, "b2r_set_kernel_timing: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    h->timing = enable != 0;
+    return B2R_OK;
+}
+
+extern "C" int b2r_kernel_time_ms(b2r_handle h, double *total_ms, int64_t *launches, int reset) {
+    B2R_REQUIRE(h && total_ms && launches, "b2r_kernel_time_ms: NULL argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    for (auto &ev : h->ev_pending) {
+        B2R_CUDA(cudaEventSynchronize(ev.second));
+        float ms = 0.f;
+        B2R_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        h->scoring_ms += ms; h->scoring_launches++;
+        h->ev_free.push_back(ev);
+    }
+    h->ev_pending.clear();
+    *total_ms = h->scoring_ms; *launches = h->scoring_launches;
+    if (reset) { h->scoring_ms = 0.0; h->scoring_launches = 0; }
+    return B2R_OK;
+}
 extern "C" int64_t b2r_count(b2r_handle h) { return h ? h->live : -1; }
 
 extern "C" int b2r_get_stats(b2r_handle h, b2r_stats *out) {
@@ -315,9 +341,20 @@ extern "C" int b2r_get_rows_f32(b2r_handle h, const int64_t *rows, int64_t n, fl
 // ---------------------------------------------------------------------------------
 namespace {
 
-struct QueryPlan {
-    int path;       // 1 scan, 3 exact
-    int epl;        // scored-list EPL (scan) -- exact path uses epl_exact(k)
+// RAII-less pair of events around one scoring-kernel launch (only when h->timing)
+struct KernelTimer {
+    b2r_index *h; cudaStream_t s; std::pair<cudaEvent_t, cudaEvent_t> ev; bool on;
+    KernelTimer(b2r_index *h_, cudaStream_t s_) : h(h_), s(s_), on(h_->timing) {
+        if (!on) return;
+        if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
+        else if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(ev.first, s);
+    }
+    void stop() {
+        if (!on) return;
+        cudaEventRecord(ev.second, s);
+        h->ev_pending.push_back(ev);
+    }
 };
 
 int launch_scan_batch(b2r_index *h, int nq, int epl, const ScanParams &base, cudaStream_t s) {
@@ -335,7 +372,9 @@ int launch_scan_batch(b2r_index *h, int nq, int epl, const ScanParams &base, cud
         p.q0 = q;
         p.cta_lists = (KeyS *)h->scan_lists.p;
         p.stage_keys = scan_stage_keys(epl, grid);
+        KernelTimer kt(h, s);
         B2R_CUDA(scan_launch(h->dp, grp, epl, p, grid, s));
+        kt.stop();
         h->n_launches++;
         q += grp;
     }
@@ -358,7 +397,10 @@ int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const Finaliz
         p.cta_lists = (KeyD *)h->exact_lists.p; p.tickets = h->tickets + 1;
         p.n_fallbacks = (long long *)(h->counters + 1);
         p.fin = fin;
+        KernelTimer kt(h, s);
+        if (!force_all) kt.on = false;      // the certificate fix-up is not the scoring kernel
         B2R_CUDA(exact_launch(epl, p, grid, s));
+        kt.stop();
         h->n_launches++;
     }
     return B2R_OK;

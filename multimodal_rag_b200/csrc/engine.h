@@ -6,6 +6,8 @@
 
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/b2r.h"
 #include "common.cuh"
@@ -66,6 +68,13 @@ struct b2r_index {
     b2r::DevBuf o_rows, o_dist, o_dist64, o_count, need_exact;
     b2r::DevBuf scan_lists, exact_lists;
     unsigned *tickets = nullptr;    // [1 + EXACT_MAX_BATCH]
+
+    // optional per-kernel timing (bench.py roofline): CUDA events recorded around the scoring
+    // kernel launches on the caller's stream, resolved lazily by b2r_kernel_time_ms
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+    double scoring_ms = 0.0;
+    int64_t scoring_launches = 0;
 
     std::mutex mu;
 };

@@ -1,0 +1,247 @@
+"""Row-sharded collection over torch.distributed (one process per GPU).
+
+The reference is single-process (no collectives anywhere); this is the
+partitioning BASELINE.json's north_star asks for.  Every rank owns a shard of the rows and a
+full ``B200Collection`` over it.  All public methods are *collective*: every rank calls them
+with the same arguments and gets the same result.
+
+  add/upsert   new rows of a batch are split into contiguous slices, one per rank; every row
+               gets a global insertion sequence number (the oracle's tie-break key).
+  query        queries are replicated; each rank answers from its shard with the exact engine
+               (fp64 distances kept), the per-rank [nq, k] candidate lists are exchanged with ONE
+               all_gather (NCCL over NVLink on GPUs; 12-20 B per candidate), and every rank runs
+               the same merge on (fp64 distance, global sequence) -- the exchange is the only
+               data-path collective because top-k is a decomposable reduction.
+  where        each shard evaluates the clause on its own metadata tables (no global mask).
+
+``shard_factory`` / ``merge_fn`` exist so the host-side logic can be exercised with gloo on a
+machine without a GPU (tests inject CPU stand-ins); the defaults are the CUDA engine and the
+CUDA merge kernel, and there is no CPU fallback in the product path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def cuda_merge(rows, d64, cnt, k):
+    """[R,nq,k] int64 / fp64, [R,nq] int32 CUDA tensors -> merged (rows, dist fp32, count)."""
+    R, nq, _ = rows.shape
+    out_rows = torch.empty((nq, k), dtype=torch.int64, device=rows.device)
+    out_dist = torch.empty((nq, k), dtype=torch.float32, device=rows.device)
+    out_cnt = torch.empty((nq,), dtype=torch.int32, device=rows.device)
+    lib = _lib.load()
+    _lib.check(lib.b2r_merge_shards(rows.data_ptr(), d64.data_ptr(), cnt.data_ptr(), R, nq, k,
+                                    out_rows.data_ptr(), out_dist.data_ptr(), out_cnt.data_ptr(),
+                                    rows.device.index or 0,
+                                    torch.cuda.current_stream(rows.device).cuda_stream), "b2r_merge_shards")
+    return out_rows, out_dist, out_cnt
+
+
+class ShardedCollection:
+    def __init__(self, name="multimodal_rag", metadata=None, *, group=None, device=None,
+                 shard_factory=None, merge_fn=None, **shard_kw):
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedCollection needs an initialised torch.distributed process group")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.name, self.metadata = name, metadata
+        if shard_factory is None:
+            from .collection import B200Collection
+            if device is None:
+                device = torch.cuda.current_device()
+            shard_factory = lambda: B200Collection(name, metadata, device=device, **shard_kw)
+            self.comm_device = torch.device("cuda", device)
+        else:
+            self.comm_device = torch.device("cpu") if device is None else torch.device(device)
+        self.shard = shard_factory()
+        self.merge_fn = merge_fn or cuda_merge
+        self._next_seq = 0
+        self._gseq = np.zeros(0, dtype=np.int64)          # local row -> global sequence number
+        self._gseq_dev = None
+
+    # ---- helpers -------------------------------------------------------------------
+    def _all_gather_obj(self, obj):
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def _slice(self, m):
+        """contiguous, balanced slice of m new rows owned by this rank"""
+        lo = (m * self.rank) // self.world
+        hi = (m * (self.rank + 1)) // self.world
+        return lo, hi
+
+    def _ingest(self, ids, embeddings, metadatas, documents, upsert):
+        n = len(ids)
+        if len(set(ids)) != n:
+            raise ValueError("Expected IDs to be unique")
+        emb = embeddings if isinstance(embeddings, (np.ndarray, torch.Tensor)) else np.asarray(embeddings, dtype=np.float32)
+        if len(emb) != n:
+            raise ValueError(f"Number of embeddings {len(emb)} must match number of ids {n}")
+        have_local = [i for i in ids if i in self.shard._row_of]
+        have = set().union(*self._all_gather_obj(have_local))
+        if upsert:
+            if have_local:
+                self.shard.delete(ids=have_local)
+            new = list(range(n))
+        else:
+            new = [j for j, i in enumerate(ids) if i not in have]
+        lo, hi = self._slice(len(new))
+        mine = new[lo:hi]
+        if mine:
+            if isinstance(emb, torch.Tensor):
+                e = emb[torch.as_tensor(mine, device=emb.device)]
+            else:
+                e = emb[np.asarray(mine)]
+            self.shard.add(ids=[ids[j] for j in mine], embeddings=e,
+                           metadatas=None if metadatas is None else [metadatas[j] for j in mine],
+                           documents=None if documents is None else [documents[j] for j in mine])
+            self._gseq = np.concatenate([self._gseq, self._next_seq + np.asarray(range(lo, hi), dtype=np.int64)])
+            self._gseq_dev = None
+        self._next_seq += len(new)
+
+    def add(self, ids, embeddings=None, metadatas=None, documents=None):
+        self._ingest(list(ids), embeddings, metadatas, documents, upsert=False)
+
+    def upsert(self, ids, embeddings=None, metadatas=None, documents=None):
+        self._ingest(list(ids), embeddings, metadatas, documents, upsert=True)
+
+    def delete(self, ids=None, where=None):
+        if ids is not None:
+            ids = [i for i in ids if i in self.shard._row_of]
+            if not ids and where is None:
+                return
+        self.shard.delete(ids=ids, where=where)
+
+    def count(self) -> int:
+        t = torch.tensor([self.shard.count()], dtype=torch.int64, device=self.comm_device)
+        dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    # ---- query ---------------------------------------------------------------------
+    def query_rows(self, query_embeddings, n_results=10, where=None):
+        """Collective.  Returns (gseq [nq,k] int64 global sequence numbers, dist [nq,k] fp32,
+        count [nq] int32) as numpy arrays, identical on every rank."""
+        k = n_results
+        rows, _, cnt, d64 = self.shard.query_rows(query_embeddings, k, where, want_dist64=True)
+        g = np.where(rows >= 0, self._gseq[np.clip(rows, 0, max(len(self._gseq) - 1, 0))] if len(self._gseq) else -1, -1)
+        dev = self.comm_device
+        t_rows = torch.from_numpy(np.ascontiguousarray(g, dtype=np.int64)).to(dev)
+        t_d64 = torch.from_numpy(d64).to(dev)
+        t_cnt = torch.from_numpy(cnt).to(dev)
+        R = self.world
+        a_rows = torch.empty((R,) + tuple(t_rows.shape), dtype=torch.int64, device=dev)
+        a_d64 = torch.empty((R,) + tuple(t_d64.shape), dtype=torch.float64, device=dev)
+        a_cnt = torch.empty((R,) + tuple(t_cnt.shape), dtype=torch.int32, device=dev)
+        # list form of all_gather: identical on nccl and gloo (gloo's *_into_tensor is shape-picky)
+        dist.all_gather(list(a_rows.unbind(0)), t_rows, group=self.group)
+        dist.all_gather(list(a_d64.unbind(0)), t_d64, group=self.group)
+        dist.all_gather(list(a_cnt.unbind(0)), t_cnt, group=self.group)
+        o_rows, o_dist, o_cnt = self.merge_fn(a_rows, a_d64, a_cnt, k)
+        return o_rows.cpu().numpy(), o_dist.cpu().numpy(), o_cnt.cpu().numpy()
+
+    def query(self, query_embeddings=None, n_results=10, where=None,
+              include=("metadatas", "documents", "distances")):
+        """Collective ``Collection.query`` with Chroma's nested-list result on every rank."""
+        g, d, cnt = self.query_rows(query_embeddings, n_results, where)
+        nq = g.shape[0]
+        # winners owned by this rank -> payload; one object all_gather assembles the rest
+        mine = {}
+        if len(self._gseq):
+            for i in range(nq):
+                for s in g[i, : cnt[i]].tolist():
+                    pos = int(np.searchsorted(self._gseq, s))
+                    if pos < len(self._gseq) and self._gseq[pos] == s:
+                        mine[s] = (self.shard._ids[pos], self.shard._meta.meta[pos], self.shard._docs[pos])
+        table = {}
+        for part in self._all_gather_obj(mine):
+            table.update(part)
+        res = {"ids": [], "distances": None, "metadatas": None, "documents": None, "embeddings": None}
+        for key in include:
+            res[key] = []
+        for i in range(nq):
+            seqs = g[i, : cnt[i]].tolist()
+            res["ids"].append([table[s][0] for s in seqs])
+            if res["distances"] is not None:
+                res["distances"].append(d[i, : cnt[i]].tolist())
+            if res["metadatas"] is not None:
+                res["metadatas"].append([table[s][1] for s in seqs])
+            if res["documents"] is not None:
+                res["documents"].append([table[s][2] for s in seqs])
+        return res
+
+
+class DeviceShard:
+    """Minimal device-resident shard for throughput runs (bench.py): no ids, no metadata, rows
+    numbered row_base + local.  query_device keeps every tensor on the GPU and enqueues
+    local scan -> all_gather -> merge on the current stream without a host sync."""
+
+    def __init__(self, dim, space="cosine", *, capacity=0, row_base=0, device=None, group=None,
+                 keep_f32_master=True):
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else device
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.b2r_create(dim, _lib.SPACE_CODE[space], capacity, self.device,
+                                       0 if keep_f32_master else _lib.FLAG_NO_F32_MASTER, ctypes.byref(h)))
+        self.h = h
+        self.dim = dim
+        _lib.check(self.lib.b2r_set_row_base(h, row_base))
+
+    def close(self):
+        if self.h is not None:
+            self.lib.b2r_destroy(self.h)
+            self.h = None
+
+    def ingest(self, x: torch.Tensor):
+        first = ctypes.c_int64()
+        x = x.contiguous()
+        _lib.check(self.lib.b2r_ingest_f32(self.h, x.data_ptr(), x.shape[0], None, ctypes.byref(first),
+                                           torch.cuda.current_stream().cuda_stream), "b2r_ingest_f32")
+        return first.value
+
+    def alloc_out(self, nq, k):
+        dev = torch.device("cuda", self.device)
+        R = self.world
+        return {
+            "rows": torch.empty((nq, k), dtype=torch.int64, device=dev),
+            "dist": torch.empty((nq, k), dtype=torch.float32, device=dev),
+            "d64": torch.empty((nq, k), dtype=torch.float64, device=dev),
+            "cnt": torch.empty((nq,), dtype=torch.int32, device=dev),
+            "a_rows": torch.empty((R, nq, k), dtype=torch.int64, device=dev),
+            "a_d64": torch.empty((R, nq, k), dtype=torch.float64, device=dev),
+            "a_cnt": torch.empty((R, nq), dtype=torch.int32, device=dev),
+            "m_rows": torch.empty((nq, k), dtype=torch.int64, device=dev),
+            "m_dist": torch.empty((nq, k), dtype=torch.float32, device=dev),
+            "m_cnt": torch.empty((nq,), dtype=torch.int32, device=dev),
+        }
+
+    def query_local(self, q: torch.Tensor, k: int, o: dict):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.b2r_query_ex(self.h, q.data_ptr(), q.shape[0], k, None, o["rows"].data_ptr(),
+                                         o["dist"].data_ptr(), o["d64"].data_ptr(), o["cnt"].data_ptr(), st),
+                   "b2r_query")
+
+    def query_device(self, q: torch.Tensor, k: int, o: dict):
+        """Replicated queries against the row-sharded corpus: local exact top-k, one all_gather of
+        the candidate lists over NCCL, merge kernel.  Results in o['m_rows'|'m_dist'|'m_cnt']."""
+        self.query_local(q, k, o)
+        if self.world == 1:
+            return o["rows"], o["dist"], o["cnt"]
+        dist.all_gather_into_tensor(o["a_rows"], o["rows"], group=self.group)
+        dist.all_gather_into_tensor(o["a_d64"], o["d64"], group=self.group)
+        dist.all_gather_into_tensor(o["a_cnt"], o["cnt"], group=self.group)
+        st = torch.cuda.current_stream().cuda_stream
+        nq = q.shape[0]
+        _lib.check(self.lib.b2r_merge_shards(o["a_rows"].data_ptr(), o["a_d64"].data_ptr(), o["a_cnt"].data_ptr(),
+                                             self.world, nq, k, o["m_rows"].data_ptr(), o["m_dist"].data_ptr(),
+                                             o["m_cnt"].data_ptr(), self.device, st), "b2r_merge_shards")
+        return o["m_rows"], o["m_dist"], o["m_cnt"]

@@ -1,0 +1,73 @@
+"""CPU: the C-ABI library loads here (no GPU), exports every symbol include/b2r.h declares, and
+fails loudly -- never falls back -- when asked to compute without a device."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from multimodal_rag_b200 import _lib, build as b2r_build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    b2r_build.build()
+    return _lib.load()
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "b2r.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2r_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported(lib):
+    decl = _declared()
+    assert sorted(_lib.ABI_SYMBOLS) == decl
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert set(decl) <= exported
+    assert {s for s in exported if s.startswith("b2r_")} == set(decl)       # nothing undocumented
+    assert lib.b2r_abi_version() == 1
+
+
+def test_library_is_sm100a_native(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p()
+    rc = lib.b2r_create(384, 1, 0, 0, 0, ctypes.byref(h))
+    assert rc == _lib.B2R_ECUDA and b"no CPU fallback" in lib.b2r_last_error()
+    from multimodal_rag_b200 import B200Collection
+    c = B200Collection("c", {"hnsw:space": "cosine"})
+    with pytest.raises(RuntimeError):
+        c.add(ids=["a"], embeddings=[[0.0] * 384])
+    with pytest.raises(ValueError):
+        B200Collection("c", {"hnsw:space": "hamming"})
+
+
+def test_argument_validation_without_device(lib):
+    h = ctypes.c_void_p()
+    assert lib.b2r_create(0, 1, 0, 0, 0, ctypes.byref(h)) == _lib.B2R_EINVAL
+    assert lib.b2r_create(384, 7, 0, 0, 0, ctypes.byref(h)) == _lib.B2R_EINVAL
+    assert lib.b2r_query(None, None, 1, 5, None, None, None, None, None) == _lib.B2R_EINVAL
+    assert lib.b2r_count(None) == -1
+    with pytest.raises(ValueError):
+        _lib.check(lib.b2r_create(384, 7, 0, 0, 0, ctypes.byref(h)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "multimodal_rag_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in src.replace("the oracle's tie-break key", ""), f"{fn} mentions the oracle"

@@ -1,0 +1,76 @@
+"""CPU: the product's columnar where-evaluator (multimodal_rag_b200/where.py) against the oracle's
+per-row restatement of Chroma's grammar."""
+import numpy as np
+import pytest
+
+from multimodal_rag_b200.where import MetaTable, pack_bits
+from oracle.exact_oracle import where_match
+
+
+def _table(n=500, seed=0):
+    rng = np.random.default_rng(seed)
+    t, metas = MetaTable(), []
+    for i in range(n):
+        m = {"doc_id": f"doc_{i % 17:04d}", "item_id": f"text_{i}", "type": str(rng.choice(["text", "table", "image"]))}
+        if i % 3:
+            m["page"] = int(i % 11)
+        if i % 5 == 0:
+            m["score"] = float(i) / 7
+        if i % 7 == 0:
+            m["flag"] = bool(i % 2)
+        if i % 50 == 0:
+            m = None
+        metas.append(m)
+        t.append(m)
+    return t, metas
+
+
+CLAUSES = [
+    {"type": "image"}, {"type": {"$eq": "text"}}, {"type": {"$ne": "text"}}, {"type": {"$in": ["image", "table"]}},
+    {"type": {"$nin": ["image"]}}, {"doc_id": "doc_0007"}, {"page": {"$gte": 5}}, {"page": {"$lt": 3}},
+    {"page": 4}, {"page": 4.0}, {"score": {"$gt": 20.5}}, {"flag": True}, {"flag": {"$ne": True}},
+    {"page": {"$ne": "4"}}, {"missing": "x"}, {"missing": {"$ne": "x"}}, {"type": "video"},
+    {"$and": [{"type": "text"}, {"page": {"$lte": 2}}]},
+    {"$or": [{"type": "image"}, {"$and": [{"doc_id": "doc_0003"}, {"page": {"$in": [1, 2, 3]}}]}]},
+    {"page": {"$in": [1, "1", True]}},
+]
+
+
+@pytest.mark.parametrize("where", CLAUSES)
+def test_mask_matches_oracle(where):
+    t, metas = _table()
+    got = t.mask(where)
+    want = np.array([where_match(m, where) for m in metas])
+    np.testing.assert_array_equal(got, want)
+
+
+def test_type_fast_path_and_bits():
+    t, metas = _table()
+    tm = t.type_only_mask({"type": "image"})
+    codes = np.array([t.type_code_of(m) for m in metas])
+    np.testing.assert_array_equal(((tm >> codes) & 1).astype(bool), t.mask({"type": "image"}))
+    tm = t.type_only_mask({"type": {"$in": ["image", "nope"]}})
+    np.testing.assert_array_equal(((tm >> codes) & 1).astype(bool), t.mask({"type": "image"}))
+    assert t.type_only_mask({"type": "nope"}) == 0
+    assert t.type_only_mask({"doc_id": "doc_0001"}) is None and t.type_only_mask({"type": {"$ne": "text"}}) is None
+    m = t.mask({"page": {"$gte": 5}})
+    bits = pack_bits(m)
+    assert bits.dtype == np.uint32 and bits.shape[0] == (m.shape[0] + 31) // 32
+    back = np.array([(bits[r >> 5] >> (r & 31)) & 1 for r in range(m.shape[0])], dtype=bool)
+    np.testing.assert_array_equal(back, m)
+
+
+def test_type_code_overflow_falls_back_to_bitmap():
+    t = MetaTable()
+    for i in range(100):
+        t.append({"type": f"kind{i}"})
+    assert t.type_overflow and t.type_only_mask({"type": "kind3"}) is None
+    assert t.mask({"type": "kind99"}).sum() == 1
+
+
+@pytest.mark.parametrize("bad", [{"a": 1, "b": 2}, {"$xor": []}, {"a": {"$like": "x"}}, {"a": {"$gt": "x"}},
+                                 {"a": {"$in": []}}, {"$and": []}])
+def test_bad_clauses_raise(bad):
+    t, _ = _table(20)
+    with pytest.raises(ValueError):
+        t.mask(bad)
