@@ -23,15 +23,15 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O2,-Wall", "-ccbin", "/usr/bin/g++"]
 SCAN_DPS = [64, 128, 256, 384, 512, 768, 1024]
+GEMM_KBS = [2, 4, 6, 8, 12]          # padded dim / 64: 128, 256, 384, 512, 768
 
 
 def _units():
     units = [("b2r_api", "b2r_api.cu", []), ("exact_kernels", "exact_kernels.cu", []),
              ("scan_dispatch", "scan_kernels.cu", [])]
     units += [(f"scan_dp{dp}", "scan_kernels.cu", [f"-DB2R_DP={dp}"]) for dp in SCAN_DPS]
-    extra = os.path.join(CSRC, "gemm_kernels.cu")
-    if os.path.exists(extra):
-        units.append(("gemm_kernels", "gemm_kernels.cu", []))
+    units.append(("gemm_dispatch", "gemm_kernels.cu", []))
+    units += [(f"gemm_kb{kb}", "gemm_kernels.cu", [f"-DB2R_KB={kb}"]) for kb in GEMM_KBS]
     return units
 
 

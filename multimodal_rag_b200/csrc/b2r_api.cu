@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "gemm.cuh"
 #include "ingest.cuh"
 
 using namespace b2r;
@@ -73,7 +74,7 @@ int grow(b2r_index *h, int64_t cap, cudaStream_t s) {
         if (e != cudaSuccess) { cudaFree(corpus); B2R_CUDA(e); }
     }
     if (h->space == B2R_SPACE_L2) {
-        cudaError_t e = cudaMalloc(&bias, (size_t)cap * 4);
+        cudaError_t e = cudaMalloc(&bias, ((size_t)cap + 512) * 4);   // K3 reads whole tiles
         if (e != cudaSuccess) { cudaFree(corpus); cudaFree(master); B2R_CUDA(e); }
     }
     {
@@ -148,7 +149,7 @@ extern "C" int b2r_destroy(b2r_handle h) {
     cudaFree(h->max_norm2); cudaFree(h->counters); cudaFree(h->tickets);
     DevBuf *bufs[] = {&h->x_stage, &h->t_stage, &h->q_raw, &h->q_prep, &h->allow, &h->rows_stage, &h->gather_out,
                       &h->o_rows, &h->o_dist, &h->o_dist64, &h->o_count, &h->need_exact, &h->scan_lists,
-                      &h->exact_lists};
+                      &h->exact_lists, &h->q_bf16, &h->pass_bits, &h->gthr, &h->gemm_lists};
     for (DevBuf *b : bufs) release(*b);
     for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -406,6 +407,53 @@ int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const Finaliz
     return B2R_OK;
 }
 
+// K3: pass bitmap -> tcgen05 scoring + per-(query, slice) lists -> per-query finalize
+constexpr int GEMM_MIN_BATCH = 5;        // below this the scan reads the corpus at most twice anyway
+constexpr int GEMM_MAX_QBLOCKS = 8;      // 128-query blocks per launch (1024 queries per corpus pass)
+
+int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams &fin, const b2r_filter &f,
+                      const uint32_t *allow_dev, cudaStream_t s) {
+    const int L = gemm_list_len(k);
+    const int BN = gemm_tile_rows(h->dp);
+    const int tiles_total = (int)((h->rows + BN - 1) / BN);
+    const unsigned n_words = (unsigned)tiles_total * (unsigned)(BN / 32);
+    const int qblocks_total = (nq + GEMM_BM - 1) / GEMM_BM;
+    const int list_stride = h->sm_count * L;
+    int rc;
+    if ((rc = ensure(h->pass_bits, (size_t)n_words * 4 + 16)) != B2R_OK) return rc;
+    if ((rc = ensure(h->gthr, (size_t)qblocks_total * GEMM_BM * 4)) != B2R_OK) return rc;
+    if ((rc = ensure(h->gemm_lists, sizeof(KeyS) * (size_t)nq * list_stride)) != B2R_OK) return rc;
+    B2R_CUDA(cudaMemsetAsync(h->gthr.p, 0, (size_t)qblocks_total * GEMM_BM * 4, s));
+    B2R_CUDA(pass_bits_launch(h->type_code, f.type_mask, allow_dev, (unsigned)h->rows, n_words,
+                              (uint32_t *)h->pass_bits.p, h->sm_count, s));
+    h->n_launches++;
+    if (h->tm_corpus_base != h->corpus || h->tm_corpus_rows != h->capacity) {
+        if ((rc = gemm_encode_map(&h->tm_corpus, h->corpus, h->dp, (uint64_t)h->capacity, BN)) != B2R_OK) return rc;
+        h->tm_corpus_base = h->corpus; h->tm_corpus_rows = h->capacity;
+    }
+    if (h->tm_query_base != h->q_bf16.p || h->tm_query_rows != nq) {
+        if ((rc = gemm_encode_map(&h->tm_query, h->q_bf16.p, h->dp, (uint64_t)nq, GEMM_BM)) != B2R_OK) return rc;
+        h->tm_query_base = h->q_bf16.p; h->tm_query_rows = nq;
+    }
+    for (int qb0 = 0; qb0 < qblocks_total; qb0 += GEMM_MAX_QBLOCKS) {
+        GemmParams gp;
+        gp.n = (unsigned)h->rows; gp.nq = nq; gp.qblock0 = qb0;
+        gp.n_qblocks = std::min(GEMM_MAX_QBLOCKS, qblocks_total - qb0);
+        gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, tiles_total));
+        gp.list_stride = list_stride; gp.tiles_total = tiles_total;
+        gp.pass_bits = (const uint32_t *)h->pass_bits.p; gp.bias = h->bias;
+        gp.gthr = (unsigned *)h->gthr.p; gp.lists = (KeyS *)h->gemm_lists.p;
+        KernelTimer kt(h, s);
+        B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
+        kt.stop();
+        h->n_launches++;
+        const int q0 = qb0 * GEMM_BM, nq_here = std::min(nq - q0, gp.n_qblocks * GEMM_BM);
+        B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, gp.n_slices * L, gp.gthr, q0, nq_here, s));
+        h->n_launches++;
+    }
+    return B2R_OK;
+}
+
 }  // namespace
 
 extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
@@ -456,11 +504,25 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
         }
     }
 
-    // ---- prepare queries (cosine: hnswlib normalisation; zero-pad to dp) ----
+    // ---- choose the scoring path ----
+    //   1  warp-shuffle scan (K2): batches of <= 4 queries per corpus pass, HBM-bound
+    //   2  tcgen05 GEMM (K3): one corpus pass per <= 1024 queries
+    //   3  exact fp64 scan (K5): always correct, used for shapes the fast kernels are not built for
+    int path = h->path;
+    const int epl_s = epl_scored(k);
+    const bool scan_ok = scan_supported(h->dp) && epl_s != 0;
+    const bool gemm_ok = gemm_supported(h->dp, k) && epl_s != 0 && epl_s <= 2;
+    if (path == 0) path = (gemm_ok && nq >= GEMM_MIN_BATCH) ? 2 : scan_ok ? 1 : 3;
+    if (path == 2 && !gemm_ok) path = scan_ok ? 1 : 3;
+    if (path == 1 && !scan_ok) path = 3;
+    if (h->rows == 0) path = 3;   // empty collection: Chroma returns empty lists; only the padding is written
+
+    // ---- prepare queries (cosine: hnswlib normalisation; zero-pad to dp; bf16 copy for K3) ----
+    if (path == 2 && (rc = ensure(h->q_bf16, (size_t)nq * h->dp * 2)) != B2R_OK) return rc;
     {
         IngestParams p;
         p.x = q_raw; p.n = nq; p.d = h->dim; p.dp = h->dp; p.space = h->space;
-        p.corpus = nullptr; p.master = (float *)h->q_prep.p; p.bias = nullptr;
+        p.corpus = path == 2 ? (uint4 *)h->q_bf16.p : nullptr; p.master = (float *)h->q_prep.p; p.bias = nullptr;
         p.type_out = nullptr; p.type_in = nullptr; p.max_norm2 = nullptr;
         const int wpb = INGEST_THREADS / 32;
         int grid = std::min((nq + wpb - 1) / wpb, h->sm_count * 8);
@@ -476,28 +538,24 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     fin.max_norm2 = h->max_norm2; fin.dp = h->dp; fin.space = h->space; fin.k = k;
     fin.row_base = h->row_base; fin.out_rows = o_rows; fin.out_dist = o_dist; fin.out_dist64 = o_dist64;
     fin.out_count = o_count; fin.need_exact = (int *)h->need_exact.p;
-    // scan: fp32 query x bf16 corpus, fp32 accumulate.  bf16 unit roundoff 2^-8 only if
-    // the exact answer is defined on the fp32 master; fp32 accumulation adds (dp+2)*2^-24.
+    // |scan score - exact score| <= eps_rel * |q| * max|x| (+ small abs term, finalize_candidates).
+    // Corpus rounded to bf16: unit roundoff 2^-8 (only counts when the exact answer is defined on the
+    // fp32 master).  K2 keeps the query in fp32 and accumulates in fp32: (dp+8) * 2^-24.  K3 also rounds
+    // the query to bf16 (another 2^-8, plus the 2^-16 cross term) and the tensor core's fp32 accumulation
+    // is allowed 4x the rounding slop.
     fin.eps_rel = (h->master ? 0.00390625f : 0.f) + (float)(h->dp + 8) * 5.9604645e-8f;
+    if (path == 2) fin.eps_rel += 0.00390625f + 1.52587890625e-5f + 3.f * (float)(h->dp + 8) * 5.9604645e-8f;
     fin.eps_rel *= 1.01f;
 
-    // ---- choose the scoring path ----
-    int path = h->path;
-    const int epl_s = epl_scored(k);
-    if (path == 0) path = (scan_supported(h->dp) && epl_s != 0) ? 1 : 3;
-    if (path == 2) path = 1;   // tcgen05 path not built into this library version
-    if (path == 1 && (!scan_supported(h->dp) || epl_s == 0)) path = 3;
-
-    if (h->rows == 0) {
-        // empty collection: Chroma returns empty lists; nothing to launch but the padding
-        path = 3;
-    }
     if (path == 1) {
         ScanParams sp;
         sp.corpus = h->corpus; sp.bias = h->bias; sp.type_code = h->type_code; sp.allow_bits = allow_dev;
         sp.type_mask = f.type_mask; sp.n = (unsigned)h->rows; sp.q0 = 0; sp.cta_lists = nullptr;
         sp.ticket = h->tickets; sp.fin = fin;
         if ((rc = launch_scan_batch(h, nq, epl_s, sp, s)) != B2R_OK) return rc;
+        if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
+    } else if (path == 2) {
+        if ((rc = launch_gemm_batch(h, nq, k, epl_s, fin, f, allow_dev, s)) != B2R_OK) return rc;
         if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
     } else {
         if ((rc = launch_exact_batch(h, nq, k, 1, fin, f, allow_dev, s)) != B2R_OK) return rc;

@@ -1,6 +1,7 @@
 // Host-side engine state behind the C ABI (include/b2r.h) and the launcher interfaces
 // each kernel translation unit exports.  Not part of the ABI.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -39,6 +40,19 @@ int scan_tile_rows(int dp);
 int exact_max_grid(int epl, int dp, int sm_count);
 cudaError_t exact_launch(int epl, const ExactParams &p, int grid, cudaStream_t s);
 
+// K3 (gemm_kernels.cu): tcgen05 batched scoring
+struct GemmParams;
+bool gemm_supported(int dp, int k);
+int gemm_list_len(int k);          // per-(query, slice) list length L for n_results = k (0 = unsupported)
+int gemm_tile_rows(int dp);        // corpus rows per MMA tile (BN)
+int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, int box_rows);
+cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
+                        const GemmParams &p, cudaStream_t s);
+cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_mask, const uint32_t *allow_bits,
+                             unsigned n, unsigned n_words, uint32_t *out, int sm_count, cudaStream_t s);
+cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
+                                  int entries_per_query, const unsigned *gthr, int q0, int nq, cudaStream_t s);
+
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
@@ -67,6 +81,12 @@ struct b2r_index {
     b2r::DevBuf x_stage, t_stage, q_raw, q_prep, allow, rows_stage, gather_out;
     b2r::DevBuf o_rows, o_dist, o_dist64, o_count, need_exact;
     b2r::DevBuf scan_lists, exact_lists;
+    b2r::DevBuf q_bf16, pass_bits, gthr, gemm_lists;   // K3 scratch
+
+    // TMA tensor maps (K3), re-encoded when the buffer they describe moves or grows
+    CUtensorMap tm_corpus, tm_query;
+    const void *tm_corpus_base = nullptr; int64_t tm_corpus_rows = -1;
+    const void *tm_query_base = nullptr; int64_t tm_query_rows = -1;
     unsigned *tickets = nullptr;    // [1 + EXACT_MAX_BATCH]
 
     // optional per-kernel timing (bench.py roofline): CUDA events recorded around the scoring

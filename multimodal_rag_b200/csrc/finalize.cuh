@@ -93,6 +93,43 @@ __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, con
     if (threadIdx.x == 0) p.out_count[qi] = cnt;
 }
 
+// Stages shared by every scoring path once the candidate set is known: exact re-rank of the
+// nvalid candidates in sm_keys (one warp per candidate), Chroma-ordered output, and the certificate:
+// every row outside the candidate set has scan score <= T, so its exact score is <= T + eps; if the
+// k-th exact candidate beats that, no outsider can belong to the top-k.  T = -inf means there are no
+// outsiders.  All FIN_THREADS threads call; sm_q must already hold the prepared query.
+__device__ __forceinline__ void finalize_candidates(const FinalizeParams &p, int qi, const KeyS *sm_keys, int nvalid,
+                                                    float T, KeyD *sm_ex, const float *sm_q, KeyD *sm_misc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = warp; c < nvalid; c += FIN_WARPS) {
+        unsigned row = sm_keys[c].row();
+        double d = exact_distance_warp(p, sm_q, row, lane);
+        if (lane == 0) sm_ex[c] = KeyD::make(d, row);
+    }
+    if (threadIdx.x == 0) sm_misc[0] = KeyD::worst();
+    __syncthreads();
+    emit_sorted(p, qi, sm_ex, nvalid, &sm_misc[0]);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int flag = 0;
+        if (T > -INFINITY) {
+            double qn2 = 0.0;
+            for (int i = lane; i < p.dp; i += 32) qn2 = fma((double)sm_q[i], (double)sm_q[i], qn2);
+            qn2 = warp_sum(qn2);
+            double xn = sqrt((double)*p.max_norm2), qn = sqrt(qn2);
+            double eps = (double)p.eps_rel * qn * xn + 1e-6 * (0.5 * xn * xn + qn * xn) + 1e-30;
+            KeyD kth = sm_misc[0];
+            double s_k;
+            if (!kth.valid()) s_k = -1e300;                       // fewer than k candidates but rows were rejected
+            else if (p.space == 0) s_k = 0.5 * (qn2 - kth.d);
+            else s_k = 1.0 - kth.d;
+            flag = (s_k - eps > (double)T) ? 0 : 1;
+        }
+        if (lane == 0) p.need_exact[qi] = flag;
+    }
+    __syncthreads();
+}
+
 // Tree-merge the per-warp lists of a CTA: after the call warp 0 holds the CTA's best KP and
 // has stored them rank-ordered at sm[0, KP).  sm must hold FIN_WARPS*KP keys.  All threads call.
 template <class K, int EPL>
@@ -146,38 +183,9 @@ __device__ void finalize_scored_query(const FinalizeParams &p, int qi, const Key
     int nvalid = 0;
     for (int i = 0; i < KP; ++i) nvalid += sm_keys[i].valid() ? 1 : 0;   // tiny, uniform
 
-    // ---- stage 3: exact re-rank, one warp per candidate ----
-    for (int c = warp; c < nvalid; c += FIN_WARPS) {
-        unsigned row = sm_keys[c].row();
-        double d = exact_distance_warp(p, sm_q, row, lane);
-        if (lane == 0) sm_ex[c] = KeyD::make(d, row);
-    }
-    if (threadIdx.x == 0) sm_misc[0] = KeyD::worst();
-    __syncthreads();
-    emit_sorted(p, qi, sm_ex, nvalid, &sm_misc[0]);
-    __syncthreads();
-
-    // ---- stage 4: certificate ----
-    if (threadIdx.x < 32) {
-        int flag = 0;
-        if (nvalid == KP) {   // otherwise every passing row of the shard is already a candidate
-            // every row outside the list scored <= T in the scan; its exact score is <= T + eps
-            float T = sm_keys[KP - 1].score();
-            double qn2 = 0.0;
-            for (int i = lane; i < p.dp; i += 32) qn2 = fma((double)sm_q[i], (double)sm_q[i], qn2);
-            qn2 = warp_sum(qn2);
-            double xn = sqrt((double)*p.max_norm2), qn = sqrt(qn2);
-            double eps = (double)p.eps_rel * qn * xn + 1e-6 * (0.5 * xn * xn + qn * xn) + 1e-30;
-            KeyD kth = sm_misc[0];
-            double s_k;
-            if (!kth.valid()) s_k = -1e300;                       // fewer than k results: cannot happen with nvalid==KP>=k
-            else if (p.space == 0) s_k = 0.5 * (qn2 - kth.d);
-            else s_k = 1.0 - kth.d;
-            flag = (s_k - eps > (double)T) ? 0 : 1;
-        }
-        if (lane == 0) p.need_exact[qi] = flag;
-    }
-    __syncthreads();
+    // every row outside the list scored <= T in the scan (T = -inf: the list holds every passing row)
+    const float T = nvalid == KP ? sm_keys[KP - 1].score() : -INFINITY;
+    finalize_candidates(p, qi, sm_keys, nvalid, T, sm_ex, sm_q, sm_misc);
 }
 
 }  // namespace b2r

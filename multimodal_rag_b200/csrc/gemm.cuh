@@ -1,0 +1,392 @@
+// K3: batched scoring on the 5th-gen tensor cores (tcgen05 / TMEM / TMA), fused selection.
+//
+// One CTA = one block of 128 queries x one contiguous slice of the corpus.
+//   A operand  128 prepared queries (bf16), all K-blocks, loaded ONCE by TMA and kept in shared memory
+//   B operand  corpus tiles of BN rows, streamed K-block by K-block (64 bf16 = one 128-byte swizzle row)
+//              through a STAGES-deep TMA/mbarrier ring
+//   D          128 x BN fp32 scores in TMEM, double buffered (2*BN columns) so the tensor pipe fills
+//              tile t+1 while the epilogue drains tile t
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 =
+// epilogue.  In TMEM a lane is a query and a column is a corpus row, so every epilogue thread owns ONE
+// query: it streams that query's scores through a single compare against a private threshold and keeps
+// the best L rows of its slice in a register-resident sorted list.  The threshold is
+// max(own L-th best, shared per-query bound): whenever a thread's list is full it publishes its L-th
+// best score to gthr[q] (atomicMax); all slices of the same query read it once per tile, so the
+// admission rate falls with the rows seen by the WHOLE grid, not by one slice.
+//
+// What leaves the kernel: per (query, slice) the L best admitted rows (KeyS: score, local row) and the
+// final gthr[q].  Invariant used by the certificate (finalize_union_kernel): a row that is not in any
+// list was rejected by, or evicted below, a value that was published to gthr[q] or is some list's final
+// L-th best (also published) -- so its bf16 score is <= the final gthr[q].
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "finalize.cuh"
+
+namespace b2r {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARP0 = 2;
+constexpr int GEMM_SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA
+constexpr int GEMM_SMEM_SLACK = 1024 + 512;   // manual 1024-byte alignment + static barriers
+
+struct GemmParams {
+    unsigned n;                  // rows in this shard
+    int nq;                      // queries in the batch
+    int qblock0;                 // first 128-query block of this launch (batches > 8 blocks are chunked)
+    int n_qblocks, n_slices;     // grid = n_slices * n_qblocks (blockIdx = slice * n_qblocks + qblock)
+    int list_stride;             // KeyS entries reserved per query in `lists` (>= n_slices * L)
+    int tiles_total;             // ceil(n / BN)
+    const uint32_t *pass_bits;   // bit r = row r is live and passes the filter; 0 for r >= n
+    const float *bias;           // [n] -|x|^2/2 (l2) or nullptr
+    unsigned *gthr;              // [n_qblocks*128] shared per-query bound, KeyS::ord encoding, 0 = none yet
+    KeyS *lists;                 // [nq][list_stride]: slice s of query q at q*list_stride + s*L
+};
+
+__host__ __device__ constexpr int gemm_bn(int KB) { return KB <= 8 ? 256 : 128; }
+__host__ __device__ constexpr int gemm_stages(int KB) {
+    int a = KB * GEMM_BM * 128, st = gemm_bn(KB) * 128;
+    int s = (GEMM_SMEM_LIMIT - GEMM_SMEM_SLACK - a) / st;
+    return s > 8 ? 8 : s;
+}
+__host__ __device__ constexpr size_t gemm_smem_bytes(int KB) {
+    return (size_t)KB * GEMM_BM * 128 + (size_t)gemm_stages(KB) * gemm_bn(KB) * 128 + 1024;
+}
+
+// ---------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait with a watchdog: a protocol bug must fail the launch (trap -> CUDA error), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
+}
+// 2-D tiled load global -> shared, completion on an mbarrier (bytes)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {   // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp (the allocating one)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32; one thread issues for the CTA
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 64 bf16 (128 B),
+// 8-row groups 1024 B apart (SBO); version 1 (sm_100); LBO unused for swizzled K-major
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (lane = thread)
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tmem_ld_x1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\ntcgen05.wait::ld.sync.aligned;\n"
+                 : "=r"(r) : "r"(taddr) : "memory");
+    return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------
+// per-thread sorted list (descending score; equal scores keep the earlier = lower row first)
+// ---------------------------------------------------------------------------------
+template <int L>
+struct RegList {
+    float s[L];
+    unsigned r[L];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < L; ++i) { s[i] = -INFINITY; r[i] = 0xffffffffu; }
+    }
+    // x must beat s[L-1]
+    __device__ __forceinline__ void insert(float x, unsigned row) {
+#pragma unroll
+        for (int i = L - 1; i >= 1; --i) {
+            const bool above = x > s[i - 1];       // x ranks before slot i-1: slot i-1 moves down
+            const bool here = x > s[i];
+            s[i] = above ? s[i - 1] : (here ? x : s[i]);
+            r[i] = above ? r[i - 1] : (here ? row : r[i]);
+        }
+        const bool top = x > s[0];
+        s[0] = top ? x : s[0];
+        r[0] = top ? row : r[0];
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------
+template <int KB, int L, bool HAS_BIAS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
+    constexpr int BN = gemm_bn(KB);
+    constexpr int STAGES = gemm_stages(KB);
+    constexpr uint32_t A_KB_BYTES = GEMM_BM * 128;          // one K-block of the query block
+    constexpr uint32_t B_STAGE_BYTES = BN * 128;            // one K-block of a corpus tile
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+    constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM, BN);
+    static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
+    unsigned char *smA = sm;                                  // [KB][128 rows][128 B]
+    unsigned char *smB = sm + (size_t)KB * A_KB_BYTES;       // [STAGES][BN rows][128 B]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = p.qblock0 + blockIdx.x % p.n_qblocks, slice = blockIdx.x / p.n_qblocks;
+    const int t0 = (int)((long long)p.tiles_total * slice / p.n_slices);
+    const int t1 = (int)((long long)p.tiles_total * (slice + 1) / p.n_slices);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_x);
+        mbar_init(&bar_a, 1);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(&bar_a, KB * A_KB_BYTES);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(smA + (size_t)kb * A_KB_BYTES, &tm_q, &bar_a, kb * 64, qb * GEMM_BM);
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t0; t < t1; ++t) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&bar_full[stage], B_STAGE_BYTES);
+                    tma_load_2d(smB + (size_t)stage * B_STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            mbar_wait(&bar_a, 0);
+            tc_fence_after();
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t0, it = 0; t < t1; ++t, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&bar_full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t ad = umma_smem_desc(smem_u32(smA + (size_t)kb * A_KB_BYTES));
+                    const uint64_t bd = umma_smem_desc(smem_u32(smB + (size_t)stage * B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)      // UMMA_K = 16 bf16 = 32 B: +2 in the (>>4) address field
+                        umma_bf16_ss(d, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&bar_empty[stage]);                  // smem slot free once these MMAs retire
+                    if (kb == KB - 1) umma_commit(&bar_tfull[buf]);  // accumulator complete
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: thread = query, column = corpus row =====
+        const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
+        const int q = qb * GEMM_BM + quad * 32 + lane;
+        RegList<L> list; list.init();
+        float thr = -INFINITY;
+        unsigned g_seen = 0;
+        unsigned *gq = p.gthr + q;
+        for (int t = t0, it = 0; t < t1; ++t, ++it) {
+            const int buf = it & 1;
+            {   // the other slices' progress on this query
+                unsigned g = *reinterpret_cast<volatile unsigned *>(gq);
+                if (g > g_seen) { g_seen = g; thr = fmaxf(thr, KeyS::unord(g)); }
+            }
+            mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+            const unsigned row0 = (unsigned)t * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float v[32];
+                tmem_ld_x32(trow + c * 32, v);
+                const unsigned r0 = row0 + c * 32;
+                if (HAS_BIAS) {
+                    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + r0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 b = __ldg(b4 + j);
+                        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    }
+                }
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) any |= v[j] > thr;
+                if (__any_sync(FULL_MASK, any)) {
+                    unsigned hm = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) hm |= (v[j] > thr ? 1u : 0u) << j;
+                    unsigned wm = __reduce_or_sync(FULL_MASK, hm) & __ldg(p.pass_bits + (r0 >> 5));
+                    while (wm) {                                     // warp-uniform: columns somebody wants
+                        const int j = __ffs(wm) - 1;
+                        wm &= wm - 1;
+                        float x = tmem_ld_x1(trow + c * 32 + j);
+                        if (HAS_BIAS) x += __ldg(p.bias + r0 + j);
+                        if (x > thr) {
+                            list.insert(x, r0 + j);
+                            const float lmin = list.s[L - 1];
+                            if (lmin > -INFINITY) {                  // list full: its L-th best bounds everything rejected
+                                thr = fmaxf(thr, lmin);
+                                const unsigned o = KeyS::ord(lmin);
+                                if (o > g_seen) { atomicMax(gq, o); g_seen = o; }
+                            }
+                        }
+                        __syncwarp();                                // tcgen05.ld is warp-collective: reconverge
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+        }
+        if (q < p.nq) {
+            KeyS *dst = p.lists + (size_t)q * p.list_stride + (size_t)slice * L;
+#pragma unroll
+            for (int i = 0; i < L; ++i)
+                dst[i] = list.r[i] != 0xffffffffu ? KeyS::make(list.s[i], list.r[i]) : KeyS::worst();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------------------------
+// finalize: one CTA per query.  Fold the (slice) lists into the best KP by bf16 score, re-rank
+// them exactly, certify against max(KP-th best candidate score, final gthr[q]), emit.
+// ---------------------------------------------------------------------------------
+template <int EPL>
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, int list_stride, int entries_per_query,
+                      const unsigned *__restrict__ gthr, int q0) {
+    constexpr int KP = 32 * EPL;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KeyS *stage = reinterpret_cast<KeyS *>(smem_raw);                       // [FIN_WARPS*KP]
+    KeyD *sm_ex = reinterpret_cast<KeyD *>(stage + FIN_WARPS * KP);        // [KP]
+    KeyD *sm_misc = sm_ex + KP;                                            // [4]
+    float *sm_q = reinterpret_cast<float *>(sm_misc + 4);                  // [dp]
+    const int qi = q0 + blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int i = threadIdx.x; i < fin.dp; i += FIN_THREADS) sm_q[i] = fin.q[(size_t)qi * fin.dp + i];
+
+    WarpList<KeyS, EPL> wl; wl.init();
+    const KeyS *src = lists + (size_t)qi * list_stride;
+    for (int b = warp * 32; b < entries_per_query; b += FIN_WARPS * 32) {
+        const int idx = b + lane;
+        KeyS mine = idx < entries_per_query ? src[idx] : KeyS::worst();
+        unsigned hits = __ballot_sync(FULL_MASK, mine.valid() && wl.accepts(mine));
+        while (hits) {
+            const int s = __ffs(hits) - 1;
+            hits &= hits - 1;
+            wl.offer(KeyS::shfl(mine, s), lane);
+        }
+    }
+    __syncthreads();
+    cta_tree_merge<KeyS, EPL>(wl, stage, warp, lane);
+    int nvalid = 0;
+    for (int i = 0; i < KP; ++i) nvalid += stage[i].valid() ? 1 : 0;
+    // rows outside the candidate set: either in some list but below the KP-th candidate, or never
+    // kept by any list, hence <= the final shared bound (0 = nothing was ever rejected)
+    const unsigned g = gthr[qi];
+    float T = -INFINITY;
+    if (nvalid == KP) T = stage[KP - 1].score();
+    if (g != 0u) T = fmaxf(T, KeyS::unord(g));
+    finalize_candidates(fin, qi, stage, nvalid, T, sm_ex, sm_q, sm_misc);
+}
+
+inline size_t finalize_union_smem(int EPL, int dp) {
+    const int KP = 32 * EPL;
+    return sizeof(KeyS) * (size_t)FIN_WARPS * KP + sizeof(KeyD) * (KP + 4) + sizeof(float) * dp;
+}
+
+}  // namespace b2r

@@ -1,0 +1,152 @@
+// Instantiations + launch table for K3 (gemm.cuh) and the TMA tensor-map encoding.
+// Compiled once per supported K-block count (-DB2R_KB=...) plus a dispatcher unit.
+#include <map>
+#include <tuple>
+
+#include "engine.h"
+#include "gemm.cuh"
+
+namespace b2r {
+
+typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmParams);
+
+#ifdef B2R_KB
+#define B2R_CAT2(a, b) a##b
+#define B2R_CAT(a, b) B2R_CAT2(a, b)
+gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias) {
+    if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true> : gemm_topk_kernel<B2R_KB, 8, false>;
+    if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true> : gemm_topk_kernel<B2R_KB, 16, false>;
+    if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true> : gemm_topk_kernel<B2R_KB, 32, false>;
+    return nullptr;
+}
+}  // namespace b2r
+#else
+gemm_fn gemm_lookup_2(int, bool);
+gemm_fn gemm_lookup_4(int, bool);
+gemm_fn gemm_lookup_6(int, bool);
+gemm_fn gemm_lookup_8(int, bool);
+gemm_fn gemm_lookup_12(int, bool);
+
+// ---------------------------------------------------------------------------------
+// pass bitmap: bit r of word r>>5 = row r is live, passes the type mask and the allow bitmap.
+// Words cover [0, n_words*32); rows >= n get 0, so tile padding never scores.
+// ---------------------------------------------------------------------------------
+static __global__ void pass_bits_kernel(const uint8_t *__restrict__ type_code, unsigned long long type_mask,
+                                 const uint32_t *__restrict__ allow_bits, unsigned n, unsigned n_words,
+                                 uint32_t *__restrict__ out) {
+    const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned nthreads = gridDim.x * blockDim.x;
+    for (unsigned long long r = gt; r < (unsigned long long)n_words * 32; r += nthreads) {
+        bool ok = r < n && row_passes((unsigned)r, type_code, type_mask, allow_bits);
+        unsigned w = __ballot_sync(FULL_MASK, ok);
+        if ((threadIdx.x & 31) == 0) out[r >> 5] = w;
+    }
+}
+
+
+namespace {
+gemm_fn lookup(int kb, int L, bool bias) {
+    switch (kb) {
+        case 2:  return gemm_lookup_2(L, bias);
+        case 4:  return gemm_lookup_4(L, bias);
+        case 6:  return gemm_lookup_6(L, bias);     // all-MiniLM-L6-v2 (384)
+        case 8:  return gemm_lookup_8(L, bias);     // CLIP ViT-B/32 shape (512)
+        case 12: return gemm_lookup_12(L, bias);    // 768
+        default: return nullptr;
+    }
+}
+size_t smem_of(int kb) {
+    switch (kb) {
+        case 2:  return gemm_smem_bytes(2);
+        case 4:  return gemm_smem_bytes(4);
+        case 6:  return gemm_smem_bytes(6);
+        case 8:  return gemm_smem_bytes(8);
+        case 12: return gemm_smem_bytes(12);
+        default: return 0;
+    }
+}
+
+typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_fn get_encode() {
+    static encode_fn fn = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    if (fn) return fn;
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !sym) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    fn = reinterpret_cast<encode_fn>(sym);
+    return fn;
+}
+}  // namespace
+
+int gemm_list_len(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 0; }
+int gemm_tile_rows(int dp) { return gemm_bn(dp / 64); }
+bool gemm_supported(int dp, int k) { return dp % 64 == 0 && lookup(dp / 64, 8, false) != nullptr && gemm_list_len(k) != 0; }
+
+// [rows, dp] bf16 row-major -> 2-D tensor map, box = 64 elements (128 B, one swizzle row) x box_rows
+int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, int box_rows) {
+    encode_fn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return B2R_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)dp, rows ? rows : 1};
+    cuuint64_t strides[1] = {(cuuint64_t)dp * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r)); return B2R_ECUDA; }
+    return B2R_OK;
+}
+
+cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
+                        const GemmParams &p, cudaStream_t s) {
+    const int kb = dp / 64;
+    gemm_fn f = lookup(kb, L, bias);
+    if (!f) return cudaErrorInvalidValue;
+    const size_t smem = smem_of(kb);
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void *>, bool> done;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> g(mu);
+        auto key = std::make_tuple(dev, (const void *)f);
+        if (!done.count(key)) {
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            done[key] = true;
+        }
+    }
+    f<<<p.n_slices * p.n_qblocks, GEMM_THREADS, smem, s>>>(tm_q, tm_x, p);
+    return cudaGetLastError();
+}
+
+cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_mask, const uint32_t *allow_bits,
+                             unsigned n, unsigned n_words, uint32_t *out, int sm_count, cudaStream_t s) {
+    unsigned blocks = (unsigned)std::min<unsigned long long>(((unsigned long long)n_words * 32 + 255) / 256,
+                                                             (unsigned long long)sm_count * 8);
+    if (blocks == 0) blocks = 1;
+    pass_bits_kernel<<<blocks, 256, 0, s>>>(type_code, type_mask, allow_bits, n, n_words, out);
+    return cudaGetLastError();
+}
+
+cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
+                                  int entries_per_query, const unsigned *gthr, int q0, int nq, cudaStream_t s) {
+    const size_t smem = finalize_union_smem(epl, fin.dp);
+    switch (epl) {
+        case 1: finalize_union_kernel<1><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, q0); break;
+        case 2: finalize_union_kernel<2><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, q0); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace b2r
+#endif  // B2R_KB
