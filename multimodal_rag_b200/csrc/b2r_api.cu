@@ -128,12 +128,14 @@ extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device,
     int rc = B2R_OK;
     do {
         if (cudaMalloc(&h->max_norm2, 256) != cudaSuccess || cudaMalloc(&h->counters, 256) != cudaSuccess ||
-            cudaMalloc(&h->tickets, sizeof(unsigned) * (1 + EXACT_MAX_BATCH)) != cudaSuccess) {
+            cudaMalloc(&h->tickets, sizeof(unsigned) * (1 + 2 * EXACT_MAX_BATCH)) != cudaSuccess ||
+            cudaMalloc(&h->need_ctl, 16) != cudaSuccess) {
             set_error("b2r_create: cudaMalloc failed"); rc = B2R_ENOMEM; break;
         }
         cudaMemset(h->max_norm2, 0, 256);
         cudaMemset(h->counters, 0, 256);
-        cudaMemset(h->tickets, 0, sizeof(unsigned) * (1 + EXACT_MAX_BATCH));
+        cudaMemset(h->tickets, 0, sizeof(unsigned) * (1 + 2 * EXACT_MAX_BATCH));
+        cudaMemset(h->need_ctl, 0, 16);
         rc = grow(h, std::max<int64_t>(capacity_rows, 1024), 0);
     } while (0);
     if (rc != B2R_OK) { b2r_destroy(h); return rc; }
@@ -146,9 +148,9 @@ extern "C" int b2r_destroy(b2r_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     cudaFree(h->corpus); cudaFree(h->master); cudaFree(h->bias); cudaFree(h->type_code);
-    cudaFree(h->max_norm2); cudaFree(h->counters); cudaFree(h->tickets);
+    cudaFree(h->max_norm2); cudaFree(h->counters); cudaFree(h->tickets); cudaFree(h->need_ctl);
     DevBuf *bufs[] = {&h->x_stage, &h->t_stage, &h->q_raw, &h->q_prep, &h->allow, &h->rows_stage, &h->gather_out,
-                      &h->o_rows, &h->o_dist, &h->o_dist64, &h->o_count, &h->need_exact, &h->scan_lists,
+                      &h->o_rows, &h->o_dist, &h->o_dist64, &h->o_count, &h->need_list, &h->scan_lists,
                       &h->exact_lists, &h->q_bf16, &h->pass_bits, &h->gthr, &h->gemm_lists};
     for (DevBuf *b : bufs) release(*b);
     for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -162,7 +164,7 @@ extern "C" int b2r_clear(b2r_handle h) {
     std::lock_guard<std::mutex> g(h->mu);
     B2R_CUDA(cudaSetDevice(h->device));
     B2R_CUDA(cudaDeviceSynchronize());
-    h->rows = 0; h->live = 0;
+    h->rows = 0; h->live = 0; h->mut_gen++;
     B2R_CUDA(cudaMemset(h->max_norm2, 0, 4));
     return B2R_OK;
 }
@@ -281,7 +283,7 @@ extern "C" int b2r_ingest_f32(b2r_handle h, const float *x, int64_t n, const uin
     B2R_CUDA(cudaGetLastError());
     h->n_launches++;
     if (xd != x || td != type_code) B2R_CUDA(cudaStreamSynchronize(s));   // staging buffers are reused
-    h->rows += n; h->live += n;
+    h->rows += n; h->live += n; h->mut_gen++;
     return B2R_OK;
 }
 
@@ -306,6 +308,7 @@ extern "C" int b2r_tombstone(b2r_handle h, const int64_t *rows, int64_t n, void 
     B2R_CUDA(cudaMemcpyAsync(&after, h->counters, 8, cudaMemcpyDeviceToHost, s));
     B2R_CUDA(cudaStreamSynchronize(s));
     h->live -= (int64_t)(after - before);
+    h->mut_gen++;
     return B2R_OK;
 }
 
@@ -391,25 +394,24 @@ int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const Finaliz
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps_needed + EXACT_WARPS - 1) / EXACT_WARPS, max_grid));
     int rc = ensure(h->exact_lists, sizeof(KeyD) * (size_t)EXACT_MAX_BATCH * max_grid * 32 * epl);
     if (rc != B2R_OK) return rc;
-    for (int q0 = 0; q0 < nq; q0 += EXACT_MAX_BATCH) {
-        ExactParams p;
-        p.type_code = h->type_code; p.allow_bits = allow_dev; p.type_mask = f.type_mask;
-        p.n = (unsigned)h->rows; p.q0 = q0; p.nq = std::min(EXACT_MAX_BATCH, nq - q0); p.force_all = force_all;
-        p.cta_lists = (KeyD *)h->exact_lists.p; p.tickets = h->tickets + 1;
-        p.n_fallbacks = (long long *)(h->counters + 1);
-        p.fin = fin;
-        KernelTimer kt(h, s);
-        if (!force_all) kt.on = false;      // the certificate fix-up is not the scoring kernel
-        B2R_CUDA(exact_launch(epl, p, grid, s));
-        kt.stop();
-        h->n_launches++;
-    }
+    ExactParams p;
+    p.type_code = h->type_code; p.allow_bits = allow_dev; p.type_mask = f.type_mask;
+    p.n = (unsigned)h->rows; p.nq = nq; p.force_all = force_all;
+    p.cta_lists = (KeyD *)h->exact_lists.p; p.tickets = h->tickets + 1;
+    p.n_fallbacks = (long long *)(h->counters + 1);
+    p.fin = fin;
+    KernelTimer kt(h, s);
+    if (!force_all) kt.on = false;      // the certificate fix-up is not the scoring kernel
+    B2R_CUDA(exact_launch(epl, p, grid, s));
+    kt.stop();
+    h->n_launches++;
     return B2R_OK;
 }
 
 // K3: pass bitmap -> tcgen05 scoring + per-(query, slice) lists -> per-query finalize
 constexpr int GEMM_MIN_BATCH = 5;        // below this the scan reads the corpus at most twice anyway
 constexpr int GEMM_MAX_QBLOCKS = 8;      // 128-query blocks per launch (1024 queries per corpus pass)
+constexpr int GEMM_SAMPLE_TILES = 128;   // tiles of the threshold-seeding sample (32k rows at BN = 256)
 
 int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams &fin, const b2r_filter &f,
                       const uint32_t *allow_dev, cudaStream_t s) {
@@ -418,15 +420,24 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
     const int tiles_total = (int)((h->rows + BN - 1) / BN);
     const unsigned n_words = (unsigned)tiles_total * (unsigned)(BN / 32);
     const int qblocks_total = (nq + GEMM_BM - 1) / GEMM_BM;
-    const int list_stride = h->sm_count * L;
+    const int list_stride = h->sm_count * GEMM_HALVES * L;
     int rc;
     if ((rc = ensure(h->pass_bits, (size_t)n_words * 4 + 16)) != B2R_OK) return rc;
-    if ((rc = ensure(h->gthr, (size_t)qblocks_total * GEMM_BM * 4)) != B2R_OK) return rc;
+    {   // gthr is all-zero between calls: zeroed when (re)allocated, and finalize_union_kernel clears what it read
+        const void *before = h->gthr.p;
+        if ((rc = ensure(h->gthr, (size_t)qblocks_total * GEMM_BM * 4)) != B2R_OK) return rc;
+        if (h->gthr.p != before) B2R_CUDA(cudaMemsetAsync(h->gthr.p, 0, h->gthr.bytes, s));
+    }
     if ((rc = ensure(h->gemm_lists, sizeof(KeyS) * (size_t)nq * list_stride)) != B2R_OK) return rc;
-    B2R_CUDA(cudaMemsetAsync(h->gthr.p, 0, (size_t)qblocks_total * GEMM_BM * 4, s));
-    B2R_CUDA(pass_bits_launch(h->type_code, f.type_mask, allow_dev, (unsigned)h->rows, n_words,
-                              (uint32_t *)h->pass_bits.p, h->sm_count, s));
-    h->n_launches++;
+    const bool pb_hit = !allow_dev && h->pb_buf == h->pass_bits.p && h->pb_gen == h->mut_gen && h->pb_rows == h->rows &&
+                        h->pb_mask == f.type_mask && h->pb_bn == BN;
+    if (!pb_hit) {
+        B2R_CUDA(pass_bits_launch(h->type_code, f.type_mask, allow_dev, (unsigned)h->rows, n_words,
+                                  (uint32_t *)h->pass_bits.p, h->sm_count, s));
+        h->n_launches++;
+        h->pb_buf = allow_dev ? nullptr : h->pass_bits.p;
+        h->pb_gen = h->mut_gen; h->pb_rows = h->rows; h->pb_mask = f.type_mask; h->pb_bn = BN;
+    }
     if (h->tm_corpus_base != h->corpus || h->tm_corpus_rows != h->capacity) {
         if ((rc = gemm_encode_map(&h->tm_corpus, h->corpus, h->dp, (uint64_t)h->capacity, BN)) != B2R_OK) return rc;
         h->tm_corpus_base = h->corpus; h->tm_corpus_rows = h->capacity;
@@ -435,20 +446,30 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         if ((rc = gemm_encode_map(&h->tm_query, h->q_bf16.p, h->dp, (uint64_t)nq, GEMM_BM)) != B2R_OK) return rc;
         h->tm_query_base = h->q_bf16.p; h->tm_query_rows = nq;
     }
+    // sampling pass: GEMM_SAMPLE_TILES tiles strided across the shard seed gthr[q] (skipped for small shards)
+    const int sample_tiles = tiles_total >= 2 * GEMM_SAMPLE_TILES ? GEMM_SAMPLE_TILES : 0;
     for (int qb0 = 0; qb0 < qblocks_total; qb0 += GEMM_MAX_QBLOCKS) {
         GemmParams gp;
         gp.n = (unsigned)h->rows; gp.nq = nq; gp.qblock0 = qb0;
         gp.n_qblocks = std::min(GEMM_MAX_QBLOCKS, qblocks_total - qb0);
-        gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, tiles_total));
-        gp.list_stride = list_stride; gp.tiles_total = tiles_total;
+        gp.list_stride = list_stride;
         gp.pass_bits = (const uint32_t *)h->pass_bits.p; gp.bias = h->bias;
         gp.gthr = (unsigned *)h->gthr.p; gp.lists = (KeyS *)h->gemm_lists.p;
+        const int q0 = qb0 * GEMM_BM, nq_here = std::min(nq - q0, gp.n_qblocks * GEMM_BM);
+        if (sample_tiles) {
+            gp.tiles_total = sample_tiles; gp.tile_mul = tiles_total / sample_tiles;
+            gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, sample_tiles));
+            B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
+            B2R_CUDA(sample_threshold_launch(gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, L, gp.gthr, q0, nq_here, s));
+            h->n_launches += 2;
+        }
+        gp.tiles_total = tiles_total; gp.tile_mul = 1;
+        gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, tiles_total));
         KernelTimer kt(h, s);
         B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
         kt.stop();
         h->n_launches++;
-        const int q0 = qb0 * GEMM_BM, nq_here = std::min(nq - q0, gp.n_qblocks * GEMM_BM);
-        B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, gp.n_slices * L, gp.gthr, q0, nq_here, s));
+        B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, gp.gthr, q0, nq_here, s));
         h->n_launches++;
     }
     return B2R_OK;
@@ -491,7 +512,7 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
         allow_dev = (const uint32_t *)h->allow.p;
     }
     if ((rc = ensure(h->q_prep, (size_t)nq * h->dp * 4)) != B2R_OK) return rc;
-    if ((rc = ensure(h->need_exact, (size_t)nq * 4)) != B2R_OK) return rc;
+    if ((rc = ensure(h->need_list, (size_t)nq * 4)) != B2R_OK) return rc;
     long long *o_rows = (long long *)out_rows; float *o_dist = out_dist; double *o_dist64 = out_dist64; int *o_count = out_count;
     if (!dev_out) {
         if ((rc = ensure(h->o_rows, (size_t)nq * k * 8)) != B2R_OK) return rc;
@@ -537,7 +558,7 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     fin.master = h->master; fin.corpus = h->corpus; fin.q = (const float *)h->q_prep.p;
     fin.max_norm2 = h->max_norm2; fin.dp = h->dp; fin.space = h->space; fin.k = k;
     fin.row_base = h->row_base; fin.out_rows = o_rows; fin.out_dist = o_dist; fin.out_dist64 = o_dist64;
-    fin.out_count = o_count; fin.need_exact = (int *)h->need_exact.p;
+    fin.out_count = o_count; fin.need_ctl = h->need_ctl; fin.need_list = (int *)h->need_list.p;
     // |scan score - exact score| <= eps_rel * |q| * max|x| (+ small abs term, finalize_candidates).
     // Corpus rounded to bf16: unit roundoff 2^-8 (only counts when the exact answer is defined on the
     // fp32 master).  K2 keeps the query in fp32 and accumulates in fp32: (dp+8) * 2^-24.  K3 also rounds

@@ -50,8 +50,10 @@ cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const
                         const GemmParams &p, cudaStream_t s);
 cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_mask, const uint32_t *allow_bits,
                              unsigned n, unsigned n_words, uint32_t *out, int sm_count, cudaStream_t s);
+cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
+                                    int q0, int nq, cudaStream_t s);
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
-                                  int entries_per_query, const unsigned *gthr, int q0, int nq, cudaStream_t s);
+                                  int entries_per_query, unsigned *gthr, int q0, int nq, cudaStream_t s);
 
 struct DevBuf {
     void *p = nullptr;
@@ -79,7 +81,8 @@ struct b2r_index {
 
     // scratch (device), grown on demand
     b2r::DevBuf x_stage, t_stage, q_raw, q_prep, allow, rows_stage, gather_out;
-    b2r::DevBuf o_rows, o_dist, o_dist64, o_count, need_exact;
+    b2r::DevBuf o_rows, o_dist, o_dist64, o_count, need_list;
+    int *need_ctl = nullptr;        // [4]: failed-certificate count, exit ticket (reset by K5 itself)
     b2r::DevBuf scan_lists, exact_lists;
     b2r::DevBuf q_bf16, pass_bits, gthr, gemm_lists;   // K3 scratch
 
@@ -87,7 +90,9 @@ struct b2r_index {
     CUtensorMap tm_corpus, tm_query;
     const void *tm_corpus_base = nullptr; int64_t tm_corpus_rows = -1;
     const void *tm_query_base = nullptr; int64_t tm_query_rows = -1;
-    unsigned *tickets = nullptr;    // [1 + EXACT_MAX_BATCH]
+    // the pass bitmap is reused while (rows, type mask, tombstones) are unchanged and no allow bitmap is given
+    int64_t mut_gen = 0, pb_gen = -1, pb_rows = -1; unsigned long long pb_mask = 0; const void *pb_buf = nullptr; int pb_bn = 0;
+    unsigned *tickets = nullptr;    // [1 + 2*EXACT_MAX_BATCH]: scan ticket, exact tickets, exact slot generations
 
     // optional per-kernel timing (bench.py roofline): CUDA events recorded around the scoring
     // kernel launches on the caller's stream, resolved lazily by b2r_kernel_time_ms

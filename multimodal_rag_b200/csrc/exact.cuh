@@ -1,8 +1,9 @@
 // K5: exact fp64 scan.  Reads the stored fp32 rows (or the bf16 rows when the handle
 // keeps no fp32 master), accumulates every distance in fp64 and selects on
 // (distance, row) directly, so its answer needs no certificate.  It is the always-correct
-// fallback for queries whose bf16 candidate certificate failed (need_exact[q] != 0), and
-// the forced path for tests (mode 1 = every query).  One query at a time, whole grid.
+// fallback for queries whose bf16 candidate certificate failed (fin.need_list), and the forced
+// path for shapes the fast kernels are not built for.  One query at a time, whole grid; a launch
+// with an empty work list costs one L2 read per CTA.
 #pragma once
 #include "common.cuh"
 #include "finalize.cuh"
@@ -18,10 +19,10 @@ struct ExactParams {
     const uint32_t *allow_bits;
     unsigned long long type_mask;
     unsigned n;
-    int q0, nq;                   // queries [q0, q0+nq) of the batch; nq <= EXACT_MAX_BATCH
-    int force_all;                // 1: ignore need_exact and redo every query
-    KeyD *cta_lists;              // [EXACT_MAX_BATCH][gridDim.x][KP]: one slot per query, never reused in a launch
-    unsigned *tickets;            // [EXACT_MAX_BATCH]
+    int nq;                       // queries in the batch
+    int force_all;                // 1: redo every query of the batch; 0: only fin.need_list[0 .. need_ctl[0])
+    KeyD *cta_lists;              // [EXACT_MAX_BATCH][gridDim.x][KP]: slot = work item % EXACT_MAX_BATCH
+    unsigned *tickets;            // [EXACT_MAX_BATCH] arrival tickets, then [EXACT_MAX_BATCH] slot generations
     long long *n_fallbacks;       // device counter (may be nullptr)
     FinalizeParams fin;
 };
@@ -37,10 +38,20 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
     float *sm_q = reinterpret_cast<float *>(sm_misc + 4);              // [dp]
     __shared__ unsigned s_ticket;
 
-    for (int qs = 0; qs < p.nq; ++qs) {
-        const int qi = p.q0 + qs;
-        KeyD *my_lists = p.cta_lists + (size_t)qs * gridDim.x * KP;
-        if (!p.force_all && __ldcg(&p.fin.need_exact[qi]) == 0) continue;   // CTA-uniform
+    // Work list: every query (forced) or the compacted list of failed certificates.  The grid is
+    // sized to be fully resident, so waiting on another CTA's progress below cannot deadlock.
+    int count = p.force_all ? p.nq : min(__ldcg(&p.fin.need_ctl[0]), p.nq);
+    unsigned *slot_gen = p.tickets + EXACT_MAX_BATCH;
+    for (int it = 0; it < count; ++it) {
+        const int qi = p.force_all ? it : __ldcg(&p.fin.need_list[it]);
+        const int slot = it % EXACT_MAX_BATCH;
+        const unsigned gen = (unsigned)(it / EXACT_MAX_BATCH);
+        KeyD *my_lists = p.cta_lists + (size_t)slot * gridDim.x * KP;
+        if (gen > 0) {      // the slot's previous user must have been merged before its lists are overwritten
+            if (threadIdx.x == 0)
+                while (*reinterpret_cast<volatile unsigned *>(&slot_gen[slot]) < gen) __nanosleep(200);
+            __threadfence();
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < dp; i += EXACT_THREADS) sm_q[i] = p.fin.q[(size_t)qi * dp + i];
         __syncthreads();
@@ -57,7 +68,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
         if (warp == 0) wl.store(my_lists + (size_t)blockIdx.x * KP, lane);
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[qs], 1u);
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[slot], 1u);
         __syncthreads();
         if (s_ticket == gridDim.x - 1) {
             // ---- last CTA for this query: fold all CTA lists, emit ----
@@ -75,13 +86,24 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
             int nvalid = 0;
             for (int i = 0; i < KP; ++i) nvalid += sm_keys[i].valid() ? 1 : 0;
             emit_sorted(p.fin, qi, sm_keys, nvalid, &sm_misc[0]);
+            __syncthreads();
             if (threadIdx.x == 0) {
-                p.tickets[qs] = 0u;
+                p.tickets[slot] = 0u;
                 if (!p.force_all && p.n_fallbacks) atomicAdd((unsigned long long *)p.n_fallbacks, 1ull);
-                p.fin.need_exact[qi] = 0;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned *>(&slot_gen[slot]) = gen + 1;
             }
         }
         __syncthreads();
+    }
+    // ---- leave the control block clean for the next call (last CTA out) ----
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd((unsigned *)&p.fin.need_ctl[1], 1u) == gridDim.x - 1) {
+            for (int i = 0; i < EXACT_MAX_BATCH; ++i) slot_gen[i] = 0u;
+            p.fin.need_ctl[0] = 0;
+            p.fin.need_ctl[1] = 0;
+        }
     }
 }
 

@@ -21,7 +21,8 @@ struct FinalizeParams {
     float *out_dist;            // [nq, k]
     double *out_dist64;         // [nq, k] or nullptr
     int *out_count;             // [nq]
-    int *need_exact;            // [nq]: 1 = certificate failed, exact scan must redo it
+    int *need_ctl;              // [0] = number of queries whose certificate failed (this call), [1] = exit ticket
+    int *need_list;             // [nq]: those queries, in arrival order; the exact scan (K5) redoes them
     float eps_rel;              // |score_scan - score_exact| <= eps_rel * |q| * max|x| (+ small abs term)
 };
 
@@ -125,7 +126,7 @@ __device__ __forceinline__ void finalize_candidates(const FinalizeParams &p, int
             else s_k = 1.0 - kth.d;
             flag = (s_k - eps > (double)T) ? 0 : 1;
         }
-        if (lane == 0) p.need_exact[qi] = flag;
+        if (lane == 0 && flag) p.need_list[atomicAdd(&p.need_ctl[0], 1)] = qi;
     }
     __syncthreads();
 }

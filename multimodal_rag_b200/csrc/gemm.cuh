@@ -6,10 +6,11 @@
 //              through a STAGES-deep TMA/mbarrier ring
 //   D          128 x BN fp32 scores in TMEM, double buffered (2*BN columns) so the tensor pipe fills
 //              tile t+1 while the epilogue drains tile t
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 =
-// epilogue.  In TMEM a lane is a query and a column is a corpus row, so every epilogue thread owns ONE
-// query: it streams that query's scores through a single compare against a private threshold and keeps
-// the best L rows of its slice in a register-resident sorted list.  The threshold is
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..9 =
+// epilogue, two per SM sub-partition so one hides the other's latencies.  In TMEM a lane is a query and a
+// column is a corpus row, so every epilogue thread owns ONE query (and one half of each tile's columns):
+// it streams that query's scores through a max-tree + one compare against a private threshold and keeps
+// the best L rows it has seen in a register-resident sorted list.  The threshold is
 // max(own L-th best, shared per-query bound): whenever a thread's list is full it publishes its L-th
 // best score to gthr[q] (atomicMax); all slices of the same query read it once per tile, so the
 // admission rate falls with the rows seen by the WHOLE grid, not by one slice.
@@ -27,8 +28,9 @@
 namespace b2r {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_EPI_WARP0 = 2;
+constexpr int GEMM_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_HALVES = 2;          // epilogue warps w and w+4 share a TMEM lane quadrant and split a tile's columns
 constexpr int GEMM_SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA
 constexpr int GEMM_SMEM_SLACK = 1024 + 512;   // manual 1024-byte alignment + static barriers
 
@@ -37,12 +39,13 @@ struct GemmParams {
     int nq;                      // queries in the batch
     int qblock0;                 // first 128-query block of this launch (batches > 8 blocks are chunked)
     int n_qblocks, n_slices;     // grid = n_slices * n_qblocks (blockIdx = slice * n_qblocks + qblock)
-    int list_stride;             // KeyS entries reserved per query in `lists` (>= n_slices * L)
-    int tiles_total;             // ceil(n / BN)
+    int list_stride;             // KeyS entries reserved per query in `lists` (>= n_slices * 2 * L)
+    int tiles_total;             // tiles this launch covers (main pass: ceil(n / BN); sampling pass: the sample size)
+    int tile_mul;                // launch tile t is corpus tile t * tile_mul (1 = main pass; > 1 = strided sample)
     const uint32_t *pass_bits;   // bit r = row r is live and passes the filter; 0 for r >= n
     const float *bias;           // [n] -|x|^2/2 (l2) or nullptr
     unsigned *gthr;              // [n_qblocks*128] shared per-query bound, KeyS::ord encoding, 0 = none yet
-    KeyS *lists;                 // [nq][list_stride]: slice s of query q at q*list_stride + s*L
+    KeyS *lists;                 // [nq][list_stride]: (slice s, half h) of query q at q*list_stride + (2s+h)*L
 };
 
 __host__ __device__ constexpr int gemm_bn(int KB) { return KB <= 8 ? 256 : 128; }
@@ -133,27 +136,27 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (lane = thread)
-__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (lane = thread).  The load is
+// asynchronous: v[] is defined only after tmem_ld_wait(v), which also pins the compiler's ordering.
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        "tcgen05.wait::ld.sync.aligned;\n"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float tmem_ld_x1(uint32_t taddr) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\ntcgen05.wait::ld.sync.aligned;\n"
-                 : "=r"(r) : "r"(taddr) : "memory");
-    return __uint_as_float(r);
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
 }
 
 // ---------------------------------------------------------------------------------
@@ -181,6 +184,76 @@ struct RegList {
         r[0] = top ? row : r[0];
     }
 };
+
+// One epilogue step: 32 scores of this thread's query (columns r0 .. r0+31 of the corpus).
+// Hot path: a max tree (log depth -- a single resident warp per scheduler cannot hide serial chains)
+// and one compare.  When any lane of the warp has a hit, every lane walks its own hits lowest column
+// first and ALL hitting lanes insert simultaneously (one insert site), so a step costs the max over
+// lanes of the hits, not their sum.
+template <int L, bool HAS_BIAS>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&raw)[32], unsigned r0, const GemmParams &p, RegList<L> &list,
+                                          float &thr, unsigned &g_seen, unsigned *gq, bool publish) {
+    const unsigned pm = __ldg(p.pass_bits + (r0 >> 5));   // issued early, consumed only on the slow path
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+    if (HAS_BIAS) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + r0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+    }
+    float m8[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float a = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
+        const float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
+        m8[g] = fmaxf(a, b);
+    }
+    const float m32 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+    if (!__any_sync(FULL_MASK, m32 > thr)) return;
+    // ---- slow path ----
+    unsigned hm = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (m8[g] > thr) {
+            unsigned b = 0;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) b |= (v[8 * g + t] > thr ? 1u : 0u) << t;
+            hm |= b << (8 * g);
+        }
+    }
+    hm &= pm;                                            // dead / filtered / padding rows never enter
+    while (__any_sync(FULL_MASK, hm != 0u)) {
+        if (hm) {
+            const int j = __ffs(hm) - 1;
+            hm &= hm - 1;
+            // x = v[j] by a 5-level select tree on the bits of j (depth 5, not a 31-deep chain)
+            float w16[16], w8[8], w4[4], w2[2];
+            const bool b4 = j & 16, b3 = j & 8, b2 = j & 4, b1 = j & 2, b0 = j & 1;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w16[i] = b4 ? v[16 + i] : v[i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w8[i] = b3 ? w16[8 + i] : w16[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w4[i] = b2 ? w8[4 + i] : w8[i];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) w2[i] = b1 ? w4[2 + i] : w4[i];
+            const float x = b0 ? w2[1] : w2[0];
+            if (x > thr) {
+                list.insert(x, r0 + j);
+                const float lmin = list.s[L - 1];
+                if (lmin > -INFINITY) {                  // list full: its L-th best bounds everything it rejects
+                    thr = fmaxf(thr, lmin);
+                    const unsigned o = KeyS::ord(lmin);
+                    if (o > g_seen) { if (publish) atomicMax(gq, o); g_seen = o; }
+                }
+            }
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------
 // the kernel
@@ -216,7 +289,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tma_prefetch_desc(&tm_x);
         mbar_init(&bar_a, 1);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], GEMM_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
@@ -235,7 +308,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     mbar_expect_tx(&bar_full[stage], B_STAGE_BYTES);
-                    tma_load_2d(smB + (size_t)stage * B_STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * BN);
+                    tma_load_2d(smB + (size_t)stage * B_STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * p.tile_mul * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -267,60 +340,37 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
     } else {
         // ===== epilogue: thread = query, column = corpus row =====
+        constexpr int NC = BN / 32 / GEMM_HALVES;                    // 32-column steps per tile per warp
+        static_assert(NC % 2 == 0, "steps are processed in double-buffered pairs");
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;                            // which half of a tile's columns
         const int q = qb * GEMM_BM + quad * 32 + lane;
+        const bool publish = q < p.nq;
         RegList<L> list; list.init();
         float thr = -INFINITY;
         unsigned g_seen = 0;
         unsigned *gq = p.gthr + q;
+        unsigned g_next = *reinterpret_cast<volatile unsigned *>(gq);   // seeded by the sampling pass
         for (int t = t0, it = 0; t < t1; ++t, ++it) {
             const int buf = it & 1;
-            {   // the other slices' progress on this query
-                unsigned g = *reinterpret_cast<volatile unsigned *>(gq);
-                if (g > g_seen) { g_seen = g; thr = fmaxf(thr, KeyS::unord(g)); }
-            }
+            if (g_next > g_seen) { g_seen = g_next; thr = fmaxf(thr, KeyS::unord(g_next)); }
             mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
-            const unsigned row0 = (unsigned)t * BN;
+            // the other slices' progress on this query: loaded now, consumed at the top of the next tile
+            g_next = *reinterpret_cast<volatile unsigned *>(gq);
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * NC * 32);
+            const unsigned row0 = (unsigned)(t * p.tile_mul) * BN + (unsigned)(half * NC * 32);
+            uint32_t va[32], vb[32];
+            tmem_ld_x32(trow, va);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                float v[32];
-                tmem_ld_x32(trow + c * 32, v);
-                const unsigned r0 = row0 + c * 32;
-                if (HAS_BIAS) {
-                    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + r0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 b = __ldg(b4 + j);
-                        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-                    }
-                }
-                bool any = false;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) any |= v[j] > thr;
-                if (__any_sync(FULL_MASK, any)) {
-                    unsigned hm = 0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) hm |= (v[j] > thr ? 1u : 0u) << j;
-                    unsigned wm = __reduce_or_sync(FULL_MASK, hm) & __ldg(p.pass_bits + (r0 >> 5));
-                    while (wm) {                                     // warp-uniform: columns somebody wants
-                        const int j = __ffs(wm) - 1;
-                        wm &= wm - 1;
-                        float x = tmem_ld_x1(trow + c * 32 + j);
-                        if (HAS_BIAS) x += __ldg(p.bias + r0 + j);
-                        if (x > thr) {
-                            list.insert(x, r0 + j);
-                            const float lmin = list.s[L - 1];
-                            if (lmin > -INFINITY) {                  // list full: its L-th best bounds everything rejected
-                                thr = fmaxf(thr, lmin);
-                                const unsigned o = KeyS::ord(lmin);
-                                if (o > g_seen) { atomicMax(gq, o); g_seen = o; }
-                            }
-                        }
-                        __syncwarp();                                // tcgen05.ld is warp-collective: reconverge
-                    }
-                }
+            for (int c = 0; c < NC; c += 2) {            // two register buffers: the next load flies under this step
+                tmem_ld_wait(va);
+                tmem_ld_x32(trow + (c + 1) * 32, vb);
+                epi_chunk<L, HAS_BIAS>(va, row0 + c * 32, p, list, thr, g_seen, gq, publish);
+                __syncwarp();
+                tmem_ld_wait(vb);
+                if (c + 2 < NC) tmem_ld_x32(trow + (c + 2) * 32, va);
+                epi_chunk<L, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
             }
             tc_fence_before();
@@ -328,7 +378,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (lane == 0) mbar_arrive(&bar_tempty[buf]);
         }
         if (q < p.nq) {
-            KeyS *dst = p.lists + (size_t)q * p.list_stride + (size_t)slice * L;
+            KeyS *dst = p.lists + (size_t)q * p.list_stride + (size_t)(slice * GEMM_HALVES + half) * L;
 #pragma unroll
             for (int i = 0; i < L; ++i)
                 dst[i] = list.r[i] != 0xffffffffu ? KeyS::make(list.s[i], list.r[i]) : KeyS::worst();
@@ -341,13 +391,40 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------
+// sampling pass epilogue: one warp per query folds that query's sample lists and seeds the shared
+// bound with the L-th best sampled score -- a real row's score, so at least L rows are >= it and
+// nothing that scores below it can be among the L best of the shard.
+// ---------------------------------------------------------------------------------
+template <int DUMMY>
+__global__ void __launch_bounds__(256) sample_threshold_kernel(const KeyS *__restrict__ lists, int list_stride,
+                                                               int entries_per_query, int L, unsigned *gthr, int q0, int nq) {
+    const int lane = threadIdx.x & 31;
+    const int qi = q0 + blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (qi >= q0 + nq) return;
+    WarpList<KeyS, 1> wl; wl.init();
+    const KeyS *src = lists + (size_t)qi * list_stride;
+    for (int b = 0; b < entries_per_query; b += 32) {
+        const int idx = b + lane;
+        KeyS mine = idx < entries_per_query ? src[idx] : KeyS::worst();
+        unsigned hits = __ballot_sync(FULL_MASK, mine.valid() && wl.accepts(mine));
+        while (hits) {
+            const int sl = __ffs(hits) - 1;
+            hits &= hits - 1;
+            wl.offer(KeyS::shfl(mine, sl), lane);
+        }
+    }
+    const KeyS kth = KeyS::shfl(wl.key[0], L - 1);        // EPL = 1: rank r lives in lane r
+    if (lane == 0 && kth.valid()) atomicMax(&gthr[qi], KeyS::ord(kth.score()));
+}
+
+// ---------------------------------------------------------------------------------
 // finalize: one CTA per query.  Fold the (slice) lists into the best KP by bf16 score, re-rank
 // them exactly, certify against max(KP-th best candidate score, final gthr[q]), emit.
 // ---------------------------------------------------------------------------------
 template <int EPL>
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, int list_stride, int entries_per_query,
-                      const unsigned *__restrict__ gthr, int q0) {
+                      unsigned *__restrict__ gthr, int q0) {
     constexpr int KP = 32 * EPL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyS *stage = reinterpret_cast<KeyS *>(smem_raw);                       // [FIN_WARPS*KP]
@@ -378,6 +455,8 @@ finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, 
     // rows outside the candidate set: either in some list but below the KP-th candidate, or never
     // kept by any list, hence <= the final shared bound (0 = nothing was ever rejected)
     const unsigned g = gthr[qi];
+    __syncthreads();
+    if (threadIdx.x == 0) gthr[qi] = 0u;                 // leave the shared bounds clean for the next call
     float T = -INFINITY;
     if (nvalid == KP) T = stage[KP - 1].score();
     if (g != 0u) T = fmaxf(T, KeyS::unord(g));

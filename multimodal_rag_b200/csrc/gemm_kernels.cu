@@ -137,8 +137,14 @@ cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_m
     return cudaGetLastError();
 }
 
+cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
+                                    int q0, int nq, cudaStream_t s) {
+    sample_threshold_kernel<0><<<(nq + 7) / 8, 256, 0, s>>>(lists, list_stride, entries_per_query, L, gthr, q0, nq);
+    return cudaGetLastError();
+}
+
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
-                                  int entries_per_query, const unsigned *gthr, int q0, int nq, cudaStream_t s) {
+                                  int entries_per_query, unsigned *gthr, int q0, int nq, cudaStream_t s) {
     const size_t smem = finalize_union_smem(epl, fin.dp);
     switch (epl) {
         case 1: finalize_union_kernel<1><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, q0); break;

@@ -39,7 +39,11 @@ def run(n, d, nq, k, space="cosine", iters=20, path=0):
           f" -> {gb/kms*1e3:.0f} GB/s {fl/kms/1e9:.0f} TFLOP/s | fallbacks={c.stats()['n_exact_fallbacks']}", flush=True)
     c.close()
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) > 1:
+    # python scripts/quick_gemm.py NQ [D K ITERS N]: one configuration (used under ncu)
+    a = [int(x) for x in sys.argv[1:]] + [None] * 5
+    run(a[4] or 1_000_000, a[1] or 384, a[0], a[2] or 5, iters=a[3] or 5)
+elif __name__ == "__main__":
     run(1_000_000, 384, 256, 5)
     run(1_000_000, 384, 128, 5)
     run(1_000_000, 384, 64, 5)

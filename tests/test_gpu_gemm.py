@@ -35,6 +35,20 @@ def test_gemm_batch_crosses_query_blocks():
     assert c.stats()["n_exact_fallbacks"] == 0
 
 
+def test_gemm_sampling_pass_seeds_thresholds():
+    """>= 256 tiles: the strided sampling pass runs first; results must still equal the oracle,
+    including when the planted neighbours sit in rows the sample does not visit."""
+    n, d = 70001, 384
+    c, X, _ = _mk("cosine", d, n, seed=19)
+    Q = make_unit(24, d, 20)
+    Q[:8] = X[[1, 300, 777, 12345, 40000, 65535, 69999, 70000]] + 0.03 * make_unit(8, d, 21)
+    _check(c, X, Q, 5, "cosine", path=2)
+    _check(c, X, Q, 16, "cosine", path=2)
+    types = np.arange(n) % 3
+    c2, X2, _ = _mk("l2", d, n, seed=23, unit=False)
+    _check(c2, X2, Q, 5, "l2", path=2)
+
+
 def test_gemm_auto_path_for_batches():
     c, X, _ = _mk("cosine", 384, 20000, seed=12)
     Q = make_unit(64, 384, 13)
