@@ -151,7 +151,7 @@ extern "C" int b2r_destroy(b2r_handle h) {
     cudaFree(h->max_norm2); cudaFree(h->counters); cudaFree(h->tickets); cudaFree(h->need_ctl);
     DevBuf *bufs[] = {&h->x_stage, &h->t_stage, &h->q_raw, &h->q_prep, &h->allow, &h->rows_stage, &h->gather_out,
                       &h->o_rows, &h->o_dist, &h->o_dist64, &h->o_count, &h->need_list, &h->scan_lists,
-                      &h->exact_lists, &h->q_bf16, &h->pass_bits, &h->gthr, &h->gemm_lists};
+                      &h->exact_lists, &h->q_bf16, &h->q_err, &h->pass_bits, &h->gthr, &h->gemm_lists};
     for (DevBuf *b : bufs) release(*b);
     for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -165,7 +165,7 @@ extern "C" int b2r_clear(b2r_handle h) {
     B2R_CUDA(cudaSetDevice(h->device));
     B2R_CUDA(cudaDeviceSynchronize());
     h->rows = 0; h->live = 0; h->mut_gen++;
-    B2R_CUDA(cudaMemset(h->max_norm2, 0, 4));
+    B2R_CUDA(cudaMemset(h->max_norm2, 0, 8));
     return B2R_OK;
 }
 
@@ -274,7 +274,7 @@ extern "C" int b2r_ingest_f32(b2r_handle h, const float *x, int64_t n, const uin
     p.bias = h->bias ? h->bias + h->rows : nullptr;
     p.type_out = h->type_code + h->rows;
     p.type_in = td;
-    p.max_norm2 = h->max_norm2;
+    p.max_norm2 = h->max_norm2; p.qerr = nullptr;
     const int wpb = INGEST_THREADS / 32;
     int grid = (int)std::min<int64_t>((n + wpb - 1) / wpb, (int64_t)h->sm_count * 16);
     const bool vec = (h->dim % 8 == 0) && (((uintptr_t)xd & 15) == 0);
@@ -457,13 +457,13 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         gp.gthr = (unsigned *)h->gthr.p; gp.lists = (KeyS *)h->gemm_lists.p;
         const int q0 = qb0 * GEMM_BM, nq_here = std::min(nq - q0, gp.n_qblocks * GEMM_BM);
         if (sample_tiles) {
-            gp.tiles_total = sample_tiles; gp.tile_mul = tiles_total / sample_tiles;
+            gp.tiles_total = sample_tiles; gp.tile_mul = tiles_total / sample_tiles; gp.sample_mode = 1;
             gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, sample_tiles));
             B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
             B2R_CUDA(sample_threshold_launch(gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, L, gp.gthr, q0, nq_here, s));
             h->n_launches += 2;
         }
-        gp.tiles_total = tiles_total; gp.tile_mul = 1;
+        gp.tiles_total = tiles_total; gp.tile_mul = 1; gp.sample_mode = 0;
         gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, tiles_total));
         KernelTimer kt(h, s);
         B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
@@ -532,7 +532,7 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     int path = h->path;
     const int epl_s = epl_scored(k);
     const bool scan_ok = scan_supported(h->dp) && epl_s != 0;
-    const bool gemm_ok = gemm_supported(h->dp, k) && epl_s != 0 && epl_s <= 2;
+    const bool gemm_ok = gemm_supported(h->dp, k);
     if (path == 0) path = (gemm_ok && nq >= GEMM_MIN_BATCH) ? 2 : scan_ok ? 1 : 3;
     if (path == 2 && !gemm_ok) path = scan_ok ? 1 : 3;
     if (path == 1 && !scan_ok) path = 3;
@@ -540,11 +540,13 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
 
     // ---- prepare queries (cosine: hnswlib normalisation; zero-pad to dp; bf16 copy for K3) ----
     if (path == 2 && (rc = ensure(h->q_bf16, (size_t)nq * h->dp * 2)) != B2R_OK) return rc;
+    if (path == 2 && (rc = ensure(h->q_err, (size_t)nq * 4)) != B2R_OK) return rc;
     {
         IngestParams p;
         p.x = q_raw; p.n = nq; p.d = h->dim; p.dp = h->dp; p.space = h->space;
         p.corpus = path == 2 ? (uint4 *)h->q_bf16.p : nullptr; p.master = (float *)h->q_prep.p; p.bias = nullptr;
         p.type_out = nullptr; p.type_in = nullptr; p.max_norm2 = nullptr;
+        p.qerr = path == 2 ? (float *)h->q_err.p : nullptr;
         const int wpb = INGEST_THREADS / 32;
         int grid = std::min((nq + wpb - 1) / wpb, h->sm_count * 8);
         const bool vec = (h->dim % 8 == 0) && (((uintptr_t)q_raw & 15) == 0);
@@ -559,14 +561,12 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     fin.max_norm2 = h->max_norm2; fin.dp = h->dp; fin.space = h->space; fin.k = k;
     fin.row_base = h->row_base; fin.out_rows = o_rows; fin.out_dist = o_dist; fin.out_dist64 = o_dist64;
     fin.out_count = o_count; fin.need_ctl = h->need_ctl; fin.need_list = (int *)h->need_list.p;
-    // |scan score - exact score| <= eps_rel * |q| * max|x| (+ small abs term, finalize_candidates).
-    // Corpus rounded to bf16: unit roundoff 2^-8 (only counts when the exact answer is defined on the
-    // fp32 master).  K2 keeps the query in fp32 and accumulates in fp32: (dp+8) * 2^-24.  K3 also rounds
-    // the query to bf16 (another 2^-8, plus the 2^-16 cross term) and the tensor core's fp32 accumulation
-    // is allowed 4x the rounding slop.
-    fin.eps_rel = (h->master ? 0.00390625f : 0.f) + (float)(h->dp + 8) * 5.9604645e-8f;
-    if (path == 2) fin.eps_rel += 0.00390625f + 1.52587890625e-5f + 3.f * (float)(h->dp + 8) * 5.9604645e-8f;
-    fin.eps_rel *= 1.01f;
+    // Error bound of the scan scores: finalize_candidates() builds it from the MEASURED rounding errors
+    // (max |x - bf16(x)| from ingest, |q - bf16(q)| from the preparation above when K3 rounds the queries);
+    // eps_rel only carries the fp32 accumulation slop: (dp+8) * 2^-24 for K2's FFMA chain, 4x that for the
+    // tensor core's accumulator.
+    fin.q_err = path == 2 ? (const float *)h->q_err.p : nullptr;
+    fin.eps_rel = (float)(h->dp + 8) * 5.9604645e-8f * (path == 2 ? 4.f : 1.f) * 1.01f;
 
     if (path == 1) {
         ScanParams sp;
@@ -576,7 +576,7 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
         if ((rc = launch_scan_batch(h, nq, epl_s, sp, s)) != B2R_OK) return rc;
         if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
     } else if (path == 2) {
-        if ((rc = launch_gemm_batch(h, nq, k, epl_s, fin, f, allow_dev, s)) != B2R_OK) return rc;
+        if ((rc = launch_gemm_batch(h, nq, k, k <= 8 ? 1 : k <= 16 ? 2 : 4, fin, f, allow_dev, s)) != B2R_OK) return rc;
         if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
     } else {
         if ((rc = launch_exact_batch(h, nq, k, 1, fin, f, allow_dev, s)) != B2R_OK) return rc;

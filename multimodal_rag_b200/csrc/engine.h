@@ -76,7 +76,7 @@ struct b2r_index {
     float *master = nullptr;        // fp32 [capacity, dp] unless B2R_FLAG_NO_F32_MASTER
     float *bias = nullptr;          // [capacity], l2 only
     uint8_t *type_code = nullptr;   // [capacity]
-    float *max_norm2 = nullptr;     // scalar
+    float *max_norm2 = nullptr;     // [2]: max |x|^2, max |x - bf16(x)|^2 over the stored rows
     unsigned long long *counters = nullptr;   // [0] = rows killed by tombstone, [1] = exact fallbacks
 
     // scratch (device), grown on demand
@@ -84,7 +84,7 @@ struct b2r_index {
     b2r::DevBuf o_rows, o_dist, o_dist64, o_count, need_list;
     int *need_ctl = nullptr;        // [4]: failed-certificate count, exit ticket (reset by K5 itself)
     b2r::DevBuf scan_lists, exact_lists;
-    b2r::DevBuf q_bf16, pass_bits, gthr, gemm_lists;   // K3 scratch
+    b2r::DevBuf q_bf16, q_err, pass_bits, gthr, gemm_lists;   // K3 scratch
 
     // TMA tensor maps (K3), re-encoded when the buffer they describe moves or grows
     CUtensorMap tm_corpus, tm_query;

@@ -14,7 +14,8 @@ struct FinalizeParams {
     const float *master;        // [rows, dp] fp32 stored rows, or nullptr (bf16-only corpus)
     const uint4 *corpus;        // [rows, dp] bf16 stored rows
     const float *q;             // [nq, dp] fp32 prepared queries (normalised for cosine)
-    const float *max_norm2;     // device scalar: max |x|^2 over stored rows (bf16-rounded or fp32)
+    const float *max_norm2;     // device [2]: max |x|^2 over stored rows, max |x - bf16(x)|^2 (0 without an fp32 master)
+    const float *q_err;         // [nq] |q - bf16(q)| when the scoring kernel rounded the queries (K3), else nullptr
     int dp, space, k;
     long long row_base;         // added to local rows on output (shard offset)
     long long *out_rows;        // [nq, k]
@@ -23,7 +24,7 @@ struct FinalizeParams {
     int *out_count;             // [nq]
     int *need_ctl;              // [0] = number of queries whose certificate failed (this call), [1] = exit ticket
     int *need_list;             // [nq]: those queries, in arrival order; the exact scan (K5) redoes them
-    float eps_rel;              // |score_scan - score_exact| <= eps_rel * |q| * max|x| (+ small abs term)
+    float eps_rel;              // accumulation slop of the scoring kernel, relative to |q| * max|x|
 };
 
 // exact distance between prepared query and stored row, fp64 accumulation, whole warp
@@ -94,39 +95,67 @@ __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, con
     if (threadIdx.x == 0) p.out_count[qi] = cnt;
 }
 
-// Stages shared by every scoring path once the candidate set is known: exact re-rank of the
-// nvalid candidates in sm_keys (one warp per candidate), Chroma-ordered output, and the certificate:
-// every row outside the candidate set has scan score <= T, so its exact score is <= T + eps; if the
-// k-th exact candidate beats that, no outsider can belong to the top-k.  T = -inf means there are no
-// outsiders.  All FIN_THREADS threads call; sm_q must already hold the prepared query.
+// Stages shared by every scoring path once the candidate set is known (sm_keys: nvalid candidates,
+// best scan score first).  All FIN_THREADS threads call; sm_q must already hold the prepared query.
+//
+// Error bound.  scan score = q~.x~ (+bias) with x~ = bf16(x) and, for K3, q~ = bf16(q); the exact score is
+// q.x (+bias).  q~.x~ - q.x = (q~-q).x~ + q.(x~-x), so
+//     |scan - exact| <= |q~-q| (max|x| + max|x~-x|) + |q| max|x~-x| + accumulation slop =: eps
+// with max|x~-x| and |q~-q| MEASURED (ingest / query preparation), not the worst case 2^-8.
+//
+// 1. A candidate whose scan score is below (k-th best scan score - 2 eps) has an exact score strictly
+//    below the exact scores of k other candidates: it is skipped, only the prefix that can still reach
+//    the top-k is re-ranked (fp64 accumulate over the stored rows, one warp per candidate).
+// 2. Certificate: every row outside the candidate set has scan score <= T, hence exact score <= T + eps.
+//    If the k-th exact candidate beats that, no outsider belongs to the top-k; otherwise the query goes
+//    on the exact-scan work list.  T = -inf: there are no outsiders.
 __device__ __forceinline__ void finalize_candidates(const FinalizeParams &p, int qi, const KeyS *sm_keys, int nvalid,
                                                     float T, KeyD *sm_ex, const float *sm_q, KeyD *sm_misc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = warp; c < nvalid; c += FIN_WARPS) {
+    if (threadIdx.x < 32) {
+        double qn2 = 0.0;
+        for (int i = lane; i < p.dp; i += 32) qn2 = fma((double)sm_q[i], (double)sm_q[i], qn2);
+        qn2 = warp_sum(qn2);
+        const double xn = sqrt((double)p.max_norm2[0]), dxn = sqrt((double)p.max_norm2[1]), qn = sqrt(qn2);
+        const double dq = p.q_err ? (double)p.q_err[qi] : 0.0;
+        const double eps = dq * (xn + dxn) + qn * dxn + (double)p.eps_rel * (qn + dq) * (xn + dxn) +
+                           1e-6 * (0.5 * xn * xn + qn * xn) + 1e-30;
+        if (lane == 0) { sm_misc[1].d = eps; sm_misc[2].d = qn2; sm_misc[0] = KeyD::worst(); }
+    }
+    __syncthreads();
+    const double eps = sm_misc[1].d, qn2 = sm_misc[2].d;
+    // ---- prefix that can still reach the top-k ----
+    int m = nvalid;
+    if (nvalid > p.k) {
+        const double cut = (double)sm_keys[p.k - 1].score() - 2.0 * eps;
+        // nvalid <= KP <= FIN_THREADS: one candidate per thread; the list is sorted, so the survivors are a prefix
+        m = __syncthreads_count(threadIdx.x < nvalid && (double)sm_keys[threadIdx.x].score() >= cut);
+    }
+    {   // pull the rows towards L2 first: the re-rank below is a chain of dependent loads per warp
+        const int row_bytes = p.master ? p.dp * 4 : p.dp * 2;
+        const int lines = (row_bytes + 127) / 128;
+        for (int i = threadIdx.x; i < m * lines; i += FIN_THREADS) {
+            const unsigned row = sm_keys[i / lines].row();
+            const char *base = p.master ? reinterpret_cast<const char *>(p.master + (size_t)row * p.dp)
+                                        : reinterpret_cast<const char *>(p.corpus + (size_t)row * (p.dp / 8));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(i % lines) * 128));
+        }
+    }
+    for (int c = warp; c < m; c += FIN_WARPS) {
         unsigned row = sm_keys[c].row();
         double d = exact_distance_warp(p, sm_q, row, lane);
         if (lane == 0) sm_ex[c] = KeyD::make(d, row);
     }
-    if (threadIdx.x == 0) sm_misc[0] = KeyD::worst();
     __syncthreads();
-    emit_sorted(p, qi, sm_ex, nvalid, &sm_misc[0]);
+    emit_sorted(p, qi, sm_ex, m, &sm_misc[0]);
     __syncthreads();
-    if (threadIdx.x < 32) {
-        int flag = 0;
-        if (T > -INFINITY) {
-            double qn2 = 0.0;
-            for (int i = lane; i < p.dp; i += 32) qn2 = fma((double)sm_q[i], (double)sm_q[i], qn2);
-            qn2 = warp_sum(qn2);
-            double xn = sqrt((double)*p.max_norm2), qn = sqrt(qn2);
-            double eps = (double)p.eps_rel * qn * xn + 1e-6 * (0.5 * xn * xn + qn * xn) + 1e-30;
-            KeyD kth = sm_misc[0];
-            double s_k;
-            if (!kth.valid()) s_k = -1e300;                       // fewer than k candidates but rows were rejected
-            else if (p.space == 0) s_k = 0.5 * (qn2 - kth.d);
-            else s_k = 1.0 - kth.d;
-            flag = (s_k - eps > (double)T) ? 0 : 1;
-        }
-        if (lane == 0 && flag) p.need_list[atomicAdd(&p.need_ctl[0], 1)] = qi;
+    if (threadIdx.x == 0 && T > -INFINITY) {
+        const KeyD kth = sm_misc[0];
+        double s_k;
+        if (!kth.valid()) s_k = -1e300;                       // fewer than k candidates although rows were rejected
+        else if (p.space == 0) s_k = 0.5 * (qn2 - kth.d);
+        else s_k = 1.0 - kth.d;
+        if (!(s_k - eps > (double)T)) p.need_list[atomicAdd(&p.need_ctl[0], 1)] = qi;
     }
     __syncthreads();
 }

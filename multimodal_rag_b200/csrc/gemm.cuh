@@ -42,6 +42,7 @@ struct GemmParams {
     int list_stride;             // KeyS entries reserved per query in `lists` (>= n_slices * 2 * L)
     int tiles_total;             // tiles this launch covers (main pass: ceil(n / BN); sampling pass: the sample size)
     int tile_mul;                // launch tile t is corpus tile t * tile_mul (1 = main pass; > 1 = strided sample)
+    int sample_mode;             // 1 = sampling pass: keep only the best scores seen (one per 32-row step), no hit path
     const uint32_t *pass_bits;   // bit r = row r is live and passes the filter; 0 for r >= n
     const float *bias;           // [n] -|x|^2/2 (l2) or nullptr
     unsigned *gthr;              // [n_qblocks*128] shared per-query bound, KeyS::ord encoding, 0 = none yet
@@ -184,6 +185,38 @@ struct RegList {
         r[0] = top ? row : r[0];
     }
 };
+
+// Sampling-pass step: the best passing score among this step's 32 rows goes into the thread's list
+// (every lane inserts once per step, in lockstep).  Different steps are different rows, so the list's
+// entries are scores of distinct real rows -- all the threshold seed needs.
+template <int L, bool HAS_BIAS>
+__device__ __forceinline__ void epi_chunk_sample(const uint32_t (&raw)[32], unsigned r0, const GemmParams &p, RegList<L> &list) {
+    const unsigned pm = __ldg(p.pass_bits + (r0 >> 5));
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+    if (HAS_BIAS) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + r0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+    }
+    if (pm != 0xffffffffu) {                              // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = ((pm >> j) & 1u) ? v[j] : -INFINITY;
+    }
+    float m[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[2 * i], m[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = fmaxf(m[2 * i], m[2 * i + 1]);
+    const float x = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+    if (x > list.s[L - 1]) list.insert(x, r0);
+}
 
 // One epilogue step: 32 scores of this thread's query (columns r0 .. r0+31 of the corpus).
 // Hot path: a max tree (log depth -- a single resident warp per scheduler cannot hide serial chains)
@@ -366,11 +399,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             for (int c = 0; c < NC; c += 2) {            // two register buffers: the next load flies under this step
                 tmem_ld_wait(va);
                 tmem_ld_x32(trow + (c + 1) * 32, vb);
-                epi_chunk<L, HAS_BIAS>(va, row0 + c * 32, p, list, thr, g_seen, gq, publish);
+                if (p.sample_mode) epi_chunk_sample<L, HAS_BIAS>(va, row0 + c * 32, p, list);
+                else epi_chunk<L, HAS_BIAS>(va, row0 + c * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
                 tmem_ld_wait(vb);
                 if (c + 2 < NC) tmem_ld_x32(trow + (c + 2) * 32, va);
-                epi_chunk<L, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list, thr, g_seen, gq, publish);
+                if (p.sample_mode) epi_chunk_sample<L, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list);
+                else epi_chunk<L, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
             }
             tc_fence_before();
@@ -396,25 +431,27 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 // nothing that scores below it can be among the L best of the shard.
 // ---------------------------------------------------------------------------------
 template <int DUMMY>
-__global__ void __launch_bounds__(256) sample_threshold_kernel(const KeyS *__restrict__ lists, int list_stride,
-                                                               int entries_per_query, int L, unsigned *gthr, int q0, int nq) {
-    const int lane = threadIdx.x & 31;
-    const int qi = q0 + blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+__global__ void sample_threshold_kernel(const KeyS *__restrict__ lists, int list_stride, int entries_per_query, int L,
+                                        unsigned *gthr, int q0, int nq) {
+    // one warp per query: the L-th largest score key by bitwise bisection over warp-wide counts
+    extern __shared__ unsigned sm_keys[];                 // [warps][entries_per_query]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = q0 + blockIdx.x * (blockDim.x / 32) + warp;
     if (qi >= q0 + nq) return;
-    WarpList<KeyS, 1> wl; wl.init();
+    unsigned *mine = sm_keys + (size_t)warp * entries_per_query;
     const KeyS *src = lists + (size_t)qi * list_stride;
-    for (int b = 0; b < entries_per_query; b += 32) {
-        const int idx = b + lane;
-        KeyS mine = idx < entries_per_query ? src[idx] : KeyS::worst();
-        unsigned hits = __ballot_sync(FULL_MASK, mine.valid() && wl.accepts(mine));
-        while (hits) {
-            const int sl = __ffs(hits) - 1;
-            hits &= hits - 1;
-            wl.offer(KeyS::shfl(mine, sl), lane);
-        }
+    for (int i = lane; i < entries_per_query; i += 32) mine[i] = (unsigned)(src[i].v >> 32);   // ord(score); 0 = empty
+    __syncwarp();
+    unsigned t = 0;
+#pragma unroll 1
+    for (int bit = 31; bit >= 10; --bit) {                // 22 bits: sign, exponent, 13 mantissa bits (a lower bound)
+        const unsigned cand = t | (1u << bit);
+        int c = 0;
+        for (int i = lane; i < entries_per_query; i += 32) c += mine[i] >= cand ? 1 : 0;
+        c = __reduce_add_sync(FULL_MASK, c);
+        if (c >= L) t = cand;
     }
-    const KeyS kth = KeyS::shfl(wl.key[0], L - 1);        // EPL = 1: rank r lives in lane r
-    if (lane == 0 && kth.valid()) atomicMax(&gthr[qi], KeyS::ord(kth.score()));
+    if (lane == 0 && t != 0u) atomicMax(&gthr[qi], t);
 }
 
 // ---------------------------------------------------------------------------------

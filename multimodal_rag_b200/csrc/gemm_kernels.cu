@@ -139,7 +139,10 @@ cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_m
 
 cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
                                     int q0, int nq, cudaStream_t s) {
-    sample_threshold_kernel<0><<<(nq + 7) / 8, 256, 0, s>>>(lists, list_stride, entries_per_query, L, gthr, q0, nq);
+    int wpc = (int)std::min<size_t>(8, (size_t)(40 * 1024) / ((size_t)entries_per_query * 4));   // stay under the 48 KB default
+    if (wpc < 1) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)wpc * entries_per_query * 4;
+    sample_threshold_kernel<0><<<(nq + wpc - 1) / wpc, wpc * 32, smem, s>>>(lists, list_stride, entries_per_query, L, gthr, q0, nq);
     return cudaGetLastError();
 }
 
@@ -149,6 +152,7 @@ cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS
     switch (epl) {
         case 1: finalize_union_kernel<1><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, q0); break;
         case 2: finalize_union_kernel<2><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, q0); break;
+        case 4: finalize_union_kernel<4><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, q0); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -18,7 +18,8 @@ struct IngestParams {
     float *bias;               // [n] or nullptr (only l2)
     uint8_t *type_out;         // [n] or nullptr
     const uint8_t *type_in;    // [n] device or nullptr (= 0)
-    float *max_norm2;          // device scalar or nullptr
+    float *max_norm2;          // device [2] or nullptr: [0] max |x|^2 of the stored rows, [1] max |x - bf16(x)|^2
+    float *qerr;               // [n] or nullptr (query batches for K3): |q - bf16(q)|, rounded up
 };
 
 // 1/(sqrt(s)+1e-30) exactly as hnswlib's normalize_vector does it in fp32
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(const IngestPara
             }
             inv = hnsw_inv_norm(warp_sum(s));
         }
-        double s2 = 0.0;
+        double s2 = 0.0, e2 = 0.0;
         for (int c = lane; c < chunks; c += 32) {
             float y[8];
             if (VEC && c * 8 < d) {
@@ -80,6 +81,12 @@ __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(const IngestPara
                 m4[1] = make_float4(y[4], y[5], y[6], y[7]);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s2 = fma((double)y[i], (double)y[i], s2);
+                const unsigned ww[4] = {w.x, w.y, w.z, w.w};   // rounding error of the packed copy (exact in fp32)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double a = (double)(y[2 * i] - bf16lo(ww[i])), b = (double)(y[2 * i + 1] - bf16hi(ww[i]));
+                    e2 = fma(a, a, e2); e2 = fma(b, b, e2);
+                }
             } else {
                 const unsigned ww[4] = {w.x, w.y, w.z, w.w};   // the stored corpus is the bf16 rounding
 #pragma unroll
@@ -90,10 +97,15 @@ __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(const IngestPara
             }
         }
         s2 = warp_sum(s2);
+        e2 = warp_sum(e2);
         if (lane == 0) {
+            if (p.qerr) p.qerr[r] = __double2float_ru(sqrt(e2) * (1.0 + 1e-6));
             if (p.bias) p.bias[r] = __double2float_rn(-0.5 * s2);
             if (p.type_out) p.type_out[r] = p.type_in ? p.type_in[r] : (uint8_t)0;
-            if (p.max_norm2) atomicMax(reinterpret_cast<unsigned *>(p.max_norm2), __float_as_uint(__double2float_ru(s2)));
+            if (p.max_norm2) {
+                atomicMax(reinterpret_cast<unsigned *>(p.max_norm2), __float_as_uint(__double2float_ru(s2)));
+                atomicMax(reinterpret_cast<unsigned *>(p.max_norm2) + 1, __float_as_uint(__double2float_ru(e2)));
+            }
         }
     }
 }
