@@ -412,6 +412,7 @@ int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const Finaliz
 constexpr int GEMM_MIN_BATCH = 5;        // below this the scan reads the corpus at most twice anyway
 constexpr int GEMM_MAX_QBLOCKS = 8;      // 128-query blocks per launch (1024 queries per corpus pass)
 constexpr int GEMM_SAMPLE_TILES = 128;   // tiles of the threshold-seeding sample (32k rows at BN = 256)
+constexpr int GEMM_SAMPLE_MIN_BATCH = 24;
 
 int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams &fin, const b2r_filter &f,
                       const uint32_t *allow_dev, cudaStream_t s) {
@@ -425,7 +426,7 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
     if ((rc = ensure(h->pass_bits, (size_t)n_words * 4 + 16)) != B2R_OK) return rc;
     {   // gthr is all-zero between calls: zeroed when (re)allocated, and finalize_union_kernel clears what it read
         const void *before = h->gthr.p;
-        if ((rc = ensure(h->gthr, (size_t)qblocks_total * GEMM_BM * 4)) != B2R_OK) return rc;
+        if ((rc = ensure(h->gthr, (size_t)qblocks_total * GEMM_BM * 4 * 2)) != B2R_OK) return rc;   // bounds, then cursors
         if (h->gthr.p != before) B2R_CUDA(cudaMemsetAsync(h->gthr.p, 0, h->gthr.bytes, s));
     }
     if ((rc = ensure(h->gemm_lists, sizeof(KeyS) * (size_t)nq * list_stride)) != B2R_OK) return rc;
@@ -447,20 +448,21 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         h->tm_query_base = h->q_bf16.p; h->tm_query_rows = nq;
     }
     // sampling pass: GEMM_SAMPLE_TILES tiles strided across the shard seed gthr[q] (skipped for small shards)
-    const int sample_tiles = tiles_total >= 2 * GEMM_SAMPLE_TILES ? GEMM_SAMPLE_TILES : 0;
+    // and for small batches: with a handful of live lanes per warp the list warm-up costs a few microseconds)
+    const int sample_tiles = (tiles_total >= 2 * GEMM_SAMPLE_TILES && nq >= GEMM_SAMPLE_MIN_BATCH) ? GEMM_SAMPLE_TILES : 0;
     for (int qb0 = 0; qb0 < qblocks_total; qb0 += GEMM_MAX_QBLOCKS) {
         GemmParams gp;
         gp.n = (unsigned)h->rows; gp.nq = nq; gp.qblock0 = qb0;
         gp.n_qblocks = std::min(GEMM_MAX_QBLOCKS, qblocks_total - qb0);
         gp.list_stride = list_stride;
         gp.pass_bits = (const uint32_t *)h->pass_bits.p; gp.bias = h->bias;
-        gp.gthr = (unsigned *)h->gthr.p; gp.lists = (KeyS *)h->gemm_lists.p;
+        gp.gthr = (unsigned *)h->gthr.p; gp.cnt = gp.gthr + (size_t)qblocks_total * GEMM_BM; gp.lists = (KeyS *)h->gemm_lists.p;
         const int q0 = qb0 * GEMM_BM, nq_here = std::min(nq - q0, gp.n_qblocks * GEMM_BM);
         if (sample_tiles) {
             gp.tiles_total = sample_tiles; gp.tile_mul = tiles_total / sample_tiles; gp.sample_mode = 1;
             gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, sample_tiles));
             B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
-            B2R_CUDA(sample_threshold_launch(gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, L, gp.gthr, q0, nq_here, s));
+            B2R_CUDA(sample_threshold_launch(gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, L, gp.gthr, gp.cnt, q0, nq_here, s));
             h->n_launches += 2;
         }
         gp.tiles_total = tiles_total; gp.tile_mul = 1; gp.sample_mode = 0;
@@ -469,7 +471,7 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
         kt.stop();
         h->n_launches++;
-        B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, gp.gthr, q0, nq_here, s));
+        B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, gp.gthr, gp.cnt, q0, nq_here, s));
         h->n_launches++;
     }
     return B2R_OK;
@@ -526,14 +528,16 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     }
 
     // ---- choose the scoring path ----
-    //   1  warp-shuffle scan (K2): batches of <= 4 queries per corpus pass, HBM-bound
-    //   2  tcgen05 GEMM (K3): one corpus pass per <= 1024 queries
+    //   1  warp-shuffle scan (K2): batches of <= 4 queries per corpus pass, every padded dim up to 1024, k <= 128
+    //   2  tcgen05 GEMM (K3): one corpus pass per <= 1024 queries, k <= 32, dims 128/256/384/512/768
     //   3  exact fp64 scan (K5): always correct, used for shapes the fast kernels are not built for
     int path = h->path;
     const int epl_s = epl_scored(k);
     const bool scan_ok = scan_supported(h->dp) && epl_s != 0;
     const bool gemm_ok = gemm_supported(h->dp, k);
-    if (path == 0) path = (gemm_ok && nq >= GEMM_MIN_BATCH) ? 2 : scan_ok ? 1 : 3;
+    // K3's TMA-fed stream is also the faster batch-1 scan up to 512 dims (6.2 vs 5.1 TB/s at 1M x 384); at 768
+    // dims its shallower pipeline loses to K2 until the corpus pass is shared by a handful of queries
+    if (path == 0) path = (gemm_ok && (nq >= GEMM_MIN_BATCH || h->dp <= 512)) ? 2 : scan_ok ? 1 : 3;
     if (path == 2 && !gemm_ok) path = scan_ok ? 1 : 3;
     if (path == 1 && !scan_ok) path = 3;
     if (h->rows == 0) path = 3;   // empty collection: Chroma returns empty lists; only the padding is written

@@ -51,9 +51,9 @@ cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const
 cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_mask, const uint32_t *allow_bits,
                              unsigned n, unsigned n_words, uint32_t *out, int sm_count, cudaStream_t s);
 cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
-                                    int q0, int nq, cudaStream_t s);
+                                    unsigned *cnt, int q0, int nq, cudaStream_t s);
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
-                                  int entries_per_query, unsigned *gthr, int q0, int nq, cudaStream_t s);
+                                  int entries_per_query, unsigned *gthr, unsigned *cnt, int q0, int nq, cudaStream_t s);
 
 struct DevBuf {
     void *p = nullptr;

@@ -46,7 +46,8 @@ struct GemmParams {
     const uint32_t *pass_bits;   // bit r = row r is live and passes the filter; 0 for r >= n
     const float *bias;           // [n] -|x|^2/2 (l2) or nullptr
     unsigned *gthr;              // [n_qblocks*128] shared per-query bound, KeyS::ord encoding, 0 = none yet
-    KeyS *lists;                 // [nq][list_stride]: (slice s, half h) of query q at q*list_stride + (2s+h)*L
+    unsigned *cnt;               // [nq] entries appended to lists[q] so far (0 between calls)
+    KeyS *lists;                 // [nq][list_stride]: every thread appends its valid entries (atomic cursor cnt[q])
 };
 
 __host__ __device__ constexpr int gemm_bn(int KB) { return KB <= 8 ? 256 : 128; }
@@ -412,11 +413,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[buf]);
         }
-        if (q < p.nq) {
-            KeyS *dst = p.lists + (size_t)q * p.list_stride + (size_t)(slice * GEMM_HALVES + half) * L;
+        if (q < p.nq) {           // append this thread's entries to the query's candidate pool (compact: most lists are short)
+            int nv = 0;
 #pragma unroll
-            for (int i = 0; i < L; ++i)
-                dst[i] = list.r[i] != 0xffffffffu ? KeyS::make(list.s[i], list.r[i]) : KeyS::worst();
+            for (int i = 0; i < L; ++i) nv += list.r[i] != 0xffffffffu ? 1 : 0;
+            if (nv) {
+                KeyS *dst = p.lists + (size_t)q * p.list_stride + atomicAdd(&p.cnt[q], (unsigned)nv);
+#pragma unroll
+                for (int i = 0; i < L; ++i)              // the list is sorted: valid entries are the first nv
+                    if (i < nv) dst[i] = KeyS::make(list.s[i], list.r[i]);
+            }
         }
     }
 
@@ -431,17 +437,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 // nothing that scores below it can be among the L best of the shard.
 // ---------------------------------------------------------------------------------
 template <int DUMMY>
-__global__ void sample_threshold_kernel(const KeyS *__restrict__ lists, int list_stride, int entries_per_query, int L,
-                                        unsigned *gthr, int q0, int nq) {
+__global__ void sample_threshold_kernel(const KeyS *__restrict__ lists, int list_stride, int max_entries, int L,
+                                        unsigned *gthr, unsigned *cnt, int q0, int nq) {
     // one warp per query: the L-th largest score key by bitwise bisection over warp-wide counts
     extern __shared__ unsigned sm_keys[];                 // [warps][entries_per_query]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = q0 + blockIdx.x * (blockDim.x / 32) + warp;
     if (qi >= q0 + nq) return;
-    unsigned *mine = sm_keys + (size_t)warp * entries_per_query;
+    unsigned *mine = sm_keys + (size_t)warp * max_entries;
     const KeyS *src = lists + (size_t)qi * list_stride;
-    for (int i = lane; i < entries_per_query; i += 32) mine[i] = (unsigned)(src[i].v >> 32);   // ord(score); 0 = empty
+    const int entries_per_query = min((int)cnt[qi], max_entries);
+    for (int i = lane; i < entries_per_query; i += 32) mine[i] = (unsigned)(src[i].v >> 32);   // ord(score)
     __syncwarp();
+    if (lane == 0) cnt[qi] = 0u;                          // the main pass appends from scratch
     unsigned t = 0;
 #pragma unroll 1
     for (int bit = 31; bit >= 10; --bit) {                // 22 bits: sign, exponent, 13 mantissa bits (a lower bound)
@@ -458,42 +466,100 @@ __global__ void sample_threshold_kernel(const KeyS *__restrict__ lists, int list
 // finalize: one CTA per query.  Fold the (slice) lists into the best KP by bf16 score, re-rank
 // them exactly, certify against max(KP-th best candidate score, final gthr[q]), emit.
 // ---------------------------------------------------------------------------------
+constexpr int FU_MAX_POOL = 4096;     // pool entries staged in shared memory by the data-parallel selection
+constexpr int FU_MAX_SEL = 512;       // survivors of the score cut that are ranked by counting
+
 template <int EPL>
 __global__ void __launch_bounds__(FIN_THREADS)
-finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, int list_stride, int entries_per_query,
-                      unsigned *__restrict__ gthr, int q0) {
+finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, int list_stride, int max_entries,
+                      unsigned *__restrict__ gthr, unsigned *__restrict__ cnt, int q0) {
     constexpr int KP = 32 * EPL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyS *stage = reinterpret_cast<KeyS *>(smem_raw);                       // [FIN_WARPS*KP]
     KeyD *sm_ex = reinterpret_cast<KeyD *>(stage + FIN_WARPS * KP);        // [KP]
     KeyD *sm_misc = sm_ex + KP;                                            // [4]
     float *sm_q = reinterpret_cast<float *>(sm_misc + 4);                  // [dp]
+    KeyS *pool = reinterpret_cast<KeyS *>(sm_q + fin.dp);                  // [FU_MAX_POOL]
+    KeyS *sel = pool + FU_MAX_POOL;                                        // [FU_MAX_SEL]
+    __shared__ int s_count[3], s_nsel;
     const int qi = q0 + blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int entries = min((int)cnt[qi], max_entries);
+    const unsigned g = gthr[qi];
+    const KeyS *src = lists + (size_t)qi * list_stride;
 
     for (int i = threadIdx.x; i < fin.dp; i += FIN_THREADS) sm_q[i] = fin.q[(size_t)qi * fin.dp + i];
+    if (threadIdx.x == 0) { s_nsel = 0; s_count[0] = s_count[1] = s_count[2] = 0; }
+    int nvalid = -1;                                       // -1: the data-parallel selection did not apply
 
-    WarpList<KeyS, EPL> wl; wl.init();
-    const KeyS *src = lists + (size_t)qi * list_stride;
-    for (int b = warp * 32; b < entries_per_query; b += FIN_WARPS * 32) {
-        const int idx = b + lane;
-        KeyS mine = idx < entries_per_query ? src[idx] : KeyS::worst();
-        unsigned hits = __ballot_sync(FULL_MASK, mine.valid() && wl.accepts(mine));
-        while (hits) {
-            const int s = __ffs(hits) - 1;
-            hits &= hits - 1;
-            wl.offer(KeyS::shfl(mine, s), lane);
+    if (entries <= FU_MAX_POOL) {
+        // ---- data-parallel selection: stage the pool, cut at the KP-th best score, rank the survivors ----
+        for (int i = threadIdx.x; i < entries; i += FIN_THREADS) pool[i] = src[i];
+        __syncthreads();
+        unsigned t = 0;                                    // keep entries whose score key is >= t
+        if (entries > KP) {
+#pragma unroll 1
+            for (int bit = 31, it = 0; bit >= 10; --bit, ++it) {   // 22 bits of the ordered score: a lower bound of the KP-th best
+                const unsigned cand = t | (1u << bit);
+                int c = 0;
+                for (int i = threadIdx.x; i < entries; i += FIN_THREADS) c += (unsigned)(pool[i].v >> 32) >= cand ? 1 : 0;
+                c = __reduce_add_sync(FULL_MASK, c);
+                if (lane == 0 && c) atomicAdd(&s_count[it % 3], c);
+                if (threadIdx.x == 0) s_count[(it + 1) % 3] = 0;    // last read two rounds ago: one barrier per round
+                __syncthreads();
+                if (s_count[it % 3] >= KP) t = cand;
+            }
+        }
+        for (int i = threadIdx.x; i < entries; i += FIN_THREADS) {
+            const KeyS k = pool[i];
+            if ((unsigned)(k.v >> 32) >= t) {
+                const int slot = atomicAdd(&s_nsel, 1);
+                if (slot < FU_MAX_SEL) sel[slot] = k;
+            }
+        }
+        __syncthreads();
+        const int nsel = s_nsel;
+        if (nsel <= FU_MAX_SEL) {
+            for (int i = threadIdx.x; i < KP; i += FIN_THREADS) stage[i] = KeyS::worst();
+            __syncthreads();
+            for (int i = threadIdx.x; i < nsel; i += FIN_THREADS) {
+                const KeyS me = sel[i];
+                int rank = 0;
+                for (int j = 0; j < nsel; ++j) rank += KeyS::better(sel[j], me) ? 1 : 0;
+                if (rank < KP) stage[rank] = me;
+            }
+            __syncthreads();
+            nvalid = min(nsel, KP);
         }
     }
-    __syncthreads();
-    cta_tree_merge<KeyS, EPL>(wl, stage, warp, lane);
-    int nvalid = 0;
-    for (int i = 0; i < KP; ++i) nvalid += stage[i].valid() ? 1 : 0;
-    // rows outside the candidate set: either in some list but below the KP-th candidate, or never
-    // kept by any list, hence <= the final shared bound (0 = nothing was ever rejected)
-    const unsigned g = gthr[qi];
-    __syncthreads();
-    if (threadIdx.x == 0) gthr[qi] = 0u;                 // leave the shared bounds clean for the next call
+    if (nvalid < 0) {
+        // ---- general path (very large pools or massive score ties): warp-resident sorted lists ----
+        WarpList<KeyS, EPL> wl; wl.init();
+        constexpr int UN = 4;                             // loads in flight per lane before the first use
+        for (int b = warp * 32; b < entries; b += FIN_WARPS * 32 * UN) {
+            KeyS mine[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int idx = b + u * FIN_WARPS * 32 + lane;
+                mine[u] = idx < entries ? src[idx] : KeyS::worst();
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                unsigned hits = __ballot_sync(FULL_MASK, mine[u].valid() && wl.accepts(mine[u]));
+                while (hits) {
+                    const int sl = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    wl.offer(KeyS::shfl(mine[u], sl), lane);
+                }
+            }
+        }
+        __syncthreads();
+        cta_tree_merge<KeyS, EPL>(wl, stage, warp, lane);
+        nvalid = __syncthreads_count(threadIdx.x < KP && stage[threadIdx.x < KP ? threadIdx.x : 0].valid());
+    }
+    if (threadIdx.x == 0) { gthr[qi] = 0u; cnt[qi] = 0u; }   // leave the shared state clean for the next call
+    // rows outside the candidate set: either in the pool but below the KP-th candidate, or never kept
+    // by any list, hence <= the final shared bound (0 = nothing was ever rejected)
     float T = -INFINITY;
     if (nvalid == KP) T = stage[KP - 1].score();
     if (g != 0u) T = fmaxf(T, KeyS::unord(g));
@@ -502,7 +568,8 @@ finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, 
 
 inline size_t finalize_union_smem(int EPL, int dp) {
     const int KP = 32 * EPL;
-    return sizeof(KeyS) * (size_t)FIN_WARPS * KP + sizeof(KeyD) * (KP + 4) + sizeof(float) * dp;
+    return sizeof(KeyS) * (size_t)FIN_WARPS * KP + sizeof(KeyD) * (KP + 4) + sizeof(float) * dp +
+           sizeof(KeyS) * (size_t)(FU_MAX_POOL + FU_MAX_SEL);
 }
 
 }  // namespace b2r

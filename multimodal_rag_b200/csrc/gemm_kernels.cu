@@ -138,21 +138,28 @@ cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_m
 }
 
 cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
-                                    int q0, int nq, cudaStream_t s) {
+                                    unsigned *cnt, int q0, int nq, cudaStream_t s) {
     int wpc = (int)std::min<size_t>(8, (size_t)(40 * 1024) / ((size_t)entries_per_query * 4));   // stay under the 48 KB default
     if (wpc < 1) return cudaErrorInvalidValue;
     const size_t smem = (size_t)wpc * entries_per_query * 4;
-    sample_threshold_kernel<0><<<(nq + wpc - 1) / wpc, wpc * 32, smem, s>>>(lists, list_stride, entries_per_query, L, gthr, q0, nq);
+    sample_threshold_kernel<0><<<(nq + wpc - 1) / wpc, wpc * 32, smem, s>>>(lists, list_stride, entries_per_query, L, gthr, cnt, q0, nq);
     return cudaGetLastError();
 }
 
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
-                                  int entries_per_query, unsigned *gthr, int q0, int nq, cudaStream_t s) {
+                                  int entries_per_query, unsigned *gthr, unsigned *cnt, int q0, int nq, cudaStream_t s) {
     const size_t smem = finalize_union_smem(epl, fin.dp);
+    if (smem > 48 * 1024) {      // opt in to large dynamic shared memory (per function; cheap, idempotent)
+        cudaError_t e = cudaSuccess;
+        if (epl == 1) e = cudaFuncSetAttribute(finalize_union_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (epl == 2) e = cudaFuncSetAttribute(finalize_union_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (epl == 4) e = cudaFuncSetAttribute(finalize_union_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     switch (epl) {
-        case 1: finalize_union_kernel<1><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, q0); break;
-        case 2: finalize_union_kernel<2><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, q0); break;
-        case 4: finalize_union_kernel<4><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, q0); break;
+        case 1: finalize_union_kernel<1><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, cnt, q0); break;
+        case 2: finalize_union_kernel<2><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, cnt, q0); break;
+        case 4: finalize_union_kernel<4><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, cnt, q0); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

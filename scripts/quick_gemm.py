@@ -40,9 +40,9 @@ def run(n, d, nq, k, space="cosine", iters=20, path=0):
     c.close()
 
 if __name__ == "__main__" and len(sys.argv) > 1:
-    # python scripts/quick_gemm.py NQ [D K ITERS N]: one configuration (used under ncu)
-    a = [int(x) for x in sys.argv[1:]] + [None] * 5
-    run(a[4] or 1_000_000, a[1] or 384, a[0], a[2] or 5, iters=a[3] or 5)
+    # python scripts/quick_gemm.py NQ [D K ITERS N PATH]: one configuration (used under ncu)
+    a = [int(x) for x in sys.argv[1:]] + [None] * 6
+    run(a[4] or 1_000_000, a[1] or 384, a[0], a[2] or 5, iters=a[3] or 5, path=a[5] or 0)
 elif __name__ == "__main__":
     run(1_000_000, 384, 256, 5)
     run(1_000_000, 384, 128, 5)
@@ -53,3 +53,10 @@ elif __name__ == "__main__":
     run(1_000_000, 768, 64, 20)
     run(1_000_000, 384, 1, 5)
     run(10_000, 384, 1, 5)
+    for nq in (1, 2, 4, 8, 16):
+        run(1_000_000, 384, nq, 5, path=2, iters=50)
+    run(10_000, 384, 1, 5, path=2, iters=50)
+    run(1_000_000, 512, 1, 10, path=2, iters=50)
+    run(1_000_000, 768, 1, 20, path=2, iters=50)
+    run(1_000_000, 512, 1, 10, path=1, iters=50)
+    run(1_000_000, 768, 1, 20, path=1, iters=50)
