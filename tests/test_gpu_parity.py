@@ -43,9 +43,9 @@ def _check(c, X, Q, k, space, where_mask=None, where=None, path=None):
 def test_scan_matches_oracle(space, d):
     c, X, _ = _mk(space, d, 20000, seed=d, unit=(space == "cosine"))
     Q = make_unit(7, d, 99)
-    _check(c, X, Q, 5, space)
-    _check(c, X, Q[:1], 10, space)
-    _check(c, X, Q[:3], 16, space)
+    _check(c, X, Q, 5, space, path=1)
+    _check(c, X, Q[:1], 10, space, path=1)
+    _check(c, X, Q[:3], 16, space, path=1)
     if space == "cosine":       # unit-norm random data: the bf16 certificate must hold without help
         assert c.stats()["n_exact_fallbacks"] == 0
 
