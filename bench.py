@@ -324,7 +324,7 @@ def run_gpu(args):
             step_sharded(i)
         ms_sh = timed(step_sharded, K)
         sharded = {"rows_total": world * N_ROWS, "rows_per_gpu": N_ROWS, "qps": nq * K / (ms_sh * 1e-3),
-                   "ms_per_step": ms_sh / K, "collective": "nccl all_gather of [nq,k] x (int64 row, fp64 dist, int32 count)",
+                   "ms_per_step": ms_sh / K, "collective": "ONE nccl all_gather of the packed [nq,k] x (int64 row, fp64 dist) + [nq] int32 count block",
                    "bytes_gathered_per_step": world * nq * (k * 16 + 4)}
         sh2.close()
 

@@ -71,6 +71,8 @@ typedef struct {
                                   were recomputed by the exact fp64 scan (only counted
                                   on calls with host outputs)                          */
     int32_t sm_count, device;
+    int64_t n_pool_queries;  /* K3: queries finalized from a candidate pool ...                */
+    int64_t n_pool_entries;  /* ... and the total number of pool entries they merged           */
 } b2r_stats;
 
 int b2r_abi_version(void);
@@ -133,6 +135,14 @@ int b2r_set_row_base(b2r_handle h, int64_t row_base);
 int b2r_merge_shards(const int64_t *in_rows, const double *in_dist64, const int32_t *in_count,
                      int nshards, int nq, int k, int64_t *out_rows, float *out_dist,
                      int32_t *out_count, int device, void *stream);
+
+/* Same merge over ONE gathered buffer: shard s's block starts at packed + s*shard_stride and holds rows
+ * [nq,k] int64 at off_rows, fp64 distances [nq,k] at off_dist64, counts [nq] int32 at off_count (byte offsets,
+ * 8-byte aligned) -- so a rank can expose rows/dist64/count as views of one allocation and exchange them
+ * with a single all_gather.                                                                          */
+int b2r_merge_shards_packed(const void *packed, int64_t shard_stride, int64_t off_rows, int64_t off_dist64,
+                            int64_t off_count, int nshards, int nq, int k, int64_t *out_rows, float *out_dist,
+                            int32_t *out_count, int device, void *stream);
 
 /* Diagnostics used by bench.py: run only the scoring/selection kernel selected by
  * `path` on device-resident prepared inputs, so it can be timed alone.

@@ -19,7 +19,7 @@ TYPE_DEAD = 63
 ABI_SYMBOLS = (
     "b2r_abi_version", "b2r_last_error", "b2r_create", "b2r_destroy", "b2r_clear", "b2r_reserve",
     "b2r_ingest_f32", "b2r_tombstone", "b2r_query", "b2r_query_ex", "b2r_get_rows_f32", "b2r_count",
-    "b2r_get_stats", "b2r_set_row_base", "b2r_merge_shards", "b2r_set_path", "b2r_launch_count",
+    "b2r_get_stats", "b2r_set_row_base", "b2r_merge_shards", "b2r_merge_shards_packed", "b2r_set_path", "b2r_launch_count",
     "b2r_set_kernel_timing", "b2r_kernel_time_ms",
 )
 
@@ -32,7 +32,8 @@ class B2RStats(ctypes.Structure):
     _fields_ = [("dim", ctypes.c_int32), ("dim_padded", ctypes.c_int32), ("space", ctypes.c_int32),
                 ("flags", ctypes.c_uint32), ("rows", ctypes.c_int64), ("live", ctypes.c_int64),
                 ("capacity", ctypes.c_int64), ("bytes_device", ctypes.c_int64), ("n_queries", ctypes.c_int64),
-                ("n_exact_fallbacks", ctypes.c_int64), ("sm_count", ctypes.c_int32), ("device", ctypes.c_int32)]
+                ("n_exact_fallbacks", ctypes.c_int64), ("sm_count", ctypes.c_int32), ("device", ctypes.c_int32),
+                ("n_pool_queries", ctypes.c_int64), ("n_pool_entries", ctypes.c_int64)]
 
 
 _lib = None
@@ -65,6 +66,7 @@ def load() -> ctypes.CDLL:
         "b2r_get_stats": (i32, [vp, ctypes.POINTER(B2RStats)]),
         "b2r_set_row_base": (i32, [vp, i64]),
         "b2r_merge_shards": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp]),
+        "b2r_merge_shards_packed": (i32, [vp, i64, i64, i64, i64, i32, i32, i32, vp, vp, vp, i32, vp]),
         "b2r_set_path": (i32, [vp, i32]),
         "b2r_launch_count": (i64, [vp]),
         "b2r_set_kernel_timing": (i32, [vp, i32]),

@@ -1,6 +1,7 @@
 // C ABI implementation (include/b2r.h): handle lifetime, HBM layout, host<->device
 // staging and kernel dispatch.  No compute happens on the host.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -125,6 +126,7 @@ extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device,
     if (!h) { set_error("b2r_create: host allocation failed"); return B2R_ENOMEM; }
     h->dim = dim; h->dp = round_up(dim, 64); h->space = space; h->device = device; h->flags = flags;
     h->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("B2R_TIME_STAGE")) h->timing_stage = atoi(e);
     int rc = B2R_OK;
     do {
         if (cudaMalloc(&h->max_norm2, 256) != cudaSuccess || cudaMalloc(&h->counters, 256) != cudaSuccess ||
@@ -223,7 +225,7 @@ extern "C" int b2r_get_stats(b2r_handle h, b2r_stats *out) {
     B2R_REQUIRE(h && out, "b2r_get_stats: NULL argument");
     std::lock_guard<std::mutex> g(h->mu);
     B2R_CUDA(cudaSetDevice(h->device));
-    unsigned long long c[2] = {0, 0};
+    unsigned long long c[4] = {0, 0, 0, 0};
     B2R_CUDA(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
     std::memset(out, 0, sizeof(*out));
     out->dim = h->dim; out->dim_padded = h->dp; out->space = h->space; out->flags = h->flags;
@@ -231,6 +233,7 @@ extern "C" int b2r_get_stats(b2r_handle h, b2r_stats *out) {
     out->bytes_device = (int64_t)(row_bytes_total(h) * (size_t)h->capacity);
     out->n_queries = h->n_queries; out->n_exact_fallbacks = (int64_t)c[1];
     out->sm_count = h->sm_count; out->device = h->device;
+    out->n_pool_queries = (int64_t)c[2]; out->n_pool_entries = (int64_t)c[3];
     return B2R_OK;
 }
 
@@ -348,7 +351,7 @@ namespace {
 // RAII-less pair of events around one scoring-kernel launch (only when h->timing)
 struct KernelTimer {
     b2r_index *h; cudaStream_t s; std::pair<cudaEvent_t, cudaEvent_t> ev; bool on;
-    KernelTimer(b2r_index *h_, cudaStream_t s_) : h(h_), s(s_), on(h_->timing) {
+    KernelTimer(b2r_index *h_, cudaStream_t s_, int stage = 0) : h(h_), s(s_), on(h_->timing && h_->timing_stage == stage) {
         if (!on) return;
         if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
         else if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) { on = false; return; }
@@ -400,8 +403,7 @@ int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const Finaliz
     p.cta_lists = (KeyD *)h->exact_lists.p; p.tickets = h->tickets + 1;
     p.n_fallbacks = (long long *)(h->counters + 1);
     p.fin = fin;
-    KernelTimer kt(h, s);
-    if (!force_all) kt.on = false;      // the certificate fix-up is not the scoring kernel
+    KernelTimer kt(h, s, force_all ? 0 : 5);   // the certificate fix-up is not the scoring kernel
     B2R_CUDA(exact_launch(epl, p, grid, s));
     kt.stop();
     h->n_launches++;
@@ -461,8 +463,12 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         if (sample_tiles) {
             gp.tiles_total = sample_tiles; gp.tile_mul = tiles_total / sample_tiles; gp.sample_mode = 1;
             gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, sample_tiles));
+            KernelTimer kt2(h, s, 2);
             B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
+            kt2.stop();
+            KernelTimer kt3(h, s, 3);
             B2R_CUDA(sample_threshold_launch(gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, L, gp.gthr, gp.cnt, q0, nq_here, s));
+            kt3.stop();
             h->n_launches += 2;
         }
         gp.tiles_total = tiles_total; gp.tile_mul = 1; gp.sample_mode = 0;
@@ -471,7 +477,9 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
         kt.stop();
         h->n_launches++;
-        B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, gp.gthr, gp.cnt, q0, nq_here, s));
+        KernelTimer kt4(h, s, 4);
+        B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, gp.gthr, gp.cnt, h->counters + 2, q0, nq_here, s));
+        kt4.stop();
         h->n_launches++;
     }
     return B2R_OK;
@@ -537,7 +545,8 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     const bool gemm_ok = gemm_supported(h->dp, k);
     // K3's TMA-fed stream is also the faster batch-1 scan up to 512 dims (6.2 vs 5.1 TB/s at 1M x 384); at 768
     // dims its shallower pipeline loses to K2 until the corpus pass is shared by a handful of queries
-    if (path == 0) path = (gemm_ok && (nq >= GEMM_MIN_BATCH || h->dp <= 512)) ? 2 : scan_ok ? 1 : 3;
+    // (small shards: K2's single launch has the lower fixed cost)
+    if (path == 0) path = (gemm_ok && (nq >= GEMM_MIN_BATCH || (h->dp <= 512 && h->rows >= 262144))) ? 2 : scan_ok ? 1 : 3;
     if (path == 2 && !gemm_ok) path = scan_ok ? 1 : 3;
     if (path == 1 && !scan_ok) path = 3;
     if (h->rows == 0) path = 3;   // empty collection: Chroma returns empty lists; only the padding is written
@@ -554,9 +563,10 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
         const int wpb = INGEST_THREADS / 32;
         int grid = std::min((nq + wpb - 1) / wpb, h->sm_count * 8);
         const bool vec = (h->dim % 8 == 0) && (((uintptr_t)q_raw & 15) == 0);
-        if (vec) ingest_kernel<true><<<grid, INGEST_THREADS, 0, s>>>(p);
-        else ingest_kernel<false><<<grid, INGEST_THREADS, 0, s>>>(p);
-        B2R_CUDA(cudaGetLastError());
+        KernelTimer kt1(h, s, 1);
+        if (vec) B2R_CUDA(launch_pdl(ingest_kernel<true>, dim3(grid), dim3(INGEST_THREADS), 0, s, p));
+        else B2R_CUDA(launch_pdl(ingest_kernel<false>, dim3(grid), dim3(INGEST_THREADS), 0, s, p));
+        kt1.stop();
         h->n_launches++;
     }
 
@@ -611,8 +621,9 @@ namespace {
 constexpr int MERGE_THREADS = 256;
 // one CTA per query: rank every gathered candidate by counting (<= nshards*k <= 2048)
 __global__ void __launch_bounds__(MERGE_THREADS)
-merge_shards_kernel(const long long *in_rows, const double *in_dist, const int *in_count, int nshards, int nq,
-                    int k, long long *out_rows, float *out_dist, int *out_count) {
+merge_shards_kernel(const char *in_rows_b, const char *in_dist_b, const char *in_count_b, long long stride_rows,
+                    long long stride_dist, long long stride_count, int nshards, int nq, int k, long long *out_rows,
+                    float *out_dist, int *out_count) {
     extern __shared__ __align__(16) unsigned char sm[];
     const int qi = blockIdx.x;
     const int total = nshards * k;
@@ -624,8 +635,11 @@ merge_shards_kernel(const long long *in_rows, const double *in_dist, const int *
     int my_valid = 0;
     for (int c = threadIdx.x; c < total; c += MERGE_THREADS) {
         int sh = c / k, i = c % k;
-        bool ok = i < in_count[(size_t)sh * nq + qi];
-        size_t src = ((size_t)sh * nq + qi) * k + i;
+        const long long *in_rows = reinterpret_cast<const long long *>(in_rows_b + (size_t)sh * stride_rows);
+        const double *in_dist = reinterpret_cast<const double *>(in_dist_b + (size_t)sh * stride_dist);
+        const int *in_count = reinterpret_cast<const int *>(in_count_b + (size_t)sh * stride_count);
+        bool ok = i < in_count[qi];
+        size_t src = (size_t)qi * k + i;
         sd[c] = ok ? in_dist[src] : __longlong_as_double(0x7ff0000000000000ll);
         sr[c] = ok ? in_rows[src] : -1;
         my_valid += ok ? 1 : 0;
@@ -656,17 +670,38 @@ merge_shards_kernel(const long long *in_rows, const double *in_dist, const int *
 }
 }  // namespace
 
-extern "C" int b2r_merge_shards(const int64_t *in_rows, const double *in_dist64, const int32_t *in_count,
-                                int nshards, int nq, int k, int64_t *out_rows, float *out_dist,
-                                int32_t *out_count, int device, void *stream) {
-    B2R_REQUIRE(in_rows && in_dist64 && in_count && out_rows && out_dist && out_count, "b2r_merge_shards: NULL argument");
+// shard s of each input starts s * (its stride) bytes after the base pointer
+static int merge_launch(const char *rows_b, const char *dist_b, const char *count_b, long long stride_rows,
+                        long long stride_dist, long long stride_count, int nshards, int nq, int k, int64_t *out_rows,
+                        float *out_dist, int32_t *out_count, int device, void *stream) {
     B2R_REQUIRE(nshards >= 1 && nq >= 1 && k >= 1, "b2r_merge_shards: bad sizes");
     B2R_REQUIRE((size_t)nshards * k <= 8192, "b2r_merge_shards: nshards*k must be <= 8192");
     B2R_CUDA(cudaSetDevice(device));
     size_t smem = (size_t)nshards * k * 16;
-    B2R_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_shards_kernel<<<nq, MERGE_THREADS, smem, (cudaStream_t)stream>>>(
-        (const long long *)in_rows, in_dist64, in_count, nshards, nq, k, (long long *)out_rows, out_dist, out_count);
+    if (smem > 48 * 1024)
+        B2R_CUDA(cudaFuncSetAttribute(merge_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_shards_kernel<<<nq, MERGE_THREADS, smem, (cudaStream_t)stream>>>(rows_b, dist_b, count_b, stride_rows, stride_dist,
+                                                                           stride_count, nshards, nq, k, (long long *)out_rows,
+                                                                           out_dist, out_count);
     B2R_CUDA(cudaGetLastError());
     return B2R_OK;
+}
+
+extern "C" int b2r_merge_shards(const int64_t *in_rows, const double *in_dist64, const int32_t *in_count,
+                                int nshards, int nq, int k, int64_t *out_rows, float *out_dist,
+                                int32_t *out_count, int device, void *stream) {
+    B2R_REQUIRE(in_rows && in_dist64 && in_count && out_rows && out_dist && out_count, "b2r_merge_shards: NULL argument");
+    return merge_launch((const char *)in_rows, (const char *)in_dist64, (const char *)in_count, (long long)nq * k * 8,
+                        (long long)nq * k * 8, (long long)nq * 4, nshards, nq, k, out_rows, out_dist, out_count, device, stream);
+}
+
+extern "C" int b2r_merge_shards_packed(const void *packed, int64_t shard_stride, int64_t off_rows, int64_t off_dist64,
+                                       int64_t off_count, int nshards, int nq, int k, int64_t *out_rows, float *out_dist,
+                                       int32_t *out_count, int device, void *stream) {
+    B2R_REQUIRE(packed && out_rows && out_dist && out_count, "b2r_merge_shards_packed: NULL argument");
+    B2R_REQUIRE(shard_stride > 0 && off_rows % 8 == 0 && off_dist64 % 8 == 0 && off_count % 4 == 0,
+                "b2r_merge_shards_packed: bad layout");
+    const char *b = (const char *)packed;
+    return merge_launch(b + off_rows, b + off_dist64, b + off_count, shard_stride, shard_stride, shard_stride, nshards, nq, k,
+                        out_rows, out_dist, out_count, device, stream);
 }

@@ -192,6 +192,14 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Programmatic dependent launch (PDL).  Every kernel of a query is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so it may start while its predecessor on the stream is
+// still running: pdl_wait() blocks until the predecessor grid has completed and its writes are visible (call
+// it before the first access to anything an earlier kernel produced OR still reads), pdl_trigger() lets the
+// successor begin its own launch/prologue early.  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // row filter: tombstones carry type code 63, which no mask ever has set
 #define B2R_TYPE_DEAD 63
 __device__ __forceinline__ bool row_passes(unsigned row, const uint8_t *__restrict__ type_code,

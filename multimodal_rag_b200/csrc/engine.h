@@ -29,6 +29,18 @@ void set_error(const std::string &msg);
         }                                                                                   \
     } while (0)
 
+// launch `k` allowing programmatic dependent launch after the previous kernel on the stream
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, std::forward<Args>(args)...);
+}
+
 // ---- launchers implemented in the kernel TUs ----
 // returns false when no kernel is built for (dp, nq_group, epl)
 bool scan_supported(int dp);
@@ -53,7 +65,8 @@ cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_m
 cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
                                     unsigned *cnt, int q0, int nq, cudaStream_t s);
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
-                                  int entries_per_query, unsigned *gthr, unsigned *cnt, int q0, int nq, cudaStream_t s);
+                                  int entries_per_query, unsigned *gthr, unsigned *cnt, unsigned long long *pool_stats, int q0, int nq,
+                                  cudaStream_t s);
 
 struct DevBuf {
     void *p = nullptr;
@@ -97,6 +110,8 @@ struct b2r_index {
     // optional per-kernel timing (bench.py roofline): CUDA events recorded around the scoring
     // kernel launches on the caller's stream, resolved lazily by b2r_kernel_time_ms
     bool timing = false;
+    int timing_stage = 0;           // which launch the events bracket: 0 scoring (default); B2R_TIME_STAGE=1..5 (development):
+                                    // 1 prepare, 2 sampling pass, 3 sample reducer, 4 finalize, 5 exact fix-up
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
     double scoring_ms = 0.0;
     int64_t scoring_launches = 0;

@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
 
     // Work list: every query (forced) or the compacted list of failed certificates.  The grid is
     // sized to be fully resident, so waiting on another CTA's progress below cannot deadlock.
+    pdl_wait();
+    pdl_trigger();
     int count = p.force_all ? p.nq : min(__ldcg(&p.fin.need_ctl[0]), p.nq);
     unsigned *slot_gen = p.tickets + EXACT_MAX_BATCH;
     for (int it = 0; it < count; ++it) {

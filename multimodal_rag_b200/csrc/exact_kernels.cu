@@ -41,8 +41,7 @@ int exact_max_grid(int epl, int dp, int sm_count) {
 cudaError_t exact_launch(int epl, const ExactParams &p, int grid, cudaStream_t s) {
     exact_fn f = lookup(epl);
     if (!f) return cudaErrorInvalidValue;
-    f<<<grid, EXACT_THREADS, exact_smem_bytes(epl, p.fin.dp), s>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(f, dim3(grid), dim3(EXACT_THREADS), exact_smem_bytes(epl, p.fin.dp), s, p);
 }
 
 }  // namespace b2r

@@ -331,6 +331,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_wait();          // everything above overlapped the previous kernel; queries / bounds / bitmap are read below
+    pdl_trigger();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -437,29 +439,34 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 // nothing that scores below it can be among the L best of the shard.
 // ---------------------------------------------------------------------------------
 template <int DUMMY>
-__global__ void sample_threshold_kernel(const KeyS *__restrict__ lists, int list_stride, int max_entries, int L,
-                                        unsigned *gthr, unsigned *cnt, int q0, int nq) {
-    // one warp per query: the L-th largest score key by bitwise bisection over warp-wide counts
-    extern __shared__ unsigned sm_keys[];                 // [warps][entries_per_query]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int qi = q0 + blockIdx.x * (blockDim.x / 32) + warp;
-    if (qi >= q0 + nq) return;
-    unsigned *mine = sm_keys + (size_t)warp * max_entries;
+__global__ void __launch_bounds__(256) sample_threshold_kernel(const KeyS *__restrict__ lists, int list_stride, int max_entries,
+                                                               int L, unsigned *gthr, unsigned *cnt, int q0) {
+    // one CTA per query: the L-th largest score key by bitwise bisection on CTA-wide counts
+    extern __shared__ unsigned sm_keys[];                 // [max_entries]
+    __shared__ int s_count[3];
+    const int lane = threadIdx.x & 31;
+    const int qi = q0 + blockIdx.x;
     const KeyS *src = lists + (size_t)qi * list_stride;
-    const int entries_per_query = min((int)cnt[qi], max_entries);
-    for (int i = lane; i < entries_per_query; i += 32) mine[i] = (unsigned)(src[i].v >> 32);   // ord(score)
-    __syncwarp();
-    if (lane == 0) cnt[qi] = 0u;                          // the main pass appends from scratch
+    pdl_wait();
+    pdl_trigger();
+    const int entries = min((int)cnt[qi], max_entries);
+    for (int i = threadIdx.x; i < entries; i += 256) sm_keys[i] = (unsigned)(src[i].v >> 32);   // ord(score)
+    if (threadIdx.x == 0) s_count[0] = s_count[1] = s_count[2] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) cnt[qi] = 0u;                   // the main pass appends from scratch
     unsigned t = 0;
 #pragma unroll 1
-    for (int bit = 31; bit >= 10; --bit) {                // 22 bits: sign, exponent, 13 mantissa bits (a lower bound)
+    for (int bit = 31, it = 0; bit >= 10; --bit, ++it) {  // 22 bits: sign, exponent, 13 mantissa bits (a lower bound)
         const unsigned cand = t | (1u << bit);
         int c = 0;
-        for (int i = lane; i < entries_per_query; i += 32) c += mine[i] >= cand ? 1 : 0;
+        for (int i = threadIdx.x; i < entries; i += 256) c += sm_keys[i] >= cand ? 1 : 0;
         c = __reduce_add_sync(FULL_MASK, c);
-        if (c >= L) t = cand;
+        if (lane == 0 && c) atomicAdd(&s_count[it % 3], c);
+        if (threadIdx.x == 0) s_count[(it + 1) % 3] = 0;
+        __syncthreads();
+        if (s_count[it % 3] >= L) t = cand;
     }
-    if (lane == 0 && t != 0u) atomicMax(&gthr[qi], t);
+    if (threadIdx.x == 0 && t != 0u) atomicMax(&gthr[qi], t);
 }
 
 // ---------------------------------------------------------------------------------
@@ -472,7 +479,7 @@ constexpr int FU_MAX_SEL = 512;       // survivors of the score cut that are ran
 template <int EPL>
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, int list_stride, int max_entries,
-                      unsigned *__restrict__ gthr, unsigned *__restrict__ cnt, int q0) {
+                      unsigned *__restrict__ gthr, unsigned *__restrict__ cnt, unsigned long long *pool_stats, int q0) {
     constexpr int KP = 32 * EPL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyS *stage = reinterpret_cast<KeyS *>(smem_raw);                       // [FIN_WARPS*KP]
@@ -484,6 +491,8 @@ finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, 
     __shared__ int s_count[3], s_nsel;
     const int qi = q0 + blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();
+    pdl_trigger();
     const int entries = min((int)cnt[qi], max_entries);
     const unsigned g = gthr[qi];
     const KeyS *src = lists + (size_t)qi * list_stride;
@@ -497,7 +506,7 @@ finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, 
         for (int i = threadIdx.x; i < entries; i += FIN_THREADS) pool[i] = src[i];
         __syncthreads();
         unsigned t = 0;                                    // keep entries whose score key is >= t
-        if (entries > KP) {
+        if (entries > FU_MAX_SEL) {                        // small pools are ranked whole
 #pragma unroll 1
             for (int bit = 31, it = 0; bit >= 10; --bit, ++it) {   // 22 bits of the ordered score: a lower bound of the KP-th best
                 const unsigned cand = t | (1u << bit);
@@ -510,22 +519,31 @@ finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, 
                 if (s_count[it % 3] >= KP) t = cand;
             }
         }
-        for (int i = threadIdx.x; i < entries; i += FIN_THREADS) {
-            const KeyS k = pool[i];
-            if ((unsigned)(k.v >> 32) >= t) {
-                const int slot = atomicAdd(&s_nsel, 1);
-                if (slot < FU_MAX_SEL) sel[slot] = k;
+        const KeyS *ranked = pool;                         // small pools are ranked in place
+        int nsel = entries;
+        if (entries > FU_MAX_SEL) {
+            for (int i0 = warp * 32; i0 < entries; i0 += FIN_THREADS) {      // warp-aggregated compaction
+                const int i = i0 + lane;
+                const KeyS k = i < entries ? pool[i] : KeyS::worst();
+                const bool keep = i < entries && (unsigned)(k.v >> 32) >= t;
+                const unsigned m = __ballot_sync(FULL_MASK, keep);
+                int base = 0;
+                if (lane == 0 && m) base = atomicAdd(&s_nsel, __popc(m));
+                base = __shfl_sync(FULL_MASK, base, 0);
+                const int slot = base + __popc(m & ((1u << lane) - 1));
+                if (keep && slot < FU_MAX_SEL) sel[slot] = k;
             }
+            __syncthreads();
+            nsel = s_nsel;
+            ranked = sel;
         }
-        __syncthreads();
-        const int nsel = s_nsel;
         if (nsel <= FU_MAX_SEL) {
             for (int i = threadIdx.x; i < KP; i += FIN_THREADS) stage[i] = KeyS::worst();
             __syncthreads();
             for (int i = threadIdx.x; i < nsel; i += FIN_THREADS) {
-                const KeyS me = sel[i];
+                const KeyS me = ranked[i];
                 int rank = 0;
-                for (int j = 0; j < nsel; ++j) rank += KeyS::better(sel[j], me) ? 1 : 0;
+                for (int j = 0; j < nsel; ++j) rank += KeyS::better(ranked[j], me) ? 1 : 0;
                 if (rank < KP) stage[rank] = me;
             }
             __syncthreads();
@@ -557,7 +575,10 @@ finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, 
         cta_tree_merge<KeyS, EPL>(wl, stage, warp, lane);
         nvalid = __syncthreads_count(threadIdx.x < KP && stage[threadIdx.x < KP ? threadIdx.x : 0].valid());
     }
-    if (threadIdx.x == 0) { gthr[qi] = 0u; cnt[qi] = 0u; }   // leave the shared state clean for the next call
+    if (threadIdx.x == 0) {
+        gthr[qi] = 0u; cnt[qi] = 0u;                        // leave the shared state clean for the next call
+        atomicAdd(pool_stats, 1ull); atomicAdd(pool_stats + 1, (unsigned long long)entries);
+    }
     // rows outside the candidate set: either in the pool but below the KP-th candidate, or never kept
     // by any list, hence <= the final shared bound (0 = nothing was ever rejected)
     float T = -INFINITY;

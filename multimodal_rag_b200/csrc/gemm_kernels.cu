@@ -124,8 +124,7 @@ cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const
             done[key] = true;
         }
     }
-    f<<<p.n_slices * p.n_qblocks, GEMM_THREADS, smem, s>>>(tm_q, tm_x, p);
-    return cudaGetLastError();
+    return launch_pdl(f, dim3(p.n_slices * p.n_qblocks), dim3(GEMM_THREADS), smem, s, tm_q, tm_x, p);
 }
 
 cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_mask, const uint32_t *allow_bits,
@@ -139,15 +138,14 @@ cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_m
 
 cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
                                     unsigned *cnt, int q0, int nq, cudaStream_t s) {
-    int wpc = (int)std::min<size_t>(8, (size_t)(40 * 1024) / ((size_t)entries_per_query * 4));   // stay under the 48 KB default
-    if (wpc < 1) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)wpc * entries_per_query * 4;
-    sample_threshold_kernel<0><<<(nq + wpc - 1) / wpc, wpc * 32, smem, s>>>(lists, list_stride, entries_per_query, L, gthr, cnt, q0, nq);
-    return cudaGetLastError();
+    const size_t smem = (size_t)entries_per_query * 4;
+    if (smem > 40 * 1024) return cudaErrorInvalidValue;   // 148 SMs x 2 halves x L=32 x 4 B = 37.9 KB at most
+    return launch_pdl(sample_threshold_kernel<0>, dim3(nq), dim3(256), smem, s, lists, list_stride, entries_per_query, L, gthr, cnt, q0);
 }
 
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
-                                  int entries_per_query, unsigned *gthr, unsigned *cnt, int q0, int nq, cudaStream_t s) {
+                                  int entries_per_query, unsigned *gthr, unsigned *cnt, unsigned long long *pool_stats, int q0, int nq,
+                                  cudaStream_t s) {
     const size_t smem = finalize_union_smem(epl, fin.dp);
     if (smem > 48 * 1024) {      // opt in to large dynamic shared memory (per function; cheap, idempotent)
         cudaError_t e = cudaSuccess;
@@ -157,12 +155,11 @@ cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS
         if (e != cudaSuccess) return e;
     }
     switch (epl) {
-        case 1: finalize_union_kernel<1><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, cnt, q0); break;
-        case 2: finalize_union_kernel<2><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, cnt, q0); break;
-        case 4: finalize_union_kernel<4><<<nq, FIN_THREADS, smem, s>>>(fin, lists, list_stride, entries_per_query, gthr, cnt, q0); break;
+        case 1: return launch_pdl(finalize_union_kernel<1>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
+        case 2: return launch_pdl(finalize_union_kernel<2>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
+        case 4: return launch_pdl(finalize_union_kernel<4>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 }  // namespace b2r

@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(const IngestPara
     const long long gw = (long long)blockIdx.x * (INGEST_THREADS / 32) + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * (INGEST_THREADS / 32);
     const int d = p.d, dp = p.dp, chunks = dp / 8;
+    pdl_wait();          // query preparation overwrites buffers the previous query's kernels may still read
+    pdl_trigger();
     for (long long r = gw; r < p.n; r += nw) {
         const float *xr = p.x + r * d;
         float inv = 1.0f;

@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_topk_kernel(const ScanParam
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
+    pdl_wait();
+    pdl_trigger();
     // queries -> registers (this lane only ever touches chunks j*LPR+sl of a row)
     float qr[NQ][CPL][8];
 #pragma unroll

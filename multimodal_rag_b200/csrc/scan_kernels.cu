@@ -102,8 +102,7 @@ cudaError_t scan_launch(int dp, int nq, int epl, const ScanParams &p, int grid, 
     scan_fn f = lookup(dp, nq, epl);
     if (!f) return cudaErrorInvalidValue;
     size_t smem = scan_smem_bytes(epl, dp, p.stage_keys);
-    f<<<grid, SCAN_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(f, dim3(grid), dim3(SCAN_THREADS), smem, s, p);
 }
 
 // rows one CTA consumes per tile (grid sizing in the API layer)

@@ -209,16 +209,20 @@ class DeviceShard:
         return first.value
 
     def alloc_out(self, nq, k):
+        """Outputs of one batch.  rows / d64 / cnt are views of ONE flat allocation ('pack'), so the
+        cross-shard exchange is a single all_gather of that block."""
         dev = torch.device("cuda", self.device)
         R = self.world
+        off_rows, off_d64, off_cnt = 0, nq * k * 8, 2 * nq * k * 8
+        stride = (off_cnt + nq * 4 + 15) // 16 * 16
+        pack = torch.zeros((stride,), dtype=torch.uint8, device=dev)
         return {
-            "rows": torch.empty((nq, k), dtype=torch.int64, device=dev),
+            "pack": pack, "layout": (stride, off_rows, off_d64, off_cnt),
+            "rows": pack[off_rows:off_d64].view(torch.int64).view(nq, k),
+            "d64": pack[off_d64:off_cnt].view(torch.float64).view(nq, k),
+            "cnt": pack[off_cnt:off_cnt + nq * 4].view(torch.int32),
             "dist": torch.empty((nq, k), dtype=torch.float32, device=dev),
-            "d64": torch.empty((nq, k), dtype=torch.float64, device=dev),
-            "cnt": torch.empty((nq,), dtype=torch.int32, device=dev),
-            "a_rows": torch.empty((R, nq, k), dtype=torch.int64, device=dev),
-            "a_d64": torch.empty((R, nq, k), dtype=torch.float64, device=dev),
-            "a_cnt": torch.empty((R, nq), dtype=torch.int32, device=dev),
+            "a_pack": torch.empty((R, stride), dtype=torch.uint8, device=dev),
             "m_rows": torch.empty((nq, k), dtype=torch.int64, device=dev),
             "m_dist": torch.empty((nq, k), dtype=torch.float32, device=dev),
             "m_cnt": torch.empty((nq,), dtype=torch.int32, device=dev),
@@ -236,12 +240,11 @@ class DeviceShard:
         self.query_local(q, k, o)
         if self.world == 1:
             return o["rows"], o["dist"], o["cnt"]
-        dist.all_gather_into_tensor(o["a_rows"], o["rows"], group=self.group)
-        dist.all_gather_into_tensor(o["a_d64"], o["d64"], group=self.group)
-        dist.all_gather_into_tensor(o["a_cnt"], o["cnt"], group=self.group)
+        dist.all_gather_into_tensor(o["a_pack"], o["pack"], group=self.group)      # the only data-path collective
         st = torch.cuda.current_stream().cuda_stream
         nq = q.shape[0]
-        _lib.check(self.lib.b2r_merge_shards(o["a_rows"].data_ptr(), o["a_d64"].data_ptr(), o["a_cnt"].data_ptr(),
-                                             self.world, nq, k, o["m_rows"].data_ptr(), o["m_dist"].data_ptr(),
-                                             o["m_cnt"].data_ptr(), self.device, st), "b2r_merge_shards")
+        stride, off_rows, off_d64, off_cnt = o["layout"]
+        _lib.check(self.lib.b2r_merge_shards_packed(o["a_pack"].data_ptr(), stride, off_rows, off_d64, off_cnt,
+                                                    self.world, nq, k, o["m_rows"].data_ptr(), o["m_dist"].data_ptr(),
+                                                    o["m_cnt"].data_ptr(), self.device, st), "b2r_merge_shards_packed")
         return o["m_rows"], o["m_dist"], o["m_cnt"]
