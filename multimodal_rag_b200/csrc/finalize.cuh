@@ -35,7 +35,8 @@ __device__ __forceinline__ double exact_distance_warp(const FinalizeParams &p, c
     if (p.master) {
         const float4 *xr = reinterpret_cast<const float4 *>(p.master + (size_t)row * dp);
         const float4 *q4 = reinterpret_cast<const float4 *>(qv);
-        for (int c = lane; c < dp / 4; c += 32) {
+#pragma unroll 4
+        for (int c = lane; c < dp / 4; c += 32) {      // unrolled so the row's loads are all in flight before the fp64 chain
             float4 x = __ldcg(xr + c);
             float4 q = q4[c];
             if (p.space == 0) {
@@ -49,6 +50,7 @@ __device__ __forceinline__ double exact_distance_warp(const FinalizeParams &p, c
         }
     } else {
         const uint4 *xr = p.corpus + (size_t)row * (dp / 8);
+#pragma unroll 4
         for (int c = lane; c < dp / 8; c += 32) {
             uint4 w = __ldcg(xr + c);
             const float *qq = qv + c * 8;

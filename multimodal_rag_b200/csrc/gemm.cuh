@@ -543,7 +543,8 @@ finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, 
             for (int i = threadIdx.x; i < nsel; i += FIN_THREADS) {
                 const KeyS me = ranked[i];
                 int rank = 0;
-                for (int j = 0; j < nsel; ++j) rank += KeyS::better(ranked[j], me) ? 1 : 0;
+#pragma unroll 8
+                for (int j = 0; j < nsel; ++j) rank += KeyS::better(ranked[j], me) ? 1 : 0;   // broadcast LDS.64, 8 in flight
                 if (rank < KP) stage[rank] = me;
             }
             __syncthreads();
