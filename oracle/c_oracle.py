@@ -13,8 +13,8 @@ SPACE_CODE = {"l2": 0, "cosine": 1, "ip": 2}
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "exact_topk.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("exact_topk.c", "hnsw_port.c", "Makefile")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "libb2r_oracle.so"])
     return _SO
 
@@ -33,6 +33,15 @@ def lib():
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib.b2r_oracle_topk.restype = ctypes.c_int
+        _lib.b2r_hnsw_threads.restype = ctypes.c_int
+        _lib.b2r_hnsw_build.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_uint]
+        _lib.b2r_hnsw_build.restype = ctypes.c_void_p
+        _lib.b2r_hnsw_search.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p]
+        _lib.b2r_hnsw_search.restype = None
+        _lib.b2r_hnsw_free.argtypes = [ctypes.c_void_p]
+        _lib.b2r_hnsw_free.restype = None
     return _lib
 
 
@@ -65,3 +74,35 @@ def topk(X, Q, k, space, allowed=None, acc64=True):
     if rc != 0:
         raise ValueError("b2r_oracle_topk: bad arguments")
     return rows, dist, cnt
+
+
+class Hnsw:
+    """hnsw_port.c: restatement of the chroma-hnswlib index the reference queries (Chroma defaults
+    M=16, ef_construction=100, search ef = max(10, k)).  X must be stored rows (normalised for cosine)
+    and stay alive while the index is used."""
+
+    def __init__(self, X: np.ndarray, space: str = "cosine", M: int = 16, ef_construction: int = 100, seed: int = 100):
+        self.X = np.ascontiguousarray(X, dtype=np.float32)
+        self.space = space
+        self._h = lib().b2r_hnsw_build(self.X.ctypes.data, self.X.shape[0], self.X.shape[1],
+                                       0 if space == "l2" else 1, M, ef_construction, seed)
+        if not self._h:
+            raise ValueError("b2r_hnsw_build failed")
+
+    def query(self, Q, k: int, ef: int = 10):
+        Q = np.ascontiguousarray(np.atleast_2d(Q), dtype=np.float32)
+        rows = np.empty((Q.shape[0], k), dtype=np.int64)
+        dist = np.empty((Q.shape[0], k), dtype=np.float32)
+        lib().b2r_hnsw_search(self._h, Q.ctypes.data, Q.shape[0], k, max(ef, k), rows.ctypes.data, dist.ctypes.data)
+        return rows, dist
+
+    def close(self):
+        if self._h:
+            lib().b2r_hnsw_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
