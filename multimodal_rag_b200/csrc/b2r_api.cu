@@ -153,7 +153,7 @@ extern "C" int b2r_destroy(b2r_handle h) {
     cudaFree(h->max_norm2); cudaFree(h->counters); cudaFree(h->tickets); cudaFree(h->need_ctl);
     DevBuf *bufs[] = {&h->x_stage, &h->t_stage, &h->q_raw, &h->q_prep, &h->allow, &h->rows_stage, &h->gather_out,
                       &h->o_rows, &h->o_dist, &h->o_dist64, &h->o_count, &h->need_list, &h->scan_lists,
-                      &h->exact_lists, &h->q_bf16, &h->q_err, &h->pass_bits, &h->gthr, &h->gemm_lists};
+                      &h->exact_lists, &h->q_bf16, &h->q_err, &h->pass_bits, &h->gthr, &h->gemm_lists, &h->gemm_regions};
     for (DevBuf *b : bufs) release(*b);
     for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -415,15 +415,22 @@ constexpr int GEMM_MIN_BATCH = 5;        // below this the scan reads the corpus
 constexpr int GEMM_MAX_QBLOCKS = 8;      // 128-query blocks per launch (1024 queries per corpus pass)
 constexpr int GEMM_SAMPLE_TILES = 128;   // tiles of the threshold-seeding sample (32k rows at BN = 256)
 constexpr int GEMM_SAMPLE_MIN_BATCH = 24;
+constexpr int GEMM_REGION_CAP = 256;       // pool mode: entries per private (query, slice, half) region
+constexpr int GEMM_POOL_CAP = 16384;        // pool mode: compact pool entries per query (>= SMs*2*32 for the sampling pass)
+constexpr int GEMM_POOL_SAMPLE_RANK = 32;  // pool mode: the bound is the 32nd best sampled score
 
 int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams &fin, const b2r_filter &f,
                       const uint32_t *allow_dev, cudaStream_t s) {
-    const int L = gemm_list_len(k);
+    const int L = gemm_list_len(k);                    // 8 / 16 / 32, or 0 = pool mode (32 < k <= 128)
+    const bool pool_mode = L == 0;
+    const int L_sample = pool_mode ? GEMM_POOL_SAMPLE_RANK : L;
     const int BN = gemm_tile_rows(h->dp);
     const int tiles_total = (int)((h->rows + BN - 1) / BN);
     const unsigned n_words = (unsigned)tiles_total * (unsigned)(BN / 32);
     const int qblocks_total = (nq + GEMM_BM - 1) / GEMM_BM;
-    const int list_stride = h->sm_count * GEMM_HALVES * L;
+    // pool capacity per query: list mode = every list full; pool mode = 16x the expected 1024 entries (beyond that
+    // the query is flagged and re-done by the exact scan)
+    const int list_stride = pool_mode ? GEMM_POOL_CAP : h->sm_count * GEMM_HALVES * L;
     int rc;
     if ((rc = ensure(h->pass_bits, (size_t)n_words * 4 + 16)) != B2R_OK) return rc;
     {   // gthr is all-zero between calls: zeroed when (re)allocated, and finalize_union_kernel clears what it read
@@ -431,7 +438,13 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         if ((rc = ensure(h->gthr, (size_t)qblocks_total * GEMM_BM * 4 * 2)) != B2R_OK) return rc;   // bounds, then cursors
         if (h->gthr.p != before) B2R_CUDA(cudaMemsetAsync(h->gthr.p, 0, h->gthr.bytes, s));
     }
+    // list mode pools: [nq][SMs*2*L].  Pool mode: the sampling pass needs [nq][SMs*2*32] and the main pass
+    // compacts at most [launch queries][slots*cap] -- both fit the same allocation.
+    const int nq_launch_max = std::min(qblocks_total, GEMM_MAX_QBLOCKS) * GEMM_BM;   // padded: every lane of a block owns a region
     if ((rc = ensure(h->gemm_lists, sizeof(KeyS) * (size_t)nq * list_stride)) != B2R_OK) return rc;
+    if (pool_mode &&
+        (rc = ensure(h->gemm_regions, sizeof(KeyS) * (size_t)nq_launch_max * h->sm_count * GEMM_HALVES * GEMM_REGION_CAP)) != B2R_OK)
+        return rc;
     const bool pb_hit = !allow_dev && h->pb_buf == h->pass_bits.p && h->pb_gen == h->mut_gen && h->pb_rows == h->rows &&
                         h->pb_mask == f.type_mask && h->pb_bn == BN;
     if (!pb_hit) {
@@ -449,9 +462,14 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         if ((rc = gemm_encode_map(&h->tm_query, h->q_bf16.p, h->dp, (uint64_t)nq, GEMM_BM)) != B2R_OK) return rc;
         h->tm_query_base = h->q_bf16.p; h->tm_query_rows = nq;
     }
-    // sampling pass: GEMM_SAMPLE_TILES tiles strided across the shard seed gthr[q] (skipped for small shards)
-    // and for small batches: with a handful of live lanes per warp the list warm-up costs a few microseconds)
-    const int sample_tiles = (tiles_total >= 2 * GEMM_SAMPLE_TILES && nq >= GEMM_SAMPLE_MIN_BATCH) ? GEMM_SAMPLE_TILES : 0;
+    // Sampling pass: tiles strided across the shard seed gthr[q].
+    //   list mode: 128 tiles, skipped for small shards and for small batches (with a handful of live lanes per
+    //              warp the list warm-up costs a few microseconds);
+    //   pool mode: 1/32 of the shard (>= 4 tiles) whenever a slice could overflow a private region without a
+    //              bound -- the expected pool is then 32 * 32 = 1024 entries per query whatever the shard size.
+    int sample_tiles;
+    if (pool_mode) sample_tiles = tiles_total >= 8 ? std::max(4, tiles_total / 32) : 0;
+    else sample_tiles = (tiles_total >= 2 * GEMM_SAMPLE_TILES && nq >= GEMM_SAMPLE_MIN_BATCH) ? GEMM_SAMPLE_TILES : 0;
     for (int qb0 = 0; qb0 < qblocks_total; qb0 += GEMM_MAX_QBLOCKS) {
         GemmParams gp;
         gp.n = (unsigned)h->rows; gp.nq = nq; gp.qblock0 = qb0;
@@ -459,15 +477,16 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         gp.list_stride = list_stride;
         gp.pass_bits = (const uint32_t *)h->pass_bits.p; gp.bias = h->bias;
         gp.gthr = (unsigned *)h->gthr.p; gp.cnt = gp.gthr + (size_t)qblocks_total * GEMM_BM; gp.lists = (KeyS *)h->gemm_lists.p;
+        gp.regions = (KeyS *)h->gemm_regions.p; gp.region_cap = GEMM_REGION_CAP;
         const int q0 = qb0 * GEMM_BM, nq_here = std::min(nq - q0, gp.n_qblocks * GEMM_BM);
         if (sample_tiles) {
             gp.tiles_total = sample_tiles; gp.tile_mul = tiles_total / sample_tiles; gp.sample_mode = 1;
             gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, sample_tiles));
             KernelTimer kt2(h, s, 2);
-            B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
+            B2R_CUDA(gemm_launch(h->dp, L_sample, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
             kt2.stop();
             KernelTimer kt3(h, s, 3);
-            B2R_CUDA(sample_threshold_launch(gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, L, gp.gthr, gp.cnt, q0, nq_here, s));
+            B2R_CUDA(sample_threshold_launch(gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L_sample, L_sample, gp.gthr, gp.cnt, q0, nq_here, s));
             kt3.stop();
             h->n_launches += 2;
         }
@@ -478,7 +497,8 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         kt.stop();
         h->n_launches++;
         KernelTimer kt4(h, s, 4);
-        B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L, gp.gthr, gp.cnt, h->counters + 2, q0, nq_here, s));
+        B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, pool_mode ? GEMM_POOL_CAP : gp.n_slices * GEMM_HALVES * L,
+                                       gp.gthr, gp.cnt, h->counters + 2, q0, nq_here, s));
         kt4.stop();
         h->n_launches++;
     }
@@ -537,7 +557,7 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
 
     // ---- choose the scoring path ----
     //   1  warp-shuffle scan (K2): batches of <= 4 queries per corpus pass, every padded dim up to 1024, k <= 128
-    //   2  tcgen05 GEMM (K3): one corpus pass per <= 1024 queries, k <= 32, dims 128/256/384/512/768
+    //   2  tcgen05 GEMM (K3): one corpus pass per <= 1024 queries, k <= 128, dims 128/256/384/512/768
     //   3  exact fp64 scan (K5): always correct, used for shapes the fast kernels are not built for
     int path = h->path;
     const int epl_s = epl_scored(k);
@@ -590,7 +610,8 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
         if ((rc = launch_scan_batch(h, nq, epl_s, sp, s)) != B2R_OK) return rc;
         if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
     } else if (path == 2) {
-        if ((rc = launch_gemm_batch(h, nq, k, k <= 8 ? 1 : k <= 16 ? 2 : 4, fin, f, allow_dev, s)) != B2R_OK) return rc;
+        // candidates kept by the finalize: KP = 32 / 64 / 128 / 128 / 256 for k <= 8 / 16 / 32 / 64 / 128 (>= 2k beyond 8)
+        if ((rc = launch_gemm_batch(h, nq, k, k <= 8 ? 1 : k <= 16 ? 2 : k <= 64 ? 4 : 8, fin, f, allow_dev, s)) != B2R_OK) return rc;
         if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
     } else {
         if ((rc = launch_exact_batch(h, nq, k, 1, fin, f, allow_dev, s)) != B2R_OK) return rc;

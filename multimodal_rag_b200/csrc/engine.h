@@ -55,7 +55,7 @@ cudaError_t exact_launch(int epl, const ExactParams &p, int grid, cudaStream_t s
 // K3 (gemm_kernels.cu): tcgen05 batched scoring
 struct GemmParams;
 bool gemm_supported(int dp, int k);
-int gemm_list_len(int k);          // per-(query, slice) list length L for n_results = k (0 = unsupported)
+int gemm_list_len(int k);          // per-thread list length L for n_results = k; 0 = pool mode (32 < k <= 128); -1 = unsupported
 int gemm_tile_rows(int dp);        // corpus rows per MMA tile (BN)
 int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, int box_rows);
 cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
@@ -97,7 +97,7 @@ struct b2r_index {
     b2r::DevBuf o_rows, o_dist, o_dist64, o_count, need_list;
     int *need_ctl = nullptr;        // [4]: failed-certificate count, exit ticket (reset by K5 itself)
     b2r::DevBuf scan_lists, exact_lists;
-    b2r::DevBuf q_bf16, q_err, pass_bits, gthr, gemm_lists;   // K3 scratch
+    b2r::DevBuf q_bf16, q_err, pass_bits, gthr, gemm_lists, gemm_regions;   // K3 scratch
 
     // TMA tensor maps (K3), re-encoded when the buffer they describe moves or grows
     CUtensorMap tm_corpus, tm_query;

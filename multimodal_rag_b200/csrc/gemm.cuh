@@ -48,6 +48,8 @@ struct GemmParams {
     unsigned *gthr;              // [n_qblocks*128] shared per-query bound, KeyS::ord encoding, 0 = none yet
     unsigned *cnt;               // [nq] entries appended to lists[q] so far (0 between calls)
     KeyS *lists;                 // [nq][list_stride]: every thread appends its valid entries (atomic cursor cnt[q])
+    KeyS *regions;               // pool mode (L = 0): [nq][n_slices*2][region_cap] private append regions
+    int region_cap;              // entries per private region; overflow sets bit 31 of cnt[q] (-> exact fix-up)
 };
 
 __host__ __device__ constexpr int gemm_bn(int KB) { return KB <= 8 ? 256 : 128; }
@@ -289,6 +291,66 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&raw)[32], unsigned r0
     }
 }
 
+// Pool-mode step (32 < k <= 128, no per-thread list): every passing row that beats the query's bound --
+// seeded by the sampling pass at the 32nd best sampled score -- is appended to this thread's private region
+// with a plain store.  The bound does not move during the pass, so the expected pool is
+// (rows / sample rows) * 32 entries per query whatever the shard size.
+template <bool HAS_BIAS>
+__device__ __forceinline__ void epi_chunk_pool(const uint32_t (&raw)[32], unsigned r0, const GemmParams &p, float thr,
+                                               KeyS *region, int &count) {
+    const unsigned pm = __ldg(p.pass_bits + (r0 >> 5));
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+    if (HAS_BIAS) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + r0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+    }
+    float m8[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float a = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
+        const float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
+        m8[g] = fmaxf(a, b);
+    }
+    const float m32 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+    if (!__any_sync(FULL_MASK, m32 > thr)) return;
+    unsigned hm = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (m8[g] > thr) {
+            unsigned b = 0;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) b |= (v[8 * g + t] > thr ? 1u : 0u) << t;
+            hm |= b << (8 * g);
+        }
+    }
+    hm &= pm;
+    while (__any_sync(FULL_MASK, hm != 0u)) {
+        if (hm) {
+            const int j = __ffs(hm) - 1;
+            hm &= hm - 1;
+            float w16[16], w8[8], w4[4], w2[2];
+            const bool b4 = j & 16, b3 = j & 8, b2 = j & 4, b1 = j & 2, b0 = j & 1;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w16[i] = b4 ? v[16 + i] : v[i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w8[i] = b3 ? w16[8 + i] : w16[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w4[i] = b2 ? w8[4 + i] : w8[i];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) w2[i] = b1 ? w4[2 + i] : w4[i];
+            const float x = b0 ? w2[1] : w2[0];
+            if (count < p.region_cap) region[count] = KeyS::make(x, r0 + j);
+            ++count;                                       // counts past the capacity: overflow is reported at the end
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------
@@ -382,8 +444,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const int half = (warp - 2) >> 2;                            // which half of a tile's columns
         const int q = qb * GEMM_BM + quad * 32 + lane;
         const bool publish = q < p.nq;
-        RegList<L> list; list.init();
-        float thr = -INFINITY;
+        constexpr int LL = L > 0 ? L : 1;                          // pool mode (L = 0) keeps no list
+        RegList<LL> list; list.init();
+        float thr = (L == 0 && q >= p.nq) ? INFINITY : -INFINITY;    // pool mode: padding lanes admit nothing
+        KeyS *region = nullptr;
+        int rcount = 0;
+        if (L == 0)
+            region = p.regions + ((size_t)(q - p.qblock0 * GEMM_BM) * (p.n_slices * GEMM_HALVES) + (size_t)(slice * GEMM_HALVES + half)) * p.region_cap;
         unsigned g_seen = 0;
         unsigned *gq = p.gthr + q;
         unsigned g_next = *reinterpret_cast<volatile unsigned *>(gq);   // seeded by the sampling pass
@@ -402,27 +469,39 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             for (int c = 0; c < NC; c += 2) {            // two register buffers: the next load flies under this step
                 tmem_ld_wait(va);
                 tmem_ld_x32(trow + (c + 1) * 32, vb);
-                if (p.sample_mode) epi_chunk_sample<L, HAS_BIAS>(va, row0 + c * 32, p, list);
-                else epi_chunk<L, HAS_BIAS>(va, row0 + c * 32, p, list, thr, g_seen, gq, publish);
+                if (L == 0) epi_chunk_pool<HAS_BIAS>(va, row0 + c * 32, p, thr, region, rcount);
+                else if (p.sample_mode) epi_chunk_sample<LL, HAS_BIAS>(va, row0 + c * 32, p, list);
+                else epi_chunk<LL, HAS_BIAS>(va, row0 + c * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
                 tmem_ld_wait(vb);
                 if (c + 2 < NC) tmem_ld_x32(trow + (c + 2) * 32, va);
-                if (p.sample_mode) epi_chunk_sample<L, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list);
-                else epi_chunk<L, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list, thr, g_seen, gq, publish);
+                if (L == 0) epi_chunk_pool<HAS_BIAS>(vb, row0 + (c + 1) * 32, p, thr, region, rcount);
+                else if (p.sample_mode) epi_chunk_sample<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list);
+                else epi_chunk<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[buf]);
         }
-        if (q < p.nq) {           // append this thread's entries to the query's candidate pool (compact: most lists are short)
+        if (L == 0) {
+            if (q < p.nq && rcount > 0) {     // compact the private region into the query's pool
+                const int nv = min(rcount, p.region_cap);
+                const unsigned base = atomicAdd(&p.cnt[q], (unsigned)nv) & 0x7fffffffu;
+                const bool fits = base + (unsigned)nv <= (unsigned)p.list_stride;
+                KeyS *dst = p.lists + (size_t)q * p.list_stride + base;
+                if (fits)
+                    for (int i = 0; i < nv; ++i) dst[i] = region[i];
+                if (!fits || rcount > p.region_cap) atomicOr(&p.cnt[q], 0x80000000u);   // rows were dropped: not certifiable
+            }
+        } else if (q < p.nq) {    // append this thread's entries to the query's candidate pool (compact: most lists are short)
             int nv = 0;
 #pragma unroll
-            for (int i = 0; i < L; ++i) nv += list.r[i] != 0xffffffffu ? 1 : 0;
+            for (int i = 0; i < LL; ++i) nv += list.r[i] != 0xffffffffu ? 1 : 0;
             if (nv) {
                 KeyS *dst = p.lists + (size_t)q * p.list_stride + atomicAdd(&p.cnt[q], (unsigned)nv);
 #pragma unroll
-                for (int i = 0; i < L; ++i)              // the list is sorted: valid entries are the first nv
+                for (int i = 0; i < LL; ++i)             // the list is sorted: valid entries are the first nv
                     if (i < nv) dst[i] = KeyS::make(list.s[i], list.r[i]);
             }
         }
@@ -493,7 +572,9 @@ finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_wait();
     pdl_trigger();
-    const int entries = min((int)cnt[qi], max_entries);
+    const unsigned cnt_raw = cnt[qi];
+    const bool overflow = (cnt_raw >> 31) != 0u;          // pool mode: a private region filled up, rows were dropped
+    const int entries = overflow ? 0 : min((int)(cnt_raw & 0x7fffffffu), max_entries);   // an overflowed pool has holes
     const unsigned g = gthr[qi];
     const KeyS *src = lists + (size_t)qi * list_stride;
 
@@ -585,6 +666,7 @@ finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, 
     float T = -INFINITY;
     if (nvalid == KP) T = stage[KP - 1].score();
     if (g != 0u) T = fmaxf(T, KeyS::unord(g));
+    if (overflow) T = INFINITY;                             // nothing bounds the dropped rows: force the exact fix-up
     finalize_candidates(fin, qi, stage, nvalid, T, sm_ex, sm_q, sm_misc);
 }
 

@@ -17,6 +17,7 @@ gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias) {
     if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true> : gemm_topk_kernel<B2R_KB, 8, false>;
     if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true> : gemm_topk_kernel<B2R_KB, 16, false>;
     if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true> : gemm_topk_kernel<B2R_KB, 32, false>;
+    if (L == 0) return bias ? gemm_topk_kernel<B2R_KB, 0, true> : gemm_topk_kernel<B2R_KB, 0, false>;   // pool mode
     return nullptr;
 }
 }  // namespace b2r
@@ -86,9 +87,10 @@ encode_fn get_encode() {
 }
 }  // namespace
 
-int gemm_list_len(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 0; }
+// per-thread list length for n_results = k; 0 = pool mode (no lists, 32 < k <= 128); -1 = unsupported
+int gemm_list_len(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : k <= 128 ? 0 : -1; }
 int gemm_tile_rows(int dp) { return gemm_bn(dp / 64); }
-bool gemm_supported(int dp, int k) { return dp % 64 == 0 && lookup(dp / 64, 8, false) != nullptr && gemm_list_len(k) != 0; }
+bool gemm_supported(int dp, int k) { return dp % 64 == 0 && lookup(dp / 64, 8, false) != nullptr && gemm_list_len(k) >= 0; }
 
 // [rows, dp] bf16 row-major -> 2-D tensor map, box = 64 elements (128 B, one swizzle row) x box_rows
 int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, int box_rows) {
@@ -152,12 +154,14 @@ cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS
         if (epl == 1) e = cudaFuncSetAttribute(finalize_union_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (epl == 2) e = cudaFuncSetAttribute(finalize_union_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (epl == 4) e = cudaFuncSetAttribute(finalize_union_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (epl == 8) e = cudaFuncSetAttribute(finalize_union_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     switch (epl) {
         case 1: return launch_pdl(finalize_union_kernel<1>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
         case 2: return launch_pdl(finalize_union_kernel<2>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
         case 4: return launch_pdl(finalize_union_kernel<4>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
+        case 8: return launch_pdl(finalize_union_kernel<8>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -53,6 +53,10 @@ elif __name__ == "__main__":
     run(1_000_000, 384, 1024, 5)
     run(1_000_000, 512, 256, 10)
     run(1_000_000, 768, 64, 20)
+    run(1_000_000, 384, 1024, 100)
+    run(1_000_000, 384, 256, 100)
+    run(1_000_000, 384, 1, 100)
+    run(4_000_000, 384, 1024, 100, iters=5)
     run(1_000_000, 384, 1, 5)
     run(10_000, 384, 1, 5)
     for nq in (1, 2, 4, 8, 16):

@@ -67,6 +67,50 @@ def test_gemm_k_up_to_32_and_tiny_corpus():
     _check(c2, X2, Q, 16, "cosine", path=2)
 
 
+@pytest.mark.parametrize("k", [33, 50, 100, 128])
+def test_gemm_pool_mode_large_k(k):
+    """32 < k <= 128: no per-thread lists; sampling seeds a bound, rows above it are pooled (config 4's k=100)."""
+    c, X, _ = _mk("cosine", 384, 40000, seed=31)
+    Q = make_unit(40, 384, 32)
+    _check(c, X, Q, k, "cosine", path=2)
+    _check(c, X, Q[:3], k, "cosine", path=2)              # small batch still samples in pool mode
+    assert c.stats()["n_exact_fallbacks"] == 0
+
+
+def test_gemm_pool_mode_spaces_filters_and_small_shards():
+    c, X, _ = _mk("l2", 512, 9000, seed=33, unit=False)
+    Q = make_unit(20, 512, 34)
+    _check(c, X, Q, 64, "l2", path=2)
+    c2, X2, _ = _mk("ip", 256, 1500, seed=35, unit=False)  # < 8 tiles: no sampling, every row is pooled
+    Q2 = make_unit(10, 256, 36)
+    _check(c2, X2, Q2, 100, "ip", path=2)
+    c3, X3, _ = _mk("cosine", 384, 300, seed=37)           # fewer rows than k in the filtered set
+    mask = np.arange(300) % 4 == 0
+    c3.delete(ids=[f"doc_{i // 7:012x}_text_{i}" for i in range(300) if not mask[i]])
+    _check(c3, X3, make_unit(6, 384, 38), 100, "cosine", where_mask=mask, path=2)
+
+
+def test_gemm_pool_mode_1m_batch1024_k100():
+    """BASELINE config 4's per-GPU shape (batch 1024, top_k 100) on 1M rows: properties + torch fp32 reference."""
+    import torch
+    from multimodal_rag_b200 import B200Collection
+    n, d, k, nq = 1_000_000, 384, 100, 1024
+    g = torch.Generator(device="cuda").manual_seed(0xC0FFEE)
+    X = torch.nn.functional.normalize(torch.randn(n, d, generator=g, device="cuda"), dim=1)
+    c = B200Collection("big", {"hnsw:space": "cosine"}, capacity=n, dimension=d)
+    c.add(ids=[str(i) for i in range(n)], embeddings=X)
+    Q = torch.nn.functional.normalize(torch.randn(nq, d, generator=g, device="cuda"), dim=1)
+    rows, dist, cnt = c.query_rows(Q, k)
+    assert (cnt == k).all() and (np.diff(dist, axis=1) >= 0).all()
+    ref = torch.topk(Q[:256] @ X.T, k, dim=1).indices.cpu().numpy()
+    same = np.mean([len(set(rows[i]) & set(ref[i])) / k for i in range(256)])
+    assert same > 0.9995, same                         # fp32 matmul noise may swap the boundary candidate
+    assert (rows[:256, :50] == ref[:, :50]).mean() > 0.995
+    st = c.stats()
+    assert st["n_exact_fallbacks"] == 0
+    assert 300 < st["n_pool_entries"] / st["n_pool_queries"] < 4000
+
+
 def test_gemm_filters_and_tombstones():
     from multimodal_rag_b200 import B200Collection
     d, n = 512, 20000
