@@ -356,6 +356,48 @@ def run_gpu(args):
                    "bytes_gathered_per_step": world * nq * (k * 16 + 4)}
         sh2.close()
 
+    # ---- BASELINE config 4 (N > 1): 100M x 384 row-sharded over the N GPUs, batch 1024, top_k 100 ----
+    sharded_c4 = None
+    if world > 1 and not args.no_c4:
+        rows_total = args.c4_rows
+        per = rows_total // world
+        free_b, _ = torch.cuda.mem_get_info()
+        bytes_per_row = DIM * 2 + DIM * 4 + 8
+        scaled = False
+        if per * bytes_per_row > 0.8 * free_b:                 # does not fit beside the fp32 master: say so
+            per = int(0.8 * free_b / bytes_per_row) // 4096 * 4096
+            scaled = True
+        t = torch.tensor([per], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        per = int(t.item())
+        sh3 = DeviceShard(DIM, "cosine", capacity=per, row_base=rank * per, device=local_rank)
+        g = torch.Generator(device=dev).manual_seed(0xC4 + rank)
+        for s0 in range(0, per, 1 << 18):
+            m = min(1 << 18, per - s0)
+            sh3.ingest(torch.nn.functional.normalize(torch.randn(m, DIM, generator=g, device=dev), dim=1))
+        torch.cuda.synchronize()
+        nq4, k4 = 1024, 100
+        gq4 = torch.Generator(device=dev).manual_seed(0xBEEF4)     # replicated queries
+        Q4 = [torch.nn.functional.normalize(torch.randn(nq4, DIM, generator=gq4, device=dev), dim=1) for _ in range(2)]
+        o4 = sh3.alloc_out(nq4, k4)
+
+        def step_c4(i):
+            sh3.query_device(Q4[i % 2], k4, o4)
+
+        for i in range(2):
+            step_c4(i)
+        K4 = max(3, min(K, 5))
+        ms_c4 = timed(step_c4, K4)
+        flops4 = 2.0 * nq4 * per * DIM
+        sharded_c4 = {"workload": f"configs[3]: {per * world} x {DIM} bf16 rows row-sharded over {world} GPUs, batch {nq4}, top_k {k4}",
+                      "rows_total": per * world, "rows_per_gpu": per, "scaled_down_to_fit": scaled,
+                      "qps": nq4 * K4 / (ms_c4 * 1e-3), "ms_per_step": ms_c4 / K4,
+                      "tflops_per_gpu": flops4 / (ms_c4 / K4 * 1e-3) / 1e12,
+                      "collective": "ONE nccl all_gather of the packed per-rank top-k block",
+                      "bytes_gathered_per_step": world * nq4 * (k4 * 16 + 4),
+                      "exact_fallbacks": sh3.fallbacks()}
+        sh3.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -414,6 +456,8 @@ def run_gpu(args):
         line["cpu_baseline"] = cpu
     if sharded is not None:
         line["sharded"] = sharded
+    if sharded_c4 is not None:
+        line["sharded_c4"] = sharded_c4
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -428,6 +472,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hnsw", action="store_true", help="skip the HNSW restatement inside the CPU legs")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the 100M-row config-4 leg")
+    ap.add_argument("--c4-rows", type=int, default=100_000_000, help="total rows of the config-4 leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

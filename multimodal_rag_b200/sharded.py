@@ -201,6 +201,11 @@ class DeviceShard:
             self.lib.b2r_destroy(self.h)
             self.h = None
 
+    def fallbacks(self) -> int:
+        st = _lib.B2RStats()
+        _lib.check(self.lib.b2r_get_stats(self.h, ctypes.byref(st)))
+        return int(st.n_exact_fallbacks)
+
     def ingest(self, x: torch.Tensor):
         first = ctypes.c_int64()
         x = x.contiguous()

@@ -40,6 +40,8 @@ def lib():
         _lib.b2r_hnsw_search.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p]
         _lib.b2r_hnsw_search.restype = None
+        _lib.b2r_hnsw_set_threads.argtypes = [ctypes.c_int]
+        _lib.b2r_hnsw_set_threads.restype = None
         _lib.b2r_hnsw_free.argtypes = [ctypes.c_void_p]
         _lib.b2r_hnsw_free.restype = None
     return _lib
@@ -81,11 +83,19 @@ class Hnsw:
     M=16, ef_construction=100, search ef = max(10, k)).  X must be stored rows (normalised for cosine)
     and stay alive while the index is used."""
 
-    def __init__(self, X: np.ndarray, space: str = "cosine", M: int = 16, ef_construction: int = 100, seed: int = 100):
+    def __init__(self, X: np.ndarray, space: str = "cosine", M: int = 16, ef_construction: int = 100, seed: int = 100,
+                 build_threads: int = 0):
         self.X = np.ascontiguousarray(X, dtype=np.float32)
         self.space = space
-        self._h = lib().b2r_hnsw_build(self.X.ctypes.data, self.X.shape[0], self.X.shape[1],
-                                       0 if space == "l2" else 1, M, ef_construction, seed)
+        self._h = None
+        if build_threads > 0:                      # 1 = deterministic insertion order
+            lib().b2r_hnsw_set_threads(build_threads)
+        try:
+            self._h = lib().b2r_hnsw_build(self.X.ctypes.data, self.X.shape[0], self.X.shape[1],
+                                           0 if space == "l2" else 1, M, ef_construction, seed)
+        finally:
+            if build_threads > 0:
+                lib().b2r_hnsw_set_threads(0)
         if not self._h:
             raise ValueError("b2r_hnsw_build failed")
 

@@ -237,6 +237,15 @@ int b2r_hnsw_threads(void) {
 #endif
 }
 
+/* n <= 0 restores the default; a single-threaded build is deterministic (tests) */
+void b2r_hnsw_set_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+#else
+    (void)n;
+#endif
+}
+
 void *b2r_hnsw_build(const float *X, int n, int d, int space, int M, int ef_construction, unsigned seed) {
     if (M > 32) return NULL;
     hnsw_t *h = (hnsw_t *)calloc(1, sizeof(hnsw_t));
