@@ -189,6 +189,8 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------
 def run_gpu(args):
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     import numpy as np
     import torch
     import torch.distributed as dist

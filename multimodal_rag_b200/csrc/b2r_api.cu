@@ -463,13 +463,14 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         h->tm_query_base = h->q_bf16.p; h->tm_query_rows = nq;
     }
     // Sampling pass: tiles strided across the shard seed gthr[q].
-    //   list mode: 128 tiles, skipped for small shards and for small batches (with a handful of live lanes per
+    //   list mode: max(128 tiles, 1/32 of the shard), skipped for small shards and for small batches (with a handful of live lanes per
     //              warp the list warm-up costs a few microseconds);
     //   pool mode: 1/32 of the shard (>= 4 tiles) whenever a slice could overflow a private region without a
     //              bound -- the expected pool is then 32 * 32 = 1024 entries per query whatever the shard size.
     int sample_tiles;
     if (pool_mode) sample_tiles = tiles_total >= 8 ? std::max(4, tiles_total / 32) : 0;
-    else sample_tiles = (tiles_total >= 2 * GEMM_SAMPLE_TILES && nq >= GEMM_SAMPLE_MIN_BATCH) ? GEMM_SAMPLE_TILES : 0;
+    else sample_tiles = (tiles_total >= 2 * GEMM_SAMPLE_TILES && nq >= GEMM_SAMPLE_MIN_BATCH)
+                            ? std::max(GEMM_SAMPLE_TILES, tiles_total / 32) : 0;   // >= 1/32 of the shard: pools stay ~32 L entries
     for (int qb0 = 0; qb0 < qblocks_total; qb0 += GEMM_MAX_QBLOCKS) {
         GemmParams gp;
         gp.n = (unsigned)h->rows; gp.nq = nq; gp.qblock0 = qb0;

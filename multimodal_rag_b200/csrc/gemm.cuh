@@ -52,14 +52,19 @@ struct GemmParams {
     int region_cap;              // entries per private region; overflow sets bit 31 of cnt[q] (-> exact fix-up)
 };
 
-__host__ __device__ constexpr int gemm_bn(int KB) { return KB <= 8 ? 256 : 128; }
+// Up to 512 dims (KB <= 8) the query block stays resident in shared memory (KB * 16 KB) and a pipeline stage
+// is one corpus K-block.  Beyond that it would crowd out the ring (768 dims: 192 KB), so the query K-block is
+// streamed too: a stage = query K-block (16 KB, an L2 hit every time) + corpus K-block (32 KB).
+__host__ __device__ constexpr bool gemm_a_resident(int KB) { return KB <= 8; }
+__host__ __device__ constexpr int gemm_bn(int KB) { return 256; }
+__host__ __device__ constexpr int gemm_stage_bytes(int KB) { return gemm_bn(KB) * 128 + (gemm_a_resident(KB) ? 0 : GEMM_BM * 128); }
 __host__ __device__ constexpr int gemm_stages(int KB) {
-    int a = KB * GEMM_BM * 128, st = gemm_bn(KB) * 128;
-    int s = (GEMM_SMEM_LIMIT - GEMM_SMEM_SLACK - a) / st;
+    int a = gemm_a_resident(KB) ? KB * GEMM_BM * 128 : 0;
+    int s = (GEMM_SMEM_LIMIT - GEMM_SMEM_SLACK - a) / gemm_stage_bytes(KB);
     return s > 8 ? 8 : s;
 }
 __host__ __device__ constexpr size_t gemm_smem_bytes(int KB) {
-    return (size_t)KB * GEMM_BM * 128 + (size_t)gemm_stages(KB) * gemm_bn(KB) * 128 + 1024;
+    return (size_t)(gemm_a_resident(KB) ? KB * GEMM_BM * 128 : 0) + (size_t)gemm_stages(KB) * gemm_stage_bytes(KB) + 1024;
 }
 
 // ---------------------------------------------------------------------------------
@@ -359,8 +364,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
     constexpr int BN = gemm_bn(KB);
     constexpr int STAGES = gemm_stages(KB);
+    constexpr bool A_RES = gemm_a_resident(KB);
     constexpr uint32_t A_KB_BYTES = GEMM_BM * 128;          // one K-block of the query block
     constexpr uint32_t B_STAGE_BYTES = BN * 128;            // one K-block of a corpus tile
+    constexpr uint32_t STAGE_BYTES = gemm_stage_bytes(KB);  // ring slot: corpus K-block (+ query K-block when streamed)
     constexpr uint32_t TMEM_COLS = 2 * BN;
     constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM, BN);
     static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
@@ -372,8 +379,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
-    unsigned char *smA = sm;                                  // [KB][128 rows][128 B]
-    unsigned char *smB = sm + (size_t)KB * A_KB_BYTES;       // [STAGES][BN rows][128 B]
+    unsigned char *smA = sm;                                  // resident: [KB][128 rows][128 B]
+    unsigned char *smB = sm + (A_RES ? (size_t)KB * A_KB_BYTES : 0);   // [STAGES][BN rows][128 B] (+ [128 rows][128 B] streamed A)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = p.qblock0 + blockIdx.x % p.n_qblocks, slice = blockIdx.x / p.n_qblocks;
@@ -399,14 +406,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(&bar_a, KB * A_KB_BYTES);
-            for (int kb = 0; kb < KB; ++kb) tma_load_2d(smA + (size_t)kb * A_KB_BYTES, &tm_q, &bar_a, kb * 64, qb * GEMM_BM);
+            if (A_RES) {
+                mbar_expect_tx(&bar_a, KB * A_KB_BYTES);
+                for (int kb = 0; kb < KB; ++kb) tma_load_2d(smA + (size_t)kb * A_KB_BYTES, &tm_q, &bar_a, kb * 64, qb * GEMM_BM);
+            }
             int stage = 0; uint32_t phase = 0;
             for (int t = t0; t < t1; ++t) {
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
-                    mbar_expect_tx(&bar_full[stage], B_STAGE_BYTES);
-                    tma_load_2d(smB + (size_t)stage * B_STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * p.tile_mul * BN);
+                    mbar_expect_tx(&bar_full[stage], STAGE_BYTES);
+                    if (!A_RES) tma_load_2d(smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES, &tm_q, &bar_full[stage], kb * 64, qb * GEMM_BM);
+                    tma_load_2d(smB + (size_t)stage * STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * p.tile_mul * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -414,8 +424,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            mbar_wait(&bar_a, 0);
-            tc_fence_after();
+            if (A_RES) { mbar_wait(&bar_a, 0); tc_fence_after(); }
             int stage = 0; uint32_t phase = 0;
             for (int t = t0, it = 0; t < t1; ++t, ++it) {
                 const int buf = it & 1;
@@ -425,8 +434,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_full[stage], phase);
                     tc_fence_after();
-                    const uint64_t ad = umma_smem_desc(smem_u32(smA + (size_t)kb * A_KB_BYTES));
-                    const uint64_t bd = umma_smem_desc(smem_u32(smB + (size_t)stage * B_STAGE_BYTES));
+                    const uint64_t ad = umma_smem_desc(smem_u32(A_RES ? smA + (size_t)kb * A_KB_BYTES
+                                                                          : smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES));
+                    const uint64_t bd = umma_smem_desc(smem_u32(smB + (size_t)stage * STAGE_BYTES));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // UMMA_K = 16 bf16 = 32 B: +2 in the (>>4) address field
                         umma_bf16_ss(d, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
