@@ -23,7 +23,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O2,-Wall", "-ccbin", "/usr/bin/g++"]
 SCAN_DPS = [64, 128, 256, 384, 512, 768, 1024]
-GEMM_KBS = [2, 4, 6, 8, 12]          # padded dim / 64: 128, 256, 384, 512, 768
+GEMM_KBS = [2, 4, 6, 8, 12, 16, 24]  # padded dim / 64: 128, 256, 384, 512, 768, 1024, 1536
 
 
 def _units():

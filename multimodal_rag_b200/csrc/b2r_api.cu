@@ -558,7 +558,7 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
 
     // ---- choose the scoring path ----
     //   1  warp-shuffle scan (K2): batches of <= 4 queries per corpus pass, every padded dim up to 1024, k <= 128
-    //   2  tcgen05 GEMM (K3): one corpus pass per <= 1024 queries, k <= 128, dims 128/256/384/512/768
+    //   2  tcgen05 GEMM (K3): one corpus pass per <= 1024 queries, k <= 128, dims 128/256/384/512/768/1024/1536
     //   3  exact fp64 scan (K5): always correct, used for shapes the fast kernels are not built for
     int path = h->path;
     const int epl_s = epl_scored(k);

@@ -27,6 +27,8 @@ gemm_fn gemm_lookup_4(int, bool);
 gemm_fn gemm_lookup_6(int, bool);
 gemm_fn gemm_lookup_8(int, bool);
 gemm_fn gemm_lookup_12(int, bool);
+gemm_fn gemm_lookup_16(int, bool);
+gemm_fn gemm_lookup_24(int, bool);
 
 // ---------------------------------------------------------------------------------
 // pass bitmap: bit r of word r>>5 = row r is live, passes the type mask and the allow bitmap.
@@ -53,6 +55,8 @@ gemm_fn lookup(int kb, int L, bool bias) {
         case 6:  return gemm_lookup_6(L, bias);     // all-MiniLM-L6-v2 (384)
         case 8:  return gemm_lookup_8(L, bias);     // CLIP ViT-B/32 shape (512)
         case 12: return gemm_lookup_12(L, bias);    // 768
+        case 16: return gemm_lookup_16(L, bias);    // 1024
+        case 24: return gemm_lookup_24(L, bias);    // 1536
         default: return nullptr;
     }
 }
@@ -63,6 +67,8 @@ size_t smem_of(int kb) {
         case 6:  return gemm_smem_bytes(6);
         case 8:  return gemm_smem_bytes(8);
         case 12: return gemm_smem_bytes(12);
+        case 16: return gemm_smem_bytes(16);
+        case 24: return gemm_smem_bytes(24);
         default: return 0;
     }
 }

@@ -20,8 +20,9 @@ def test_gemm_matches_oracle(space, d):
     _check(c, X, Q[:17], 16, space, path=2)   # 16th vs 32nd best of 20k rows: fall-backs are legitimate here
 
 
-@pytest.mark.parametrize("d", [128, 256])
-def test_gemm_small_dims(d):
+@pytest.mark.parametrize("d", [128, 256, 1000, 1536])
+def test_gemm_other_dims(d):
+    """padded dims 128 / 256 (resident queries) and 1024 / 1536 (streamed query K-blocks; 1000 pads to 1024)"""
     c, X, _ = _mk("cosine", d, 6000, seed=d, unit=True)
     Q = make_unit(33, d, 5)
     _check(c, X, Q, 5, "cosine", path=2)
