@@ -359,7 +359,8 @@ __device__ __forceinline__ void epi_chunk_pool(const uint32_t (&raw)[32], unsign
 // ---------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------
-template <int KB, int L, bool HAS_BIAS>
+// SAMPLE = the sampling-pass build of the kernel (separate instantiation: the main build's hot loop stays small)
+template <int KB, int L, bool HAS_BIAS, bool SAMPLE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
     constexpr int BN = gemm_bn(KB);
@@ -480,13 +481,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 tmem_ld_wait(va);
                 tmem_ld_x32(trow + (c + 1) * 32, vb);
                 if (L == 0) epi_chunk_pool<HAS_BIAS>(va, row0 + c * 32, p, thr, region, rcount);
-                else if (p.sample_mode) epi_chunk_sample<LL, HAS_BIAS>(va, row0 + c * 32, p, list);
+                else if (SAMPLE) epi_chunk_sample<LL, HAS_BIAS>(va, row0 + c * 32, p, list);
                 else epi_chunk<LL, HAS_BIAS>(va, row0 + c * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
                 tmem_ld_wait(vb);
                 if (c + 2 < NC) tmem_ld_x32(trow + (c + 2) * 32, va);
                 if (L == 0) epi_chunk_pool<HAS_BIAS>(vb, row0 + (c + 1) * 32, p, thr, region, rcount);
-                else if (p.sample_mode) epi_chunk_sample<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list);
+                else if (SAMPLE) epi_chunk_sample<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list);
                 else epi_chunk<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
             }

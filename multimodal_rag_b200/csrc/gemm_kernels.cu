@@ -13,22 +13,28 @@ typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmParams);
 #ifdef B2R_KB
 #define B2R_CAT2(a, b) a##b
 #define B2R_CAT(a, b) B2R_CAT2(a, b)
-gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias) {
-    if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true> : gemm_topk_kernel<B2R_KB, 8, false>;
-    if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true> : gemm_topk_kernel<B2R_KB, 16, false>;
-    if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true> : gemm_topk_kernel<B2R_KB, 32, false>;
-    if (L == 0) return bias ? gemm_topk_kernel<B2R_KB, 0, true> : gemm_topk_kernel<B2R_KB, 0, false>;   // pool mode
+gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias, bool sample) {
+    if (sample) {        // sampling-pass build (lists of step maxima); pool mode samples with L = 32
+        if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true, true> : gemm_topk_kernel<B2R_KB, 8, false, true>;
+        if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true, true> : gemm_topk_kernel<B2R_KB, 16, false, true>;
+        if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true, true> : gemm_topk_kernel<B2R_KB, 32, false, true>;
+        return nullptr;
+    }
+    if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true, false> : gemm_topk_kernel<B2R_KB, 8, false, false>;
+    if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true, false> : gemm_topk_kernel<B2R_KB, 16, false, false>;
+    if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true, false> : gemm_topk_kernel<B2R_KB, 32, false, false>;
+    if (L == 0) return bias ? gemm_topk_kernel<B2R_KB, 0, true, false> : gemm_topk_kernel<B2R_KB, 0, false, false>;   // pool mode
     return nullptr;
 }
 }  // namespace b2r
 #else
-gemm_fn gemm_lookup_2(int, bool);
-gemm_fn gemm_lookup_4(int, bool);
-gemm_fn gemm_lookup_6(int, bool);
-gemm_fn gemm_lookup_8(int, bool);
-gemm_fn gemm_lookup_12(int, bool);
-gemm_fn gemm_lookup_16(int, bool);
-gemm_fn gemm_lookup_24(int, bool);
+gemm_fn gemm_lookup_2(int, bool, bool);
+gemm_fn gemm_lookup_4(int, bool, bool);
+gemm_fn gemm_lookup_6(int, bool, bool);
+gemm_fn gemm_lookup_8(int, bool, bool);
+gemm_fn gemm_lookup_12(int, bool, bool);
+gemm_fn gemm_lookup_16(int, bool, bool);
+gemm_fn gemm_lookup_24(int, bool, bool);
 
 // ---------------------------------------------------------------------------------
 // pass bitmap: bit r of word r>>5 = row r is live, passes the type mask and the allow bitmap.
@@ -48,15 +54,15 @@ static __global__ void pass_bits_kernel(const uint8_t *__restrict__ type_code, u
 
 
 namespace {
-gemm_fn lookup(int kb, int L, bool bias) {
+gemm_fn lookup(int kb, int L, bool bias, bool sample) {
     switch (kb) {
-        case 2:  return gemm_lookup_2(L, bias);
-        case 4:  return gemm_lookup_4(L, bias);
-        case 6:  return gemm_lookup_6(L, bias);     // all-MiniLM-L6-v2 (384)
-        case 8:  return gemm_lookup_8(L, bias);     // CLIP ViT-B/32 shape (512)
-        case 12: return gemm_lookup_12(L, bias);    // 768
-        case 16: return gemm_lookup_16(L, bias);    // 1024
-        case 24: return gemm_lookup_24(L, bias);    // 1536
+        case 2:  return gemm_lookup_2(L, bias, sample);
+        case 4:  return gemm_lookup_4(L, bias, sample);
+        case 6:  return gemm_lookup_6(L, bias, sample);     // all-MiniLM-L6-v2 (384)
+        case 8:  return gemm_lookup_8(L, bias, sample);     // CLIP ViT-B/32 shape (512)
+        case 12: return gemm_lookup_12(L, bias, sample);    // 768
+        case 16: return gemm_lookup_16(L, bias, sample);    // 1024
+        case 24: return gemm_lookup_24(L, bias, sample);    // 1536
         default: return nullptr;
     }
 }
@@ -96,7 +102,7 @@ encode_fn get_encode() {
 // per-thread list length for n_results = k; 0 = pool mode (no lists, 32 < k <= 128); -1 = unsupported
 int gemm_list_len(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : k <= 128 ? 0 : -1; }
 int gemm_tile_rows(int dp) { return gemm_bn(dp / 64); }
-bool gemm_supported(int dp, int k) { return dp % 64 == 0 && lookup(dp / 64, 8, false) != nullptr && gemm_list_len(k) >= 0; }
+bool gemm_supported(int dp, int k) { return dp % 64 == 0 && lookup(dp / 64, 8, false, false) != nullptr && gemm_list_len(k) >= 0; }
 
 // [rows, dp] bf16 row-major -> 2-D tensor map, box = 64 elements (128 B, one swizzle row) x box_rows
 int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, int box_rows) {
@@ -116,7 +122,7 @@ int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, i
 cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
                         const GemmParams &p, cudaStream_t s) {
     const int kb = dp / 64;
-    gemm_fn f = lookup(kb, L, bias);
+    gemm_fn f = lookup(kb, L, bias, p.sample_mode != 0);
     if (!f) return cudaErrorInvalidValue;
     const size_t smem = smem_of(kb);
     static std::mutex mu;
