@@ -12,6 +12,8 @@
 
 using namespace b2r;
 
+constexpr int GEMM_SEED_MIN_BATCH = 1;    // K3 in-kernel seeding pays from batch 1 on (smaller pools, no unseeded slow path)
+
 // ---------------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------------
@@ -127,6 +129,9 @@ extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device,
     h->dim = dim; h->dp = round_up(dim, 64); h->space = space; h->device = device; h->flags = flags;
     h->sm_count = prop.multiProcessorCount;
     if (const char *e = getenv("B2R_TIME_STAGE")) h->timing_stage = atoi(e);
+    if (const char *e = getenv("B2R_NO_SEED")) h->no_seed = atoi(e) != 0;      // development: K3 without in-kernel seeding
+    h->seed_min_batch = GEMM_SEED_MIN_BATCH;
+    if (const char *e = getenv("B2R_SEED_MIN_BATCH")) h->seed_min_batch = atoi(e);
     int rc = B2R_OK;
     do {
         if (cudaMalloc(&h->max_norm2, 256) != cudaSuccess || cudaMalloc(&h->counters, 256) != cudaSuccess ||
@@ -153,7 +158,8 @@ extern "C" int b2r_destroy(b2r_handle h) {
     cudaFree(h->max_norm2); cudaFree(h->counters); cudaFree(h->tickets); cudaFree(h->need_ctl);
     DevBuf *bufs[] = {&h->x_stage, &h->t_stage, &h->q_raw, &h->q_prep, &h->allow, &h->rows_stage, &h->gather_out,
                       &h->o_rows, &h->o_dist, &h->o_dist64, &h->o_count, &h->need_list, &h->scan_lists,
-                      &h->exact_lists, &h->q_bf16, &h->q_err, &h->pass_bits, &h->gthr, &h->gemm_lists, &h->gemm_regions};
+                      &h->exact_lists, &h->q_bf16, &h->q_err, &h->pass_bits, &h->gthr, &h->gemm_lists, &h->gemm_regions,
+                      &h->gemm_samples};
     for (DevBuf *b : bufs) release(*b);
     for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -413,8 +419,6 @@ int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const Finaliz
 // K3: pass bitmap -> tcgen05 scoring + per-(query, slice) lists -> per-query finalize
 constexpr int GEMM_MIN_BATCH = 5;        // below this the scan reads the corpus at most twice anyway
 constexpr int GEMM_MAX_QBLOCKS = 8;      // 128-query blocks per launch (1024 queries per corpus pass)
-constexpr int GEMM_SAMPLE_TILES = 128;   // tiles of the threshold-seeding sample (32k rows at BN = 256)
-constexpr int GEMM_SAMPLE_MIN_BATCH = 24;
 constexpr int GEMM_REGION_CAP = 256;       // pool mode: entries per private (query, slice, half) region
 constexpr int GEMM_POOL_CAP = 16384;        // pool mode: compact pool entries per query (>= SMs*2*32 for the sampling pass)
 constexpr int GEMM_POOL_SAMPLE_RANK = 32;  // pool mode: the bound is the 32nd best sampled score
@@ -435,7 +439,7 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
     if ((rc = ensure(h->pass_bits, (size_t)n_words * 4 + 16)) != B2R_OK) return rc;
     {   // gthr is all-zero between calls: zeroed when (re)allocated, and finalize_union_kernel clears what it read
         const void *before = h->gthr.p;
-        if ((rc = ensure(h->gthr, (size_t)qblocks_total * GEMM_BM * 4 * 2)) != B2R_OK) return rc;   // bounds, then cursors
+        if ((rc = ensure(h->gthr, (size_t)qblocks_total * (GEMM_BM * 3 + 1) * 4)) != B2R_OK) return rc;   // bounds, cursors, seed flags, arrivals
         if (h->gthr.p != before) B2R_CUDA(cudaMemsetAsync(h->gthr.p, 0, h->gthr.bytes, s));
     }
     // list mode pools: [nq][SMs*2*L].  Pool mode: the sampling pass needs [nq][SMs*2*32] and the main pass
@@ -462,15 +466,15 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         if ((rc = gemm_encode_map(&h->tm_query, h->q_bf16.p, h->dp, (uint64_t)nq, GEMM_BM)) != B2R_OK) return rc;
         h->tm_query_base = h->q_bf16.p; h->tm_query_rows = nq;
     }
-    // Sampling pass: tiles strided across the shard seed gthr[q].
-    //   list mode: max(128 tiles, 1/32 of the shard), skipped for small shards and for small batches (with a handful of live lanes per
-    //              warp the list warm-up costs a few microseconds);
-    //   pool mode: 1/32 of the shard (>= 4 tiles) whenever a slice could overflow a private region without a
-    //              bound -- the expected pool is then 32 * 32 = 1024 entries per query whatever the shard size.
-    int sample_tiles;
-    if (pool_mode) sample_tiles = tiles_total >= 8 ? std::max(4, tiles_total / 32) : 0;
-    else sample_tiles = (tiles_total >= 2 * GEMM_SAMPLE_TILES && nq >= GEMM_SAMPLE_MIN_BATCH)
-                            ? std::max(GEMM_SAMPLE_TILES, tiles_total / 32) : 0;   // >= 1/32 of the shard: pools stay ~32 L entries
+    // Threshold seeding.
+    //   list mode: in-kernel -- every CTA first scans a few tiles of its slice in sampling mode and posts the step
+    //              maxima, the epilogue warps turn the posts into gthr[q] (GemmParams::seed_tiles; no extra launch);
+    //   pool mode: a sampling PASS over 1/32 of the shard (>= 4 tiles) whenever a slice could overflow a private
+    //              region without a bound -- the expected pool is then 32 * 32 = 1024 entries per query whatever
+    //              the shard size.
+    const int sample_tiles = (pool_mode && tiles_total >= 8) ? std::max(4, tiles_total / 32) : 0;
+    if (!pool_mode && (rc = ensure(h->gemm_samples, sizeof(unsigned) * (size_t)GEMM_BM * h->sm_count * GEMM_HALVES * L)) != B2R_OK)
+        return rc;
     for (int qb0 = 0; qb0 < qblocks_total; qb0 += GEMM_MAX_QBLOCKS) {
         GemmParams gp;
         gp.n = (unsigned)h->rows; gp.nq = nq; gp.qblock0 = qb0;
@@ -479,6 +483,8 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         gp.pass_bits = (const uint32_t *)h->pass_bits.p; gp.bias = h->bias;
         gp.gthr = (unsigned *)h->gthr.p; gp.cnt = gp.gthr + (size_t)qblocks_total * GEMM_BM; gp.lists = (KeyS *)h->gemm_lists.p;
         gp.regions = (KeyS *)h->gemm_regions.p; gp.region_cap = GEMM_REGION_CAP;
+        gp.samples = (unsigned *)h->gemm_samples.p; gp.seeded = gp.cnt + (size_t)qblocks_total * GEMM_BM; gp.arrive = gp.seeded + (size_t)qblocks_total * GEMM_BM;
+        gp.seed_tiles = 0;
         const int q0 = qb0 * GEMM_BM, nq_here = std::min(nq - q0, gp.n_qblocks * GEMM_BM);
         if (sample_tiles) {
             gp.tiles_total = sample_tiles; gp.tile_mul = tiles_total / sample_tiles; gp.sample_mode = 1;
@@ -493,13 +499,18 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         }
         gp.tiles_total = tiles_total; gp.tile_mul = 1; gp.sample_mode = 0;
         gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, tiles_total));
+        {   // seeding tiles per CTA: >= 128 tiles (32k rows) over the block's slices, more on long slices (<= 1/64 extra work)
+            const int tiles_per_cta = tiles_total / gp.n_slices;
+            const int want = std::max((128 + gp.n_slices - 1) / gp.n_slices, std::min(tiles_per_cta / 64, 8));
+            gp.seed_tiles = (!pool_mode && !h->no_seed && nq >= h->seed_min_batch && tiles_per_cta >= 8 * want) ? want : 0;
+        }
         KernelTimer kt(h, s);
         B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
         kt.stop();
         h->n_launches++;
         KernelTimer kt4(h, s, 4);
         B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, pool_mode ? GEMM_POOL_CAP : gp.n_slices * GEMM_HALVES * L,
-                                       gp.gthr, gp.cnt, h->counters + 2, q0, nq_here, s));
+                                       gp.gthr, gp.cnt, gp.arrive, gp.seeded, h->counters + 2, q0, nq_here, s));
         kt4.stop();
         h->n_launches++;
     }

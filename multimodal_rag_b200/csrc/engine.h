@@ -65,8 +65,8 @@ cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_m
 cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
                                     unsigned *cnt, int q0, int nq, cudaStream_t s);
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
-                                  int entries_per_query, unsigned *gthr, unsigned *cnt, unsigned long long *pool_stats, int q0, int nq,
-                                  cudaStream_t s);
+                                  int entries_per_query, unsigned *gthr, unsigned *cnt, unsigned *arrive, unsigned *seeded,
+                                  unsigned long long *pool_stats, int q0, int nq, cudaStream_t s);
 
 struct DevBuf {
     void *p = nullptr;
@@ -97,7 +97,7 @@ struct b2r_index {
     b2r::DevBuf o_rows, o_dist, o_dist64, o_count, need_list;
     int *need_ctl = nullptr;        // [4]: failed-certificate count, exit ticket (reset by K5 itself)
     b2r::DevBuf scan_lists, exact_lists;
-    b2r::DevBuf q_bf16, q_err, pass_bits, gthr, gemm_lists, gemm_regions;   // K3 scratch
+    b2r::DevBuf q_bf16, q_err, pass_bits, gthr, gemm_lists, gemm_regions, gemm_samples;   // K3 scratch
 
     // TMA tensor maps (K3), re-encoded when the buffer they describe moves or grows
     CUtensorMap tm_corpus, tm_query;
@@ -110,6 +110,8 @@ struct b2r_index {
     // optional per-kernel timing (bench.py roofline): CUDA events recorded around the scoring
     // kernel launches on the caller's stream, resolved lazily by b2r_kernel_time_ms
     bool timing = false;
+    bool no_seed = false;
+    int seed_min_batch = 0;
     int timing_stage = 0;           // which launch the events bracket: 0 scoring (default); B2R_TIME_STAGE=1..5 (development):
                                     // 1 prepare, 2 sampling pass, 3 sample reducer, 4 finalize, 5 exact fix-up
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;

@@ -22,6 +22,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "finalize.cuh"
 
@@ -30,6 +32,7 @@ namespace b2r {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int GEMM_EPI_WARPS = 8;
+constexpr unsigned long long GEMM_SEED_TIMEOUT_NS = 50000ull;   // bound on every wait of the in-kernel seeding phase
 constexpr int GEMM_HALVES = 2;          // epilogue warps w and w+4 share a TMEM lane quadrant and split a tile's columns
 constexpr int GEMM_SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA
 constexpr int GEMM_SMEM_SLACK = 1024 + 512;   // manual 1024-byte alignment + static barriers
@@ -50,6 +53,15 @@ struct GemmParams {
     KeyS *lists;                 // [nq][list_stride]: every thread appends its valid entries (atomic cursor cnt[q])
     KeyS *regions;               // pool mode (L = 0): [nq][n_slices*2][region_cap] private append regions
     int region_cap;              // entries per private region; overflow sets bit 31 of cnt[q] (-> exact fix-up)
+    // in-kernel threshold seeding (list mode, main pass).  Before its slice every CTA scans the slice's first
+    // seed_tiles tiles in sampling mode (best score of every 32-row step), posts the best L of them per thread and
+    // bumps arrive[qblock]; once all n_slices CTAs of the block have posted, the epilogue warps of each CTA fold
+    // the posts of their share of the block's queries into gthr[q] (the L-th best post) and raise seeded[q]; every
+    // epilogue thread waits (bounded) for its own query's flag, then the slice is scanned with that bound.
+    int seed_tiles;              // 0 = off
+    unsigned *samples;           // [launch queries (padded to 128)][n_slices*2][4 .. L] ordered score keys, 0 = empty
+    unsigned *seeded;            // [all queries] 1 = gthr[q] carries its seed (0 between calls)
+    unsigned *arrive;            // [all q-blocks] CTAs that have posted (0 between calls; finalize_union_kernel resets)
 };
 
 // Up to 512 dims (KB <= 8) the query block stays resident in shared memory (KB * 16 KB) and a pipeline stage
@@ -357,6 +369,57 @@ __device__ __forceinline__ void epi_chunk_pool(const uint32_t (&raw)[32], unsign
 }
 
 // ---------------------------------------------------------------------------------
+// in-kernel threshold seeding
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void epi_bar_sync() {       // the 8 epilogue warps only (named barrier 1)
+    asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
+}
+
+// One warp: the L-th largest of vals[0..n) (ordered score keys of DISTINCT rows, 0 = empty), 0 when fewer than
+// L are set.  Every lane keeps the L best of its strided share in registers, then the warp pops the
+// maximum L times.
+template <int L>
+__device__ __forceinline__ unsigned warp_lth_largest(const unsigned *vals, int n, int lane) {
+    unsigned top[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) top[i] = 0u;
+    constexpr int UN = 8;                                // independent L2 loads in flight per lane
+    for (int b = lane; b < n; b += 32 * UN) {
+        unsigned x[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) x[u] = b + 32 * u < n ? __ldcg(vals + b + 32 * u) : 0u;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (x[u] > top[L - 1]) {
+#pragma unroll
+                for (int i = L - 1; i >= 1; --i) {
+                    const bool above = x[u] > top[i - 1];
+                    top[i] = above ? top[i - 1] : (x[u] > top[i] ? x[u] : top[i]);
+                }
+                top[0] = x[u] > top[0] ? x[u] : top[0];
+            }
+        }
+    }
+    unsigned res = 0u;
+#pragma unroll 1
+    for (int r = 0; r < L; ++r) {
+        res = __reduce_max_sync(FULL_MASK, top[0]);
+        const unsigned who = __ballot_sync(FULL_MASK, top[0] == res);
+        if (lane == __ffs(who) - 1) {                    // the winning lane advances to its next best
+#pragma unroll
+            for (int i = 0; i < L - 1; ++i) top[i] = top[i + 1];
+            top[L - 1] = 0u;
+        }
+    }
+    return res;
+}
+
+// ---------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------
 // SAMPLE = the sampling-pass build of the kernel (separate instantiation: the main build's hot loop stays small)
@@ -387,6 +450,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const int qb = p.qblock0 + blockIdx.x % p.n_qblocks, slice = blockIdx.x / p.n_qblocks;
     const int t0 = (int)((long long)p.tiles_total * slice / p.n_slices);
     const int t1 = (int)((long long)p.tiles_total * (slice + 1) / p.n_slices);
+    constexpr bool SEED = L > 0 && !SAMPLE;                 // list-mode main pass: in-kernel threshold seeding
+    const int S = SEED ? min(p.seed_tiles, t1 - t0) : 0;    // seeding tiles in front of the slice
+    const int n_iter = S + (t1 - t0);
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_q);
@@ -412,7 +478,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 for (int kb = 0; kb < KB; ++kb) tma_load_2d(smA + (size_t)kb * A_KB_BYTES, &tm_q, &bar_a, kb * 64, qb * GEMM_BM);
             }
             int stage = 0; uint32_t phase = 0;
-            for (int t = t0; t < t1; ++t) {
+            for (int i = 0; i < n_iter; ++i) {
+                const int t = i < S ? t0 + i : t0 + i - S;      // the seeding tiles are scanned again by the main loop
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     mbar_expect_tx(&bar_full[stage], STAGE_BYTES);
@@ -427,7 +494,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (lane == 0) {
             if (A_RES) { mbar_wait(&bar_a, 0); tc_fence_after(); }
             int stage = 0; uint32_t phase = 0;
-            for (int t = t0, it = 0; t < t1; ++t, ++it) {
+            for (int it = 0; it < n_iter; ++it) {
                 const int buf = it & 1;
                 mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -457,44 +524,111 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const bool publish = q < p.nq;
         constexpr int LL = L > 0 ? L : 1;                          // pool mode (L = 0) keeps no list
         RegList<LL> list; list.init();
-        float thr = (L == 0 && q >= p.nq) ? INFINITY : -INFINITY;    // pool mode: padding lanes admit nothing
+        float thr = q >= p.nq ? INFINITY : -INFINITY;                // padding lanes admit nothing
         KeyS *region = nullptr;
         int rcount = 0;
         if (L == 0)
             region = p.regions + ((size_t)(q - p.qblock0 * GEMM_BM) * (p.n_slices * GEMM_HALVES) + (size_t)(slice * GEMM_HALVES + half)) * p.region_cap;
         unsigned g_seen = 0;
         unsigned *gq = p.gthr + q;
-        unsigned g_next = *reinterpret_cast<volatile unsigned *>(gq);   // seeded by the sampling pass
-        for (int t = t0, it = 0; t < t1; ++t, ++it) {
+        unsigned g_next = *reinterpret_cast<volatile unsigned *>(gq);   // seeded by the sampling pass (pool mode)
+
+        // one tile: TMEM -> registers in 32-column steps, two register buffers so the next load flies under this step
+        auto run_tile = [&](int t, int it, auto sample_c) {
+            constexpr bool SMP = decltype(sample_c)::value;
             const int buf = it & 1;
-            if (g_next > g_seen) { g_seen = g_next; thr = fmaxf(thr, KeyS::unord(g_next)); }
+            if (!SMP && g_next > g_seen) { g_seen = g_next; thr = fmaxf(thr, KeyS::unord(g_next)); }
             mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             // the other slices' progress on this query: loaded now, consumed at the top of the next tile
-            g_next = *reinterpret_cast<volatile unsigned *>(gq);
+            if (!SMP) g_next = *reinterpret_cast<volatile unsigned *>(gq);
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * NC * 32);
             const unsigned row0 = (unsigned)(t * p.tile_mul) * BN + (unsigned)(half * NC * 32);
             uint32_t va[32], vb[32];
             tmem_ld_x32(trow, va);
 #pragma unroll 1
-            for (int c = 0; c < NC; c += 2) {            // two register buffers: the next load flies under this step
+            for (int c = 0; c < NC; c += 2) {
                 tmem_ld_wait(va);
                 tmem_ld_x32(trow + (c + 1) * 32, vb);
-                if (L == 0) epi_chunk_pool<HAS_BIAS>(va, row0 + c * 32, p, thr, region, rcount);
-                else if (SAMPLE) epi_chunk_sample<LL, HAS_BIAS>(va, row0 + c * 32, p, list);
+                if constexpr (SMP) epi_chunk_sample<LL, HAS_BIAS>(va, row0 + c * 32, p, list);
+                else if constexpr (L == 0) epi_chunk_pool<HAS_BIAS>(va, row0 + c * 32, p, thr, region, rcount);
                 else epi_chunk<LL, HAS_BIAS>(va, row0 + c * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
                 tmem_ld_wait(vb);
                 if (c + 2 < NC) tmem_ld_x32(trow + (c + 2) * 32, va);
-                if (L == 0) epi_chunk_pool<HAS_BIAS>(vb, row0 + (c + 1) * 32, p, thr, region, rcount);
-                else if (SAMPLE) epi_chunk_sample<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list);
+                if constexpr (SMP) epi_chunk_sample<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list);
+                else if constexpr (L == 0) epi_chunk_pool<HAS_BIAS>(vb, row0 + (c + 1) * 32, p, thr, region, rcount);
                 else epi_chunk<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+        };
+
+        int it = 0;
+        if constexpr (SEED) {
+            if (S > 0) {
+                // ---- seeding phase (see GemmParams::seed_tiles) ----
+                // 1. the first S tiles of the slice in sampling mode: the list collects the best step maxima
+                for (int i = 0; i < S; ++i, ++it) run_tile(t0 + i, it, std::true_type());
+                // 2. post them, count this CTA in
+                // values posted per thread: its 4 best when the block's slices then still post >= 4 L between them (the
+                // L-th best of that union is as good a bound), else all it has (S * NC step maxima at most)
+                const int pv = p.n_slices * GEMM_HALVES >= LL ? 4 : min(LL, (S * NC + 3) & ~3);
+                if (publish) {
+                    unsigned *dst = p.samples + ((size_t)(q - p.qblock0 * GEMM_BM) * (p.n_slices * GEMM_HALVES) +
+                                                 (size_t)(slice * GEMM_HALVES + half)) * pv;
+#pragma unroll
+                    for (int i = 0; i < LL; i += 4) {
+                        if (i >= pv) break;
+                        uint4 o;
+                        o.x = list.r[i] != 0xffffffffu ? KeyS::ord(list.s[i]) : 0u;
+                        o.y = list.r[i + 1] != 0xffffffffu ? KeyS::ord(list.s[i + 1]) : 0u;
+                        o.z = list.r[i + 2] != 0xffffffffu ? KeyS::ord(list.s[i + 2]) : 0u;
+                        o.w = list.r[i + 3] != 0xffffffffu ? KeyS::ord(list.s[i + 3]) : 0u;
+                        *reinterpret_cast<uint4 *>(dst + i) = o;
+                    }
+                    __threadfence();
+                }
+                list.init();
+                epi_bar_sync();                                   // every epilogue thread's post is fenced
+                if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(p.arrive + qb, 1u); }
+                // 3. this CTA's share of the block's queries, one per epilogue warp: once every slice has posted,
+                //    the L-th best posted score becomes the query's bound.  All waits are bounded: the seed is an
+                //    accelerator, the certificate never depends on it.
+                const unsigned long long t_start = globaltimer_ns();
+                const int lq0 = GEMM_BM * slice / p.n_slices, lq1 = GEMM_BM * (slice + 1) / p.n_slices;
+                const int per_q = p.n_slices * GEMM_HALVES * pv;
+                for (int lq = lq0 + (warp - 2); lq < lq1; lq += GEMM_EPI_WARPS) {
+                    const int qs = qb * GEMM_BM + lq;
+                    if (qs >= p.nq) break;
+                    bool posted;
+                    while (!(posted = ld_acquire_gpu(p.arrive + qb) >= (unsigned)p.n_slices)) {
+                        if (globaltimer_ns() - t_start > GEMM_SEED_TIMEOUT_NS) break;
+                        __nanosleep(64);
+                    }
+                    if (!posted) break;
+                    const unsigned v = warp_lth_largest<LL>(p.samples + (size_t)(qs - p.qblock0 * GEMM_BM) * per_q, per_q, lane);
+                    if (lane == 0) {
+                        if (v != 0u) atomicMax(p.gthr + qs, v);
+                        __threadfence();
+                        atomicExch(p.seeded + qs, 1u);
+                    }
+                }
+                // 4. wait for this thread's own query
+                if (publish) {
+                    while (ld_acquire_gpu(p.seeded + q) == 0u) {
+                        if (globaltimer_ns() - t_start > GEMM_SEED_TIMEOUT_NS) break;
+                        __nanosleep(64);
+                    }
+                }
+                __syncwarp();
+                g_next = *reinterpret_cast<volatile unsigned *>(gq);
+            }
         }
+        for (int t = t0; t < t1; ++t, ++it) run_tile(t, it, std::integral_constant<bool, SAMPLE>());
+
         if (L == 0) {
             if (q < p.nq && rcount > 0) {     // compact the private region into the query's pool
                 const int nv = min(rcount, p.region_cap);
@@ -506,9 +640,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 if (!fits || rcount > p.region_cap) atomicOr(&p.cnt[q], 0x80000000u);   // rows were dropped: not certifiable
             }
         } else if (q < p.nq) {    // append this thread's entries to the query's candidate pool (compact: most lists are short)
+            // entries below the bound published so far need not travel: whatever is dropped here scores
+            // <= the final gthr[q], which is all the certificate asks of a row outside the pool
             int nv = 0;
+            if constexpr (SAMPLE) {
 #pragma unroll
-            for (int i = 0; i < LL; ++i) nv += list.r[i] != 0xffffffffu ? 1 : 0;
+                for (int i = 0; i < LL; ++i) nv += list.r[i] != 0xffffffffu ? 1 : 0;
+            } else {
+                const unsigned g_now = *reinterpret_cast<volatile unsigned *>(gq);
+#pragma unroll
+                for (int i = 0; i < LL; ++i) nv += (list.r[i] != 0xffffffffu && KeyS::ord(list.s[i]) >= g_now) ? 1 : 0;
+            }
             if (nv) {
                 KeyS *dst = p.lists + (size_t)q * p.list_stride + atomicAdd(&p.cnt[q], (unsigned)nv);
 #pragma unroll
@@ -569,7 +711,8 @@ constexpr int FU_MAX_SEL = 512;       // survivors of the score cut that are ran
 template <int EPL>
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, int list_stride, int max_entries,
-                      unsigned *__restrict__ gthr, unsigned *__restrict__ cnt, unsigned long long *pool_stats, int q0) {
+                      unsigned *__restrict__ gthr, unsigned *__restrict__ cnt, unsigned *__restrict__ arrive,
+                      unsigned *__restrict__ seeded, unsigned long long *pool_stats, int q0) {
     constexpr int KP = 32 * EPL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyS *stage = reinterpret_cast<KeyS *>(smem_raw);                       // [FIN_WARPS*KP]
@@ -669,7 +812,8 @@ finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, 
         nvalid = __syncthreads_count(threadIdx.x < KP && stage[threadIdx.x < KP ? threadIdx.x : 0].valid());
     }
     if (threadIdx.x == 0) {
-        gthr[qi] = 0u; cnt[qi] = 0u;                        // leave the shared state clean for the next call
+        gthr[qi] = 0u; cnt[qi] = 0u; seeded[qi] = 0u;       // leave the shared state clean for the next call
+        if (qi % GEMM_BM == 0) arrive[qi / GEMM_BM] = 0u;
         atomicAdd(pool_stats, 1ull); atomicAdd(pool_stats + 1, (unsigned long long)entries);
     }
     // rows outside the candidate set: either in the pool but below the KP-th candidate, or never kept

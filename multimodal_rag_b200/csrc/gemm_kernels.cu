@@ -14,9 +14,7 @@ typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmParams);
 #define B2R_CAT2(a, b) a##b
 #define B2R_CAT(a, b) B2R_CAT2(a, b)
 gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias, bool sample) {
-    if (sample) {        // sampling-pass build (lists of step maxima); pool mode samples with L = 32
-        if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true, true> : gemm_topk_kernel<B2R_KB, 8, false, true>;
-        if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true, true> : gemm_topk_kernel<B2R_KB, 16, false, true>;
+    if (sample) {        // sampling-pass build (lists of step maxima): pool mode only, L = 32 (list mode seeds in-kernel)
         if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true, true> : gemm_topk_kernel<B2R_KB, 32, false, true>;
         return nullptr;
     }
@@ -158,8 +156,8 @@ cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entr
 }
 
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
-                                  int entries_per_query, unsigned *gthr, unsigned *cnt, unsigned long long *pool_stats, int q0, int nq,
-                                  cudaStream_t s) {
+                                  int entries_per_query, unsigned *gthr, unsigned *cnt, unsigned *arrive, unsigned *seeded,
+                                  unsigned long long *pool_stats, int q0, int nq, cudaStream_t s) {
     const size_t smem = finalize_union_smem(epl, fin.dp);
     if (smem > 48 * 1024) {      // opt in to large dynamic shared memory (per function; cheap, idempotent)
         cudaError_t e = cudaSuccess;
@@ -170,10 +168,10 @@ cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS
         if (e != cudaSuccess) return e;
     }
     switch (epl) {
-        case 1: return launch_pdl(finalize_union_kernel<1>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
-        case 2: return launch_pdl(finalize_union_kernel<2>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
-        case 4: return launch_pdl(finalize_union_kernel<4>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
-        case 8: return launch_pdl(finalize_union_kernel<8>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, pool_stats, q0);
+        case 1: return launch_pdl(finalize_union_kernel<1>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, arrive, seeded, pool_stats, q0);
+        case 2: return launch_pdl(finalize_union_kernel<2>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, arrive, seeded, pool_stats, q0);
+        case 4: return launch_pdl(finalize_union_kernel<4>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, arrive, seeded, pool_stats, q0);
+        case 8: return launch_pdl(finalize_union_kernel<8>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, arrive, seeded, pool_stats, q0);
         default: return cudaErrorInvalidValue;
     }
 }
