@@ -72,6 +72,54 @@ __device__ __forceinline__ double exact_distance_warp(const FinalizeParams &p, c
     return p.space == 0 ? acc : 1.0 - acc;
 }
 
+// The same with G lanes per row (G = 8 or 16): 32/G rows per warp in flight, for the short candidate prefixes of
+// the re-rank.  `sub` = lane % G; every lane of the group returns the distance.
+template <int G>
+__device__ __forceinline__ double exact_distance_group(const FinalizeParams &p, const float *qv, unsigned row, int sub) {
+    double a0 = 0.0, a1 = 0.0;
+    const int dp = p.dp;
+    if (p.master) {
+        const float4 *xr = reinterpret_cast<const float4 *>(p.master + (size_t)row * dp);
+        const float4 *q4 = reinterpret_cast<const float4 *>(qv);
+#pragma unroll 6
+        for (int c = sub; c < dp / 4; c += G) {
+            float4 x = __ldcg(xr + c);
+            float4 q = q4[c];
+            if (p.space == 0) {
+                double a = (double)q.x - (double)x.x, b = (double)q.y - (double)x.y;
+                double cc = (double)q.z - (double)x.z, d = (double)q.w - (double)x.w;
+                a0 = fma(a, a, a0); a1 = fma(b, b, a1); a0 = fma(cc, cc, a0); a1 = fma(d, d, a1);
+            } else {
+                a0 = fma((double)q.x, (double)x.x, a0); a1 = fma((double)q.y, (double)x.y, a1);
+                a0 = fma((double)q.z, (double)x.z, a0); a1 = fma((double)q.w, (double)x.w, a1);
+            }
+        }
+    } else {
+        const uint4 *xr = p.corpus + (size_t)row * (dp / 8);
+#pragma unroll 3
+        for (int c = sub; c < dp / 8; c += G) {
+            uint4 w = __ldcg(xr + c);
+            const float *qq = qv + c * 8;
+            unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double x0 = (double)bf16lo(ww[i]), x1 = (double)bf16hi(ww[i]);
+                double q0 = (double)qq[2 * i], q1 = (double)qq[2 * i + 1];
+                if (p.space == 0) {
+                    double a = q0 - x0, b = q1 - x1;
+                    a0 = fma(a, a, a0); a1 = fma(b, b, a1);
+                } else {
+                    a0 = fma(q0, x0, a0); a1 = fma(q1, x1, a1);
+                }
+            }
+        }
+    }
+    double acc = a0 + a1;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
+    return p.space == 0 ? acc : 1.0 - acc;
+}
+
 // Sort `n` exact keys held in smem (ex[0..n)) by rank computation and emit results.
 // Called by all FIN_THREADS threads.  Returns (via smem slot) nothing; writes outputs.
 __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, const KeyD *ex, int n,
@@ -114,26 +162,28 @@ __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, con
 __device__ __forceinline__ void finalize_candidates(const FinalizeParams &p, int qi, const KeyS *sm_keys, int nvalid,
                                                     float T, KeyD *sm_ex, const float *sm_q, KeyD *sm_misc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 32) {
-        double qn2 = 0.0;
-        for (int i = lane; i < p.dp; i += 32) qn2 = fma((double)sm_q[i], (double)sm_q[i], qn2);
-        qn2 = warp_sum(qn2);
-        const double xn = sqrt((double)p.max_norm2[0]), dxn = sqrt((double)p.max_norm2[1]), qn = sqrt(qn2);
-        const double dq = p.q_err ? (double)p.q_err[qi] : 0.0;
-        const double eps = dq * (xn + dxn) + qn * dxn + (double)p.eps_rel * (qn + dq) * (xn + dxn) +
-                           1e-6 * (0.5 * xn * xn + qn * xn) + 1e-30;
-        if (lane == 0) { sm_misc[1].d = eps; sm_misc[2].d = qn2; sm_misc[0] = KeyD::worst(); }
-    }
-    __syncthreads();
-    const double eps = sm_misc[1].d, qn2 = sm_misc[2].d;
-    // ---- prefix that can still reach the top-k ----
+    // every warp derives eps and the prefix length on its own (same inputs, same arithmetic -> same values):
+    // no barrier stands between the ranking and the first row fetch
+    double qn2 = 0.0;
+    for (int i = lane; i < p.dp; i += 32) qn2 = fma((double)sm_q[i], (double)sm_q[i], qn2);
+    qn2 = warp_sum(qn2);
+    const double xn = sqrt((double)__ldg(p.max_norm2)), dxn = sqrt((double)__ldg(p.max_norm2 + 1)), qn = sqrt(qn2);
+    const double dq = p.q_err ? (double)__ldg(p.q_err + qi) : 0.0;
+    const double eps = dq * (xn + dxn) + qn * dxn + (double)p.eps_rel * (qn + dq) * (xn + dxn) +
+                       1e-6 * (0.5 * xn * xn + qn * xn) + 1e-30;
+    if (threadIdx.x == 0) sm_misc[0] = KeyD::worst();
+    // ---- prefix that can still reach the top-k (the list is sorted, so the survivors are a prefix) ----
     int m = nvalid;
     if (nvalid > p.k) {
         const double cut = (double)sm_keys[p.k - 1].score() - 2.0 * eps;
-        // nvalid <= KP <= FIN_THREADS: one candidate per thread; the list is sorted, so the survivors are a prefix
-        m = __syncthreads_count(threadIdx.x < nvalid && (double)sm_keys[threadIdx.x].score() >= cut);
+        m = 0;
+        for (int i0 = 0; i0 < nvalid; i0 += 32) {
+            const int i = i0 + lane;
+            m += __popc(__ballot_sync(FULL_MASK, i < nvalid && (double)sm_keys[i].score() >= cut));
+        }
     }
-    {   // pull the rows towards L2 first: the re-rank below is a chain of dependent loads per warp
+    constexpr int G = 16, PER_WARP = 32 / G;
+    if (m > FIN_WARPS * PER_WARP) {   // several rounds per warp: pull the rows towards L2 first
         const int row_bytes = p.master ? p.dp * 4 : p.dp * 2;
         const int lines = (row_bytes + 127) / 128;
         for (int i = threadIdx.x; i < m * lines; i += FIN_THREADS) {
@@ -143,10 +193,11 @@ __device__ __forceinline__ void finalize_candidates(const FinalizeParams &p, int
             asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(i % lines) * 128));
         }
     }
-    for (int c = warp; c < m; c += FIN_WARPS) {
-        unsigned row = sm_keys[c].row();
-        double d = exact_distance_warp(p, sm_q, row, lane);
-        if (lane == 0) sm_ex[c] = KeyD::make(d, row);
+    for (int c0 = warp * PER_WARP; c0 < m; c0 += FIN_WARPS * PER_WARP) {     // warp-uniform trip count
+        const int c = c0 + lane / G;
+        const unsigned row = sm_keys[c < m ? c : m - 1].row();
+        const double d = exact_distance_group<G>(p, sm_q, row, lane % G);
+        if (c < m && lane % G == 0) sm_ex[c] = KeyD::make(d, row);
     }
     __syncthreads();
     emit_sorted(p, qi, sm_ex, m, &sm_misc[0]);
