@@ -159,7 +159,7 @@ extern "C" int b2r_destroy(b2r_handle h) {
     DevBuf *bufs[] = {&h->x_stage, &h->t_stage, &h->q_raw, &h->q_prep, &h->allow, &h->rows_stage, &h->gather_out,
                       &h->o_rows, &h->o_dist, &h->o_dist64, &h->o_count, &h->need_list, &h->scan_lists,
                       &h->exact_lists, &h->q_bf16, &h->q_err, &h->pass_bits, &h->gthr, &h->gemm_lists, &h->gemm_regions,
-                      &h->gemm_samples};
+                      &h->gemm_samples, &h->q_eps};
     for (DevBuf *b : bufs) release(*b);
     for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -283,7 +283,7 @@ extern "C" int b2r_ingest_f32(b2r_handle h, const float *x, int64_t n, const uin
     p.bias = h->bias ? h->bias + h->rows : nullptr;
     p.type_out = h->type_code + h->rows;
     p.type_in = td;
-    p.max_norm2 = h->max_norm2; p.qerr = nullptr;
+    p.max_norm2 = h->max_norm2; p.qerr = nullptr; p.zero = nullptr; p.zero_words = 0; p.q_eps = nullptr; p.norms = nullptr; p.eps_rel = 0.f;
     const int wpb = INGEST_THREADS / 32;
     int grid = (int)std::min<int64_t>((n + wpb - 1) / wpb, (int64_t)h->sm_count * 16);
     const bool vec = (h->dim % 8 == 0) && (((uintptr_t)xd & 15) == 0);
@@ -434,14 +434,10 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
     const int qblocks_total = (nq + GEMM_BM - 1) / GEMM_BM;
     // pool capacity per query: list mode = every list full; pool mode = 16x the expected 1024 entries (beyond that
     // the query is flagged and re-done by the exact scan)
-    const int list_stride = pool_mode ? GEMM_POOL_CAP : h->sm_count * GEMM_HALVES * L;
+    const int list_stride = pool_mode ? GEMM_POOL_CAP : std::max(2 * FIN_THREADS, h->sm_count * GEMM_HALVES * L);   // the finalize reads 512 slots unconditionally
     int rc;
     if ((rc = ensure(h->pass_bits, (size_t)n_words * 4 + 16)) != B2R_OK) return rc;
-    {   // gthr is all-zero between calls: zeroed when (re)allocated, and finalize_union_kernel clears what it read
-        const void *before = h->gthr.p;
-        if ((rc = ensure(h->gthr, (size_t)qblocks_total * (GEMM_BM * 3 + 1) * 4)) != B2R_OK) return rc;   // bounds, cursors, seed flags, arrivals
-        if (h->gthr.p != before) B2R_CUDA(cudaMemsetAsync(h->gthr.p, 0, h->gthr.bytes, s));
-    }
+    // h->gthr (bounds, cursors, seed flags, arrival counters) was sized and cleared by the query preparation
     // list mode pools: [nq][SMs*2*L].  Pool mode: the sampling pass needs [nq][SMs*2*32] and the main pass
     // compacts at most [launch queries][slots*cap] -- both fit the same allocation.
     const int nq_launch_max = std::min(qblocks_total, GEMM_MAX_QBLOCKS) * GEMM_BM;   // padded: every lane of a block owns a region
@@ -485,6 +481,9 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         gp.regions = (KeyS *)h->gemm_regions.p; gp.region_cap = GEMM_REGION_CAP;
         gp.samples = (unsigned *)h->gemm_samples.p; gp.seeded = gp.cnt + (size_t)qblocks_total * GEMM_BM; gp.arrive = gp.seeded + (size_t)qblocks_total * GEMM_BM;
         gp.seed_tiles = 0;
+        UnionParams un;
+        un.lists = gp.lists; un.list_stride = list_stride; un.gthr = gp.gthr; un.cnt = gp.cnt;
+        un.pool_stats = h->counters + 2;
         const int q0 = qb0 * GEMM_BM, nq_here = std::min(nq - q0, gp.n_qblocks * GEMM_BM);
         if (sample_tiles) {
             gp.tiles_total = sample_tiles; gp.tile_mul = tiles_total / sample_tiles; gp.sample_mode = 1;
@@ -504,13 +503,13 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
             const int want = std::max((128 + gp.n_slices - 1) / gp.n_slices, std::min(tiles_per_cta / 64, 8));
             gp.seed_tiles = (!pool_mode && !h->no_seed && nq >= h->seed_min_batch && tiles_per_cta >= 8 * want) ? want : 0;
         }
+        un.max_entries = pool_mode ? GEMM_POOL_CAP : gp.n_slices * GEMM_HALVES * L;
         KernelTimer kt(h, s);
         B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
         kt.stop();
         h->n_launches++;
         KernelTimer kt4(h, s, 4);
-        B2R_CUDA(finalize_union_launch(epl, fin, gp.lists, list_stride, pool_mode ? GEMM_POOL_CAP : gp.n_slices * GEMM_HALVES * L,
-                                       gp.gthr, gp.cnt, gp.arrive, gp.seeded, h->counters + 2, q0, nq_here, s));
+        B2R_CUDA(finalize_union_launch(epl, fin, un, q0, nq_here, s));
         kt4.stop();
         h->n_launches++;
     }
@@ -555,6 +554,7 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     }
     if ((rc = ensure(h->q_prep, (size_t)nq * h->dp * 4)) != B2R_OK) return rc;
     if ((rc = ensure(h->need_list, (size_t)nq * 4)) != B2R_OK) return rc;
+    if ((rc = ensure(h->q_eps, (size_t)nq * 16)) != B2R_OK) return rc;
     long long *o_rows = (long long *)out_rows; float *o_dist = out_dist; double *o_dist64 = out_dist64; int *o_count = out_count;
     if (!dev_out) {
         if ((rc = ensure(h->o_rows, (size_t)nq * k * 8)) != B2R_OK) return rc;
@@ -592,6 +592,18 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
         p.corpus = path == 2 ? (uint4 *)h->q_bf16.p : nullptr; p.master = (float *)h->q_prep.p; p.bias = nullptr;
         p.type_out = nullptr; p.type_in = nullptr; p.max_norm2 = nullptr;
         p.qerr = path == 2 ? (float *)h->q_err.p : nullptr;
+        // Error bound of the scan scores, per query, from the MEASURED rounding errors (max |x - bf16(x)| from ingest,
+        // |q - bf16(q)| when K3 rounds the queries); eps_rel only carries the fp32 accumulation slop:
+        // (dp+8) * 2^-24 for K2's FFMA chain, 4x that for the tensor core's accumulator.
+        p.q_eps = (double *)h->q_eps.p; p.norms = h->max_norm2;
+        p.eps_rel = (float)(h->dp + 8) * 5.9604645e-8f * (path == 2 ? 4.f : 1.f) * 1.01f;
+        p.zero = nullptr; p.zero_words = 0;
+        if (path == 2) {   // K3's per-call shared state: [bounds | cursors | seed flags][q-blocks * 128], [arrivals][q-blocks]
+            const int qblocks = (nq + GEMM_BM - 1) / GEMM_BM;
+            p.zero_words = qblocks * (GEMM_BM * 3 + 1);
+            if ((rc = ensure(h->gthr, (size_t)p.zero_words * 4)) != B2R_OK) return rc;
+            p.zero = (unsigned *)h->gthr.p;
+        }
         const int wpb = INGEST_THREADS / 32;
         int grid = std::min((nq + wpb - 1) / wpb, h->sm_count * 8);
         const bool vec = (h->dim % 8 == 0) && (((uintptr_t)q_raw & 15) == 0);
@@ -607,12 +619,7 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     fin.max_norm2 = h->max_norm2; fin.dp = h->dp; fin.space = h->space; fin.k = k;
     fin.row_base = h->row_base; fin.out_rows = o_rows; fin.out_dist = o_dist; fin.out_dist64 = o_dist64;
     fin.out_count = o_count; fin.need_ctl = h->need_ctl; fin.need_list = (int *)h->need_list.p;
-    // Error bound of the scan scores: finalize_candidates() builds it from the MEASURED rounding errors
-    // (max |x - bf16(x)| from ingest, |q - bf16(q)| from the preparation above when K3 rounds the queries);
-    // eps_rel only carries the fp32 accumulation slop: (dp+8) * 2^-24 for K2's FFMA chain, 4x that for the
-    // tensor core's accumulator.
-    fin.q_err = path == 2 ? (const float *)h->q_err.p : nullptr;
-    fin.eps_rel = (float)(h->dp + 8) * 5.9604645e-8f * (path == 2 ? 4.f : 1.f) * 1.01f;
+    fin.q_eps = (const double *)h->q_eps.p;
 
     if (path == 1) {
         ScanParams sp;

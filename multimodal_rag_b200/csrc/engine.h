@@ -55,6 +55,7 @@ cudaError_t exact_launch(int epl, const ExactParams &p, int grid, cudaStream_t s
 
 // K3 (gemm_kernels.cu): tcgen05 batched scoring
 struct GemmParams;
+struct UnionParams;
 bool gemm_supported(int dp, int k);
 int gemm_list_len(int k);          // per-thread list length L for n_results = k; 0 = pool mode (32 < k <= 128); -1 = unsupported
 int gemm_tile_rows(int dp);        // corpus rows per MMA tile (BN)
@@ -65,9 +66,7 @@ cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_m
                              unsigned n, unsigned n_words, uint32_t *out, int sm_count, cudaStream_t s);
 cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
                                     unsigned *cnt, int q0, int nq, cudaStream_t s);
-cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
-                                  int entries_per_query, unsigned *gthr, unsigned *cnt, unsigned *arrive, unsigned *seeded,
-                                  unsigned long long *pool_stats, int q0, int nq, cudaStream_t s);
+cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const UnionParams &u, int q0, int nq, cudaStream_t s);
 
 struct DevBuf {
     void *p = nullptr;
@@ -99,6 +98,7 @@ struct b2r_index {
     int *need_ctl = nullptr;        // [4]: failed-certificate count, exit ticket (reset by K5 itself)
     b2r::DevBuf scan_lists, exact_lists;
     b2r::DevBuf q_bf16, q_err, pass_bits, gthr, gemm_lists, gemm_regions, gemm_samples;   // K3 scratch
+    b2r::DevBuf q_eps;              // [nq][2] fp64: per-query error bound and |q|^2 (query preparation)
 
     // TMA tensor maps (K3), re-encoded when the buffer they describe moves or grows
     CUtensorMap tm_corpus, tm_query;

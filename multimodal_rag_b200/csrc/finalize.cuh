@@ -10,12 +10,25 @@ namespace b2r {
 constexpr int FIN_THREADS = 256;
 constexpr int FIN_WARPS = FIN_THREADS / 32;
 
+// Which FIN_THREADS threads run the finalize code: a whole CTA of that size (FinCta<0>), or a 256-thread group
+// of a larger CTA, threads OFFSET .. OFFSET+255, synchronised by named barrier 1.  (Running the finalize as the
+// tail of K3 was measured and dropped: a finalize is a ~10 us latency chain per query, and a K3 CTA would walk
+// its 1-8 queries one after the other, while the separate launch runs all queries side by side.)
+template <int OFFSET>
+struct FinCta {
+    static __device__ __forceinline__ int tid() { return (int)threadIdx.x - OFFSET; }
+    static __device__ __forceinline__ void sync() {
+        if (OFFSET == 0) __syncthreads();
+        else asm volatile("bar.sync 1, %0;" ::"n"(FIN_THREADS) : "memory");
+    }
+};
+
 struct FinalizeParams {
     const float *master;        // [rows, dp] fp32 stored rows, or nullptr (bf16-only corpus)
     const uint4 *corpus;        // [rows, dp] bf16 stored rows
     const float *q;             // [nq, dp] fp32 prepared queries (normalised for cosine)
     const float *max_norm2;     // device [2]: max |x|^2 over stored rows, max |x - bf16(x)|^2 (0 without an fp32 master)
-    const float *q_err;         // [nq] |q - bf16(q)| when the scoring kernel rounded the queries (K3), else nullptr
+    const double *q_eps;        // [nq][2]: error bound eps of this query's scan scores, |q|^2 (query preparation, ingest.cuh)
     int dp, space, k;
     long long row_base;         // added to local rows on output (shard offset)
     long long *out_rows;        // [nq, k]
@@ -24,7 +37,6 @@ struct FinalizeParams {
     int *out_count;             // [nq]
     int *need_ctl;              // [0] = number of queries whose certificate failed (this call), [1] = exit ticket
     int *need_list;             // [nq]: those queries, in arrival order; the exact scan (K5) redoes them
-    float eps_rel;              // accumulation slop of the scoring kernel, relative to |q| * max|x|
 };
 
 // exact distance between prepared query and stored row, fp64 accumulation, whole warp
@@ -122,11 +134,13 @@ __device__ __forceinline__ double exact_distance_group(const FinalizeParams &p, 
 
 // Sort `n` exact keys held in smem (ex[0..n)) by rank computation and emit results.
 // Called by all FIN_THREADS threads.  Returns (via smem slot) nothing; writes outputs.
+template <class C = FinCta<0>>
 __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, const KeyD *ex, int n,
                                             KeyD *kth_out /* smem, rank k-1 entry or worst */) {
     const int k = p.k;
     const int cnt = n < k ? n : k;
-    for (int t = threadIdx.x; t < n; t += FIN_THREADS) {
+    const int tid = C::tid();
+    for (int t = tid; t < n; t += FIN_THREADS) {
         KeyD me = ex[t];
         int rank = 0;
         for (int j = 0; j < n; ++j) rank += KeyD::better(ex[j], me) ? 1 : 0;
@@ -137,12 +151,12 @@ __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, con
         }
         if (rank == k - 1) *kth_out = me;
     }
-    for (int t = cnt + threadIdx.x; t < k; t += FIN_THREADS) {
+    for (int t = cnt + tid; t < k; t += FIN_THREADS) {
         p.out_rows[(size_t)qi * k + t] = -1;
         p.out_dist[(size_t)qi * k + t] = __int_as_float(0x7f800000);
         if (p.out_dist64) p.out_dist64[(size_t)qi * k + t] = __longlong_as_double(0x7ff0000000000000ll);
     }
-    if (threadIdx.x == 0) p.out_count[qi] = cnt;
+    if (tid == 0) p.out_count[qi] = cnt;
 }
 
 // Stages shared by every scoring path once the candidate set is known (sm_keys: nvalid candidates,
@@ -159,19 +173,29 @@ __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, con
 // 2. Certificate: every row outside the candidate set has scan score <= T, hence exact score <= T + eps.
 //    If the k-th exact candidate beats that, no outsider belongs to the top-k; otherwise the query goes
 //    on the exact-scan work list.  T = -inf: there are no outsiders.
+template <class C = FinCta<0>>
 __device__ __forceinline__ void finalize_candidates(const FinalizeParams &p, int qi, const KeyS *sm_keys, int nvalid,
                                                     float T, KeyD *sm_ex, const float *sm_q, KeyD *sm_misc) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // every warp derives eps and the prefix length on its own (same inputs, same arithmetic -> same values):
-    // no barrier stands between the ranking and the first row fetch
-    double qn2 = 0.0;
-    for (int i = lane; i < p.dp; i += 32) qn2 = fma((double)sm_q[i], (double)sm_q[i], qn2);
-    qn2 = warp_sum(qn2);
-    const double xn = sqrt((double)__ldg(p.max_norm2)), dxn = sqrt((double)__ldg(p.max_norm2 + 1)), qn = sqrt(qn2);
-    const double dq = p.q_err ? (double)__ldg(p.q_err + qi) : 0.0;
-    const double eps = dq * (xn + dxn) + qn * dxn + (double)p.eps_rel * (qn + dq) * (xn + dxn) +
-                       1e-6 * (0.5 * xn * xn + qn * xn) + 1e-30;
-    if (threadIdx.x == 0) sm_misc[0] = KeyD::worst();
+    const int tid = C::tid();
+    const int lane = tid & 31, warp = tid >> 5;
+    // start pulling the likeliest rows towards L2 (the re-rank prefix is rarely longer than this): a cold row
+    // costs a DRAM access and usually a TLB miss, the longest single wait of the whole finalize
+    constexpr int G = 16, PER_WARP = 32 / G, EARLY = FIN_WARPS * PER_WARP;
+    const int row_bytes = p.master ? p.dp * 4 : p.dp * 2;
+    const int lines = (row_bytes + 127) / 128;
+    auto prefetch_rows = [&](int first, int last) {
+        for (int i = first * lines + tid; i < last * lines; i += FIN_THREADS) {
+            const unsigned row = sm_keys[i / lines].row();
+            const char *base = p.master ? reinterpret_cast<const char *>(p.master + (size_t)row * p.dp)
+                                        : reinterpret_cast<const char *>(p.corpus + (size_t)row * (p.dp / 8));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(i % lines) * 128));
+        }
+    };
+    prefetch_rows(0, min(nvalid, EARLY));
+    // eps and |q|^2 come from the query preparation; every warp derives the prefix length on its own (same
+    // inputs, same arithmetic -> same value), so no barrier stands between the ranking and the first row fetch
+    const double eps = __ldg(p.q_eps + 2 * qi), qn2 = __ldg(p.q_eps + 2 * qi + 1);
+    if (tid == 0) sm_misc[0] = KeyD::worst();
     // ---- prefix that can still reach the top-k (the list is sorted, so the survivors are a prefix) ----
     int m = nvalid;
     if (nvalid > p.k) {
@@ -182,27 +206,17 @@ __device__ __forceinline__ void finalize_candidates(const FinalizeParams &p, int
             m += __popc(__ballot_sync(FULL_MASK, i < nvalid && (double)sm_keys[i].score() >= cut));
         }
     }
-    constexpr int G = 16, PER_WARP = 32 / G;
-    if (m > FIN_WARPS * PER_WARP) {   // several rounds per warp: pull the rows towards L2 first
-        const int row_bytes = p.master ? p.dp * 4 : p.dp * 2;
-        const int lines = (row_bytes + 127) / 128;
-        for (int i = threadIdx.x; i < m * lines; i += FIN_THREADS) {
-            const unsigned row = sm_keys[i / lines].row();
-            const char *base = p.master ? reinterpret_cast<const char *>(p.master + (size_t)row * p.dp)
-                                        : reinterpret_cast<const char *>(p.corpus + (size_t)row * (p.dp / 8));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(i % lines) * 128));
-        }
-    }
+    if (m > EARLY) prefetch_rows(EARLY, m);     // several rounds per warp: the rest of the prefix too
     for (int c0 = warp * PER_WARP; c0 < m; c0 += FIN_WARPS * PER_WARP) {     // warp-uniform trip count
         const int c = c0 + lane / G;
         const unsigned row = sm_keys[c < m ? c : m - 1].row();
         const double d = exact_distance_group<G>(p, sm_q, row, lane % G);
         if (c < m && lane % G == 0) sm_ex[c] = KeyD::make(d, row);
     }
-    __syncthreads();
-    emit_sorted(p, qi, sm_ex, m, &sm_misc[0]);
-    __syncthreads();
-    if (threadIdx.x == 0 && T > -INFINITY) {
+    C::sync();
+    emit_sorted<C>(p, qi, sm_ex, m, &sm_misc[0]);
+    C::sync();
+    if (tid == 0 && T > -INFINITY) {
         const KeyD kth = sm_misc[0];
         double s_k;
         if (!kth.valid()) s_k = -1e300;                       // fewer than k candidates although rows were rejected
@@ -210,23 +224,23 @@ __device__ __forceinline__ void finalize_candidates(const FinalizeParams &p, int
         else s_k = 1.0 - kth.d;
         if (!(s_k - eps > (double)T)) p.need_list[atomicAdd(&p.need_ctl[0], 1)] = qi;
     }
-    __syncthreads();
+    C::sync();
 }
 
 // Tree-merge the per-warp lists of a CTA: after the call warp 0 holds the CTA's best KP and
 // has stored them rank-ordered at sm[0, KP).  sm must hold FIN_WARPS*KP keys.  All threads call.
-template <class K, int EPL>
+template <class K, int EPL, class C = FinCta<0>>
 __device__ __forceinline__ void cta_tree_merge(WarpList<K, EPL> &wl, K *sm, int warp, int lane) {
     constexpr int KP = 32 * EPL;
 #pragma unroll
     for (int half = FIN_WARPS / 2; half >= 1; half >>= 1) {
         if (warp >= half && warp < 2 * half) wl.store(sm + warp * KP, lane);
-        __syncthreads();
+        C::sync();
         if (warp < half) wl.template merge_bitonic<false>(sm + (warp + half) * KP, lane);
-        __syncthreads();
+        C::sync();
     }
     if (warp == 0) wl.store(sm, lane);
-    __syncthreads();
+    C::sync();
 }
 
 // Merge nlists rank-ordered KeyS lists of length KP (global memory, written by other

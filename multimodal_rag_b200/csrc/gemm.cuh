@@ -37,6 +37,14 @@ constexpr int GEMM_HALVES = 2;          // epilogue warps w and w+4 share a TMEM
 constexpr int GEMM_SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA
 constexpr int GEMM_SMEM_SLACK = 1024 + 512;   // manual 1024-byte alignment + static barriers
 
+// What the finalize needs to know about the candidate pools (K3's outputs).
+struct UnionParams {
+    const KeyS *lists;           // [nq][list_stride]
+    int list_stride, max_entries;
+    unsigned *gthr, *cnt;        // [nq] final shared bound / pool cursor (bit 31 = overflow)
+    unsigned long long *pool_stats;
+};
+
 struct GemmParams {
     unsigned n;                  // rows in this shard
     int nq;                      // queries in the batch
@@ -59,9 +67,9 @@ struct GemmParams {
     // the posts of their share of the block's queries into gthr[q] (the L-th best post) and raise seeded[q]; every
     // epilogue thread waits (bounded) for its own query's flag, then the slice is scanned with that bound.
     int seed_tiles;              // 0 = off
-    unsigned *samples;           // [launch queries (padded to 128)][n_slices*2][4 .. L] ordered score keys, 0 = empty
-    unsigned *seeded;            // [all queries] 1 = gthr[q] carries its seed (0 between calls)
-    unsigned *arrive;            // [all q-blocks] CTAs that have posted (0 between calls; finalize_union_kernel resets)
+    unsigned *samples;           // [launch queries (padded to 128)][n_slices*2][2 .. L] ordered score keys, 0 = empty
+    unsigned *seeded;            // [all queries] 0 = not seeded yet, 1 = seeded without a bound, else the seed (= gthr[q] then)
+    unsigned *arrive;            // [all q-blocks] CTAs that have posted (0 between calls: the query preparation clears it)
 };
 
 // Up to 512 dims (KB <= 8) the query block stays resident in shared memory (KB * 16 KB) and a pipeline stage
@@ -369,6 +377,195 @@ __device__ __forceinline__ void epi_chunk_pool(const uint32_t (&raw)[32], unsign
 }
 
 // ---------------------------------------------------------------------------------
+// finalize: one CTA per query.  Fold the (slice) lists into the best KP by bf16 score, re-rank
+// them exactly, certify against max(KP-th best candidate score, final gthr[q]), emit.
+// ---------------------------------------------------------------------------------
+constexpr int FU_MAX_POOL = 4096;     // pool entries staged in shared memory by the data-parallel selection
+constexpr int FU_MAX_SEL = 512;       // survivors of the score cut that are ranked by counting
+
+// bitonic sort of one key per lane, best (largest v) first
+__device__ __forceinline__ KeyS warp_sort_desc(KeyS x, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j >= 1; j >>= 1) {
+            const KeyS o = KeyS::shfl_xor(x, j);
+            const bool lower = (lane & j) == 0;               // this lane keeps the better of the pair ...
+            const bool desc = (lane & k) == 0 || k == 32;     // ... in a best-first sub-sequence
+            const bool take_better = lower == desc;
+            const bool o_better = KeyS::better(o, x);
+            if (o_better == take_better) x = o;
+        }
+    }
+    return x;
+}
+// keys of a best-first sorted run of 32 that rank before x (keys are distinct; worst() pads sort last)
+__device__ __forceinline__ int run_count_better(const KeyS *run, const KeyS &x) {
+    int lo = 0;                                               // invariant: run[0 .. lo) are better than x
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1)
+        if (KeyS::better(run[lo + step - 1], x)) lo += step;
+    if (lo == 31 && KeyS::better(run[31], x)) lo = 32;
+    return lo;
+}
+
+// One query, FIN_THREADS threads (C says which, and how they synchronise), `smem_raw` = finalize_union_smem() bytes.
+template <int EPL, class C>
+__device__ __forceinline__ void finalize_union_query(const FinalizeParams &fin, const UnionParams &u, int qi,
+                                                     unsigned char *smem_raw) {
+    constexpr int KP = 32 * EPL;
+    KeyS *stage = reinterpret_cast<KeyS *>(smem_raw);                       // [FIN_WARPS*KP]
+    KeyD *sm_ex = reinterpret_cast<KeyD *>(stage + FIN_WARPS * KP);        // [KP]
+    KeyD *sm_misc = sm_ex + KP;                                            // [4]
+    float *sm_q = reinterpret_cast<float *>(sm_misc + 4);                  // [dp]
+    KeyS *pool = reinterpret_cast<KeyS *>(sm_q + fin.dp);                  // [FU_MAX_POOL]
+    KeyS *sel = pool + FU_MAX_POOL;                                        // [FU_MAX_SEL]
+    int *s_count = reinterpret_cast<int *>(sel + FU_MAX_SEL);              // [3] + s_nsel
+    int &s_nsel = s_count[3];
+    const int tid = C::tid();
+    const int lane = tid & 31, warp = tid >> 5;
+    // written by other CTAs (or an earlier kernel): L2 loads.  The first 512 pool slots are fetched before the
+    // cursor is known (every pool is at least that long), so cursor and entries cost one round trip, not two.
+    const KeyS *src = u.lists + (size_t)qi * u.list_stride;
+    const KeyS spec0 = KeyS::load_cg(src + tid), spec1 = KeyS::load_cg(src + tid + FIN_THREADS);
+    const unsigned cnt_raw = __ldcg(u.cnt + qi);
+    const bool overflow = (cnt_raw >> 31) != 0u;          // pool mode: a private region filled up, rows were dropped
+    const int entries = overflow ? 0 : min((int)(cnt_raw & 0x7fffffffu), u.max_entries);   // an overflowed pool has holes
+    const unsigned g = __ldcg(u.gthr + qi);
+
+    for (int i = tid; i < fin.dp; i += FIN_THREADS) sm_q[i] = fin.q[(size_t)qi * fin.dp + i];
+    if (tid == 0) { s_nsel = 0; s_count[0] = s_count[1] = s_count[2] = 0; }
+    int nvalid = -1;                                       // -1: the data-parallel selection did not apply
+
+    if (entries <= FU_MAX_POOL) {
+        // ---- data-parallel selection: stage the pool, cut at the KP-th best score, rank the survivors ----
+        const KeyS e0 = tid < entries ? spec0 : KeyS::worst(), e1 = tid + FIN_THREADS < entries ? spec1 : KeyS::worst();
+        if (entries > FU_MAX_SEL) {
+            pool[tid] = e0; pool[tid + FIN_THREADS] = e1;
+            for (int i = tid + 2 * FIN_THREADS; i < entries; i += FIN_THREADS) pool[i] = KeyS::load_cg(src + i);
+        }
+        for (int i = tid; i < KP; i += FIN_THREADS) stage[i] = KeyS::worst();
+        if (entries <= FU_MAX_SEL) {
+            // ---- small pool (the usual case): warp-sorted runs of 32 + binary-search ranks ----
+            // thread t holds pool entries t and t + 256; every warp sorts its 32 (best first) into run w / 8 + w;
+            // an entry's rank = its position in its own run + the better entries of every other run.
+            const int n_runs = (entries + 31) / 32;
+            KeyS *runs = sel;                                  // [16][32]
+            KeyS a = warp_sort_desc(e0, lane);
+            runs[warp * 32 + lane] = a;
+            KeyS b = KeyS::worst();
+            if (entries > FIN_THREADS) { b = warp_sort_desc(e1, lane); runs[(FIN_WARPS + warp) * 32 + lane] = b; }
+            C::sync();
+            int ra = lane, rb = lane;
+            for (int r = 0; r < n_runs; ++r) {
+                const KeyS *run = runs + r * 32;
+                if (r != warp) ra += run_count_better(run, a);
+                if (r != FIN_WARPS + warp) rb += run_count_better(run, b);
+            }
+            if (a.valid() && ra < KP) stage[ra] = a;
+            if (b.valid() && rb < KP) stage[rb] = b;
+            C::sync();
+            nvalid = min(entries, KP);
+        } else {
+        C::sync();
+        unsigned t = 0;                                    // keep entries whose score key is >= t
+        {
+#pragma unroll 1
+            for (int bit = 31, it = 0; bit >= 10; --bit, ++it) {   // 22 bits of the ordered score: a lower bound of the KP-th best
+                const unsigned cand = t | (1u << bit);
+                int c = 0;
+                for (int i = tid; i < entries; i += FIN_THREADS) c += (unsigned)(pool[i].v >> 32) >= cand ? 1 : 0;
+                c = __reduce_add_sync(FULL_MASK, c);
+                if (lane == 0 && c) atomicAdd(&s_count[it % 3], c);
+                if (tid == 0) s_count[(it + 1) % 3] = 0;    // last read two rounds ago: one barrier per round
+                C::sync();
+                if (s_count[it % 3] >= KP) t = cand;
+            }
+        }
+        const KeyS *ranked = pool;
+        int nsel = entries;
+        {
+            for (int i0 = warp * 32; i0 < entries; i0 += FIN_THREADS) {      // warp-aggregated compaction
+                const int i = i0 + lane;
+                const KeyS k = i < entries ? pool[i] : KeyS::worst();
+                const bool keep = i < entries && (unsigned)(k.v >> 32) >= t;
+                const unsigned m = __ballot_sync(FULL_MASK, keep);
+                int base = 0;
+                if (lane == 0 && m) base = atomicAdd(&s_nsel, __popc(m));
+                base = __shfl_sync(FULL_MASK, base, 0);
+                const int slot = base + __popc(m & ((1u << lane) - 1));
+                if (keep && slot < FU_MAX_SEL) sel[slot] = k;
+            }
+            C::sync();
+            nsel = s_nsel;
+            ranked = sel;
+        }
+        if (nsel <= FU_MAX_SEL) {
+            for (int i = tid; i < nsel; i += FIN_THREADS) {
+                const KeyS me = ranked[i];
+                int rank = 0;
+#pragma unroll 8
+                for (int j = 0; j < nsel; ++j) rank += KeyS::better(ranked[j], me) ? 1 : 0;   // broadcast LDS.64, 8 in flight
+                if (rank < KP) stage[rank] = me;
+            }
+            C::sync();
+            nvalid = min(nsel, KP);
+        }
+        }
+    }
+    if (nvalid < 0) {
+        // ---- general path (very large pools or massive score ties): warp-resident sorted lists ----
+        WarpList<KeyS, EPL> wl; wl.init();
+        constexpr int UN = 4;                             // loads in flight per lane before the first use
+        for (int b = warp * 32; b < entries; b += FIN_WARPS * 32 * UN) {
+            KeyS mine[UN];
+#pragma unroll
+            for (int u2 = 0; u2 < UN; ++u2) {
+                const int idx = b + u2 * FIN_WARPS * 32 + lane;
+                mine[u2] = idx < entries ? KeyS::load_cg(src + idx) : KeyS::worst();
+            }
+#pragma unroll
+            for (int u2 = 0; u2 < UN; ++u2) {
+                unsigned hits = __ballot_sync(FULL_MASK, mine[u2].valid() && wl.accepts(mine[u2]));
+                while (hits) {
+                    const int sl = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    wl.offer(KeyS::shfl(mine[u2], sl), lane);
+                }
+            }
+        }
+        C::sync();
+        cta_tree_merge<KeyS, EPL, C>(wl, stage, warp, lane);
+        nvalid = 0;
+        for (int i0 = 0; i0 < KP; i0 += 32) nvalid += __popc(__ballot_sync(FULL_MASK, stage[i0 + lane].valid()));
+    }
+    if (tid == 0) { atomicAdd(u.pool_stats, 1ull); atomicAdd(u.pool_stats + 1, (unsigned long long)entries); }
+    // rows outside the candidate set: either in the pool but below the KP-th candidate, or never kept
+    // by any list, hence <= the final shared bound (0 = nothing was ever rejected)
+    float T = -INFINITY;
+    if (nvalid == KP) T = stage[KP - 1].score();
+    if (g != 0u) T = fmaxf(T, KeyS::unord(g));
+    if (overflow) T = INFINITY;                             // nothing bounds the dropped rows: force the exact fix-up
+    finalize_candidates<C>(fin, qi, stage, nvalid, T, sm_ex, sm_q, sm_misc);
+}
+
+// the finalize as its own launch (pool mode's sampling flow, or K3 without the fused tail): one CTA per query
+template <int EPL>
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_union_kernel(const FinalizeParams fin, const UnionParams u, int q0) {
+    extern __shared__ __align__(16) unsigned char fu_smem[];
+    pdl_wait();
+    pdl_trigger();
+    finalize_union_query<EPL, FinCta<0>>(fin, u, q0 + blockIdx.x, fu_smem);
+}
+
+inline size_t finalize_union_smem(int EPL, int dp) {
+    const int KP = 32 * EPL;
+    return sizeof(KeyS) * (size_t)FIN_WARPS * KP + sizeof(KeyD) * (KP + 4) + sizeof(float) * dp +
+           sizeof(KeyS) * (size_t)(FU_MAX_POOL + FU_MAX_SEL) + 16;
+}
+
+// ---------------------------------------------------------------------------------
 // in-kernel threshold seeding
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
@@ -573,21 +770,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 // 1. the first S tiles of the slice in sampling mode: the list collects the best step maxima
                 for (int i = 0; i < S; ++i, ++it) run_tile(t0 + i, it, std::true_type());
                 // 2. post them, count this CTA in
-                // values posted per thread: its 4 best when the block's slices then still post >= 4 L between them (the
-                // L-th best of that union is as good a bound), else all it has (S * NC step maxima at most)
-                const int pv = p.n_slices * GEMM_HALVES >= LL ? 4 : min(LL, (S * NC + 3) & ~3);
+                // values posted per thread: its 2 (4) best when the block's slices then still post >= 4 L (2 L) between
+                // them -- the L-th best of that union is as good a bound -- else all it has (S * NC step maxima at most)
+                const int pv = p.n_slices >= LL ? 2 : p.n_slices * GEMM_HALVES >= LL ? 4 : min(LL, (S * NC + 3) & ~3);
                 if (publish) {
                     unsigned *dst = p.samples + ((size_t)(q - p.qblock0 * GEMM_BM) * (p.n_slices * GEMM_HALVES) +
                                                  (size_t)(slice * GEMM_HALVES + half)) * pv;
 #pragma unroll
-                    for (int i = 0; i < LL; i += 4) {
+                    for (int i = 0; i < LL; i += 2) {
                         if (i >= pv) break;
-                        uint4 o;
+                        uint2 o;
                         o.x = list.r[i] != 0xffffffffu ? KeyS::ord(list.s[i]) : 0u;
                         o.y = list.r[i + 1] != 0xffffffffu ? KeyS::ord(list.s[i + 1]) : 0u;
-                        o.z = list.r[i + 2] != 0xffffffffu ? KeyS::ord(list.s[i + 2]) : 0u;
-                        o.w = list.r[i + 3] != 0xffffffffu ? KeyS::ord(list.s[i + 3]) : 0u;
-                        *reinterpret_cast<uint4 *>(dst + i) = o;
+                        *reinterpret_cast<uint2 *>(dst + i) = o;
                     }
                     __threadfence();
                 }
@@ -611,21 +806,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     if (!posted) break;
                     const unsigned v = warp_lth_largest<LL>(p.samples + (size_t)(qs - p.qblock0 * GEMM_BM) * per_q, per_q, lane);
                     if (lane == 0) {
-                        if (v != 0u) atomicMax(p.gthr + qs, v);
+                        if (v != 0u) atomicMax(p.gthr + qs, v);       // the finalize reads the bound from gthr[q]
                         __threadfence();
-                        atomicExch(p.seeded + qs, 1u);
+                        atomicExch(p.seeded + qs, v != 0u ? v : 1u);  // flag and seed in one word (1 = no seed: too few rows pass)
                     }
                 }
                 // 4. wait for this thread's own query: even with one live lane per warp an unseeded tile costs more
                 //    than the wait (measured: batch 1 144 vs 149 us, batch 16 151 vs 172 us per call)
                 if (publish) {
-                    while (ld_acquire_gpu(p.seeded + q) == 0u) {
+                    unsigned sd;
+                    while ((sd = ld_acquire_gpu(p.seeded + q)) == 0u) {
                         if (globaltimer_ns() - t_start > GEMM_SEED_TIMEOUT_NS) break;
-                        __nanosleep(64);
+                        __nanosleep(32);
                     }
+                    if (sd > 1u) g_next = sd;
                 }
                 __syncwarp();
-                g_next = *reinterpret_cast<volatile unsigned *>(gq);
             }
         }
         for (int t = t0; t < t1; ++t, ++it) run_tile(t, it, std::integral_constant<bool, SAMPLE>());
@@ -700,135 +896,6 @@ __global__ void __launch_bounds__(256) sample_threshold_kernel(const KeyS *__res
         if (s_count[it % 3] >= L) t = cand;
     }
     if (threadIdx.x == 0 && t != 0u) atomicMax(&gthr[qi], t);
-}
-
-// ---------------------------------------------------------------------------------
-// finalize: one CTA per query.  Fold the (slice) lists into the best KP by bf16 score, re-rank
-// them exactly, certify against max(KP-th best candidate score, final gthr[q]), emit.
-// ---------------------------------------------------------------------------------
-constexpr int FU_MAX_POOL = 4096;     // pool entries staged in shared memory by the data-parallel selection
-constexpr int FU_MAX_SEL = 512;       // survivors of the score cut that are ranked by counting
-
-template <int EPL>
-__global__ void __launch_bounds__(FIN_THREADS)
-finalize_union_kernel(const FinalizeParams fin, const KeyS *__restrict__ lists, int list_stride, int max_entries,
-                      unsigned *__restrict__ gthr, unsigned *__restrict__ cnt, unsigned *__restrict__ arrive,
-                      unsigned *__restrict__ seeded, unsigned long long *pool_stats, int q0) {
-    constexpr int KP = 32 * EPL;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    KeyS *stage = reinterpret_cast<KeyS *>(smem_raw);                       // [FIN_WARPS*KP]
-    KeyD *sm_ex = reinterpret_cast<KeyD *>(stage + FIN_WARPS * KP);        // [KP]
-    KeyD *sm_misc = sm_ex + KP;                                            // [4]
-    float *sm_q = reinterpret_cast<float *>(sm_misc + 4);                  // [dp]
-    KeyS *pool = reinterpret_cast<KeyS *>(sm_q + fin.dp);                  // [FU_MAX_POOL]
-    KeyS *sel = pool + FU_MAX_POOL;                                        // [FU_MAX_SEL]
-    __shared__ int s_count[3], s_nsel;
-    const int qi = q0 + blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    pdl_wait();
-    pdl_trigger();
-    const unsigned cnt_raw = cnt[qi];
-    const bool overflow = (cnt_raw >> 31) != 0u;          // pool mode: a private region filled up, rows were dropped
-    const int entries = overflow ? 0 : min((int)(cnt_raw & 0x7fffffffu), max_entries);   // an overflowed pool has holes
-    const unsigned g = gthr[qi];
-    const KeyS *src = lists + (size_t)qi * list_stride;
-
-    for (int i = threadIdx.x; i < fin.dp; i += FIN_THREADS) sm_q[i] = fin.q[(size_t)qi * fin.dp + i];
-    if (threadIdx.x == 0) { s_nsel = 0; s_count[0] = s_count[1] = s_count[2] = 0; }
-    int nvalid = -1;                                       // -1: the data-parallel selection did not apply
-
-    if (entries <= FU_MAX_POOL) {
-        // ---- data-parallel selection: stage the pool, cut at the KP-th best score, rank the survivors ----
-        for (int i = threadIdx.x; i < entries; i += FIN_THREADS) pool[i] = src[i];
-        for (int i = threadIdx.x; i < KP; i += FIN_THREADS) stage[i] = KeyS::worst();
-        __syncthreads();
-        unsigned t = 0;                                    // keep entries whose score key is >= t
-        if (entries > FU_MAX_SEL) {                        // small pools are ranked whole
-#pragma unroll 1
-            for (int bit = 31, it = 0; bit >= 10; --bit, ++it) {   // 22 bits of the ordered score: a lower bound of the KP-th best
-                const unsigned cand = t | (1u << bit);
-                int c = 0;
-                for (int i = threadIdx.x; i < entries; i += FIN_THREADS) c += (unsigned)(pool[i].v >> 32) >= cand ? 1 : 0;
-                c = __reduce_add_sync(FULL_MASK, c);
-                if (lane == 0 && c) atomicAdd(&s_count[it % 3], c);
-                if (threadIdx.x == 0) s_count[(it + 1) % 3] = 0;    // last read two rounds ago: one barrier per round
-                __syncthreads();
-                if (s_count[it % 3] >= KP) t = cand;
-            }
-        }
-        const KeyS *ranked = pool;                         // small pools are ranked in place
-        int nsel = entries;
-        if (entries > FU_MAX_SEL) {
-            for (int i0 = warp * 32; i0 < entries; i0 += FIN_THREADS) {      // warp-aggregated compaction
-                const int i = i0 + lane;
-                const KeyS k = i < entries ? pool[i] : KeyS::worst();
-                const bool keep = i < entries && (unsigned)(k.v >> 32) >= t;
-                const unsigned m = __ballot_sync(FULL_MASK, keep);
-                int base = 0;
-                if (lane == 0 && m) base = atomicAdd(&s_nsel, __popc(m));
-                base = __shfl_sync(FULL_MASK, base, 0);
-                const int slot = base + __popc(m & ((1u << lane) - 1));
-                if (keep && slot < FU_MAX_SEL) sel[slot] = k;
-            }
-            __syncthreads();
-            nsel = s_nsel;
-            ranked = sel;
-        }
-        if (nsel <= FU_MAX_SEL) {
-            for (int i = threadIdx.x; i < nsel; i += FIN_THREADS) {
-                const KeyS me = ranked[i];
-                int rank = 0;
-#pragma unroll 8
-                for (int j = 0; j < nsel; ++j) rank += KeyS::better(ranked[j], me) ? 1 : 0;   // broadcast LDS.64, 8 in flight
-                if (rank < KP) stage[rank] = me;
-            }
-            __syncthreads();
-            nvalid = min(nsel, KP);
-        }
-    }
-    if (nvalid < 0) {
-        // ---- general path (very large pools or massive score ties): warp-resident sorted lists ----
-        WarpList<KeyS, EPL> wl; wl.init();
-        constexpr int UN = 4;                             // loads in flight per lane before the first use
-        for (int b = warp * 32; b < entries; b += FIN_WARPS * 32 * UN) {
-            KeyS mine[UN];
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                const int idx = b + u * FIN_WARPS * 32 + lane;
-                mine[u] = idx < entries ? src[idx] : KeyS::worst();
-            }
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                unsigned hits = __ballot_sync(FULL_MASK, mine[u].valid() && wl.accepts(mine[u]));
-                while (hits) {
-                    const int sl = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    wl.offer(KeyS::shfl(mine[u], sl), lane);
-                }
-            }
-        }
-        __syncthreads();
-        cta_tree_merge<KeyS, EPL>(wl, stage, warp, lane);
-        nvalid = __syncthreads_count(threadIdx.x < KP && stage[threadIdx.x < KP ? threadIdx.x : 0].valid());
-    }
-    if (threadIdx.x == 0) {
-        gthr[qi] = 0u; cnt[qi] = 0u; seeded[qi] = 0u;       // leave the shared state clean for the next call
-        if (qi % GEMM_BM == 0) arrive[qi / GEMM_BM] = 0u;
-        atomicAdd(pool_stats, 1ull); atomicAdd(pool_stats + 1, (unsigned long long)entries);
-    }
-    // rows outside the candidate set: either in the pool but below the KP-th candidate, or never kept
-    // by any list, hence <= the final shared bound (0 = nothing was ever rejected)
-    float T = -INFINITY;
-    if (nvalid == KP) T = stage[KP - 1].score();
-    if (g != 0u) T = fmaxf(T, KeyS::unord(g));
-    if (overflow) T = INFINITY;                             // nothing bounds the dropped rows: force the exact fix-up
-    finalize_candidates(fin, qi, stage, nvalid, T, sm_ex, sm_q, sm_misc);
-}
-
-inline size_t finalize_union_smem(int EPL, int dp) {
-    const int KP = 32 * EPL;
-    return sizeof(KeyS) * (size_t)FIN_WARPS * KP + sizeof(KeyD) * (KP + 4) + sizeof(float) * dp +
-           sizeof(KeyS) * (size_t)(FU_MAX_POOL + FU_MAX_SEL);
 }
 
 }  // namespace b2r

@@ -155,9 +155,7 @@ cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entr
     return launch_pdl(sample_threshold_kernel<0>, dim3(nq), dim3(256), smem, s, lists, list_stride, entries_per_query, L, gthr, cnt, q0);
 }
 
-cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS *lists, int list_stride,
-                                  int entries_per_query, unsigned *gthr, unsigned *cnt, unsigned *arrive, unsigned *seeded,
-                                  unsigned long long *pool_stats, int q0, int nq, cudaStream_t s) {
+cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const UnionParams &u, int q0, int nq, cudaStream_t s) {
     const size_t smem = finalize_union_smem(epl, fin.dp);
     if (smem > 48 * 1024) {      // opt in to large dynamic shared memory (per function; cheap, idempotent)
         cudaError_t e = cudaSuccess;
@@ -168,10 +166,10 @@ cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const KeyS
         if (e != cudaSuccess) return e;
     }
     switch (epl) {
-        case 1: return launch_pdl(finalize_union_kernel<1>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, arrive, seeded, pool_stats, q0);
-        case 2: return launch_pdl(finalize_union_kernel<2>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, arrive, seeded, pool_stats, q0);
-        case 4: return launch_pdl(finalize_union_kernel<4>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, arrive, seeded, pool_stats, q0);
-        case 8: return launch_pdl(finalize_union_kernel<8>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, lists, list_stride, entries_per_query, gthr, cnt, arrive, seeded, pool_stats, q0);
+        case 1: return launch_pdl(finalize_union_kernel<1>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, u, q0);
+        case 2: return launch_pdl(finalize_union_kernel<2>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, u, q0);
+        case 4: return launch_pdl(finalize_union_kernel<4>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, u, q0);
+        case 8: return launch_pdl(finalize_union_kernel<8>, dim3(nq), dim3(FIN_THREADS), smem, s, fin, u, q0);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -20,6 +20,11 @@ struct IngestParams {
     const uint8_t *type_in;    // [n] device or nullptr (= 0)
     float *max_norm2;          // device [2] or nullptr: [0] max |x|^2 of the stored rows, [1] max |x - bf16(x)|^2
     float *qerr;               // [n] or nullptr (query batches for K3): |q - bf16(q)|, rounded up
+    double *q_eps;             // query preparation: [n][2] = { error bound eps of the scan scores, |q|^2 } (finalize.cuh) ...
+    const float *norms;        // ... from the stored rows' max |x|^2, max |x - bf16(x)|^2 ...
+    float eps_rel;             // ... and the scoring kernel's accumulation slop; qerr == nullptr: queries are not rounded
+    unsigned *zero;            // query preparation: K3's per-call shared state (bounds, cursors, flags, counters) ...
+    int zero_words;            // ... is cleared here, after the previous query's kernels have finished with it
 };
 
 // 1/(sqrt(s)+1e-30) exactly as hnswlib's normalize_vector does it in fp32
@@ -41,6 +46,7 @@ __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(const IngestPara
     const int d = p.d, dp = p.dp, chunks = dp / 8;
     pdl_wait();          // query preparation overwrites buffers the previous query's kernels may still read
     pdl_trigger();
+    for (int i = blockIdx.x * INGEST_THREADS + threadIdx.x; i < p.zero_words; i += gridDim.x * INGEST_THREADS) p.zero[i] = 0u;
     for (long long r = gw; r < p.n; r += nw) {
         const float *xr = p.x + r * d;
         float inv = 1.0f;
@@ -101,6 +107,14 @@ __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(const IngestPara
         s2 = warp_sum(s2);
         e2 = warp_sum(e2);
         if (lane == 0) {
+            if (p.q_eps) {
+                // |scan - exact| <= |q~-q| (max|x| + max|x~-x|) + |q| max|x~-x| + accumulation slop (see finalize.cuh)
+                const double dq = p.qerr ? (double)__double2float_ru(sqrt(e2) * (1.0 + 1e-6)) : 0.0;
+                const double xn = sqrt((double)p.norms[0]), dxn = sqrt((double)p.norms[1]), qn = sqrt(s2);
+                p.q_eps[2 * r] = dq * (xn + dxn) + qn * dxn + (double)p.eps_rel * (qn + dq) * (xn + dxn) +
+                                 1e-6 * (0.5 * xn * xn + qn * xn) + 1e-30;
+                p.q_eps[2 * r + 1] = s2;
+            }
             if (p.qerr) p.qerr[r] = __double2float_ru(sqrt(e2) * (1.0 + 1e-6));
             if (p.bias) p.bias[r] = __double2float_rn(-0.5 * s2);
             if (p.type_out) p.type_out[r] = p.type_in ? p.type_in[r] : (uint8_t)0;
