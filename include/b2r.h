@@ -123,6 +123,17 @@ int b2r_get_rows_f32(b2r_handle h, const int64_t *rows, int64_t n, float *out, v
 int64_t b2r_count(b2r_handle h);
 int b2r_get_stats(b2r_handle h, b2r_stats *out);
 
+/* Persistence of the vector half of a collection -- what chromadb's persist_directory keeps in its HNSW segment
+ * files (app/utils/embedder.py:164-170: ChromaSettings(persist_directory=settings.CHROMA_PERSIST_DIR); the committed
+ * chroma_db/<segment>/{data_level0,header,length,link_lists}.bin).  b2r_save writes the shard exactly as it sits in
+ * HBM (packed bf16 rows, fp32 master, l2 bias, type codes / tombstones, the measured rounding norms) to one file;
+ * b2r_load rebuilds a handle from it without re-normalising or re-packing, so a loaded shard answers bit-identically.
+ * The host keeps ids / documents / metadata next to it (multimodal_rag_b200/collection.py).
+ * File: 128-byte header ("B2RS", version, dim, dim_padded, space, flags, rows, live, row_base, norms, payload checksum)
+ * followed by the arrays in the order above.                                                                   */
+int b2r_save(b2r_handle h, const char *path, void *stream);
+int b2r_load(const char *path, int device, int64_t capacity_rows, b2r_handle *out);
+
 /* Row-sharded corpus (one process per GPU): rows reported by b2r_query are
  * row_base + local row, so every shard can answer in global row numbers.            */
 int b2r_set_row_base(b2r_handle h, int64_t row_base);

@@ -20,7 +20,7 @@ ABI_SYMBOLS = (
     "b2r_abi_version", "b2r_last_error", "b2r_create", "b2r_destroy", "b2r_clear", "b2r_reserve",
     "b2r_ingest_f32", "b2r_tombstone", "b2r_query", "b2r_query_ex", "b2r_get_rows_f32", "b2r_count",
     "b2r_get_stats", "b2r_set_row_base", "b2r_merge_shards", "b2r_merge_shards_packed", "b2r_set_path", "b2r_launch_count",
-    "b2r_set_kernel_timing", "b2r_kernel_time_ms",
+    "b2r_set_kernel_timing", "b2r_kernel_time_ms", "b2r_save", "b2r_load",
 )
 
 
@@ -71,6 +71,8 @@ def load() -> ctypes.CDLL:
         "b2r_launch_count": (i64, [vp]),
         "b2r_set_kernel_timing": (i32, [vp, i32]),
         "b2r_kernel_time_ms": (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]),
+        "b2r_save": (i32, [vp, ctypes.c_char_p, vp]),
+        "b2r_load": (i32, [ctypes.c_char_p, i32, i64, ctypes.POINTER(vp)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -15,7 +15,9 @@ library or without a B200 raises.
 from __future__ import annotations
 
 import ctypes
+import json
 import logging
+import os
 import threading
 
 import numpy as np
@@ -341,6 +343,57 @@ class B200Collection:
                     res["embeddings"].append(self._fetch_rows(rr).tolist() if rr else [])
             return res
 
+    # ---- persistence (the reference persists through ChromaSettings(persist_directory=...), embedder.py:164-170) ----
+    _FORMAT = 1
+
+    def save(self, directory: str) -> None:
+        """Write the collection under `directory`: `<name>.b2r` = the device shard exactly as it sits in HBM
+        (b2r_save), `<name>.tables.json` = ids / documents / metadata / tombstones kept on the host."""
+        with self._lock:
+            os.makedirs(directory, exist_ok=True)
+            base = os.path.join(directory, self.name)
+            if self._h is not None:
+                _lib.check(self._lib.b2r_save(self._h, (base + ".b2r").encode(), 0), "b2r_save")
+            tables = {"format": self._FORMAT, "name": self.name, "metadata": self.metadata, "space": self.space,
+                      "dimension": self._dim, "keep_f32_master": not (self._flags & _lib.FLAG_NO_F32_MASTER),
+                      "ids": self._ids, "documents": self._docs, "metadatas": self._meta.meta,
+                      "dead_rows": np.flatnonzero(~self._alive).tolist(),
+                      "type_codes": self._meta.type_codes, "type_overflow": self._meta.type_overflow}
+            tmp = base + ".tables.json.tmp"
+            with open(tmp, "w", encoding="utf-8") as f:
+                json.dump(tables, f)
+            os.replace(tmp, base + ".tables.json")
+
+    @classmethod
+    def load(cls, directory: str, name: str, *, device=0, capacity=0) -> "B200Collection":
+        """Rebuild a saved collection; the device shard is uploaded as stored (no re-normalisation), so queries
+        answer bit-identically to the collection that was saved."""
+        base = os.path.join(directory, name)
+        with open(base + ".tables.json", encoding="utf-8") as f:
+            t = json.load(f)
+        if t.get("format") != cls._FORMAT:
+            raise ValueError(f"{base}.tables.json: unknown format {t.get('format')!r}")
+        c = cls(t["name"], t["metadata"], device=device, capacity=capacity, keep_f32_master=t["keep_f32_master"])
+        if t["dimension"] is not None:
+            h = ctypes.c_void_p()
+            _lib.check(c._lib.b2r_load((base + ".b2r").encode(), int(device), int(capacity), ctypes.byref(h)), "b2r_load")
+            c._h, c._dim = h, int(t["dimension"])
+        c._ids, c._docs = list(t["ids"]), list(t["documents"])
+        c._meta.type_codes = {k: int(v) for k, v in t["type_codes"].items()}
+        c._meta.type_overflow = bool(t["type_overflow"])
+        for md in t["metadatas"]:
+            c._meta.append(md)
+        c._alive = np.ones(len(c._ids), dtype=bool)
+        c._alive[np.asarray(t["dead_rows"], dtype=np.int64)] = False
+        c._row_of = {id_: r for r, id_ in enumerate(c._ids) if c._alive[r]}
+        if c._h is not None:
+            st = c.stats()
+            if st["rows"] != len(c._ids) or st["live"] != len(c._row_of) or st["dim"] != c._dim:
+                c.close()
+                raise ValueError(f"{base}: shard file and host tables disagree "
+                                 f"(rows {st['rows']} vs {len(c._ids)}, live {st['live']} vs {len(c._row_of)})")
+        return c
+
     def stats(self) -> dict:
         with self._lock:
             if self._h is None:
@@ -359,13 +412,29 @@ class B200Collection:
 class B200Client:
     """The ``chromadb.Client`` trio the reference uses (app/utils/embedder.py:170-183, 669-678)."""
 
-    def __init__(self, device=0, keep_f32_master=True, default_capacity=0):
+    def __init__(self, device=0, keep_f32_master=True, default_capacity=0, path=None):
+        """`path` = the persist directory (the reference's ChromaSettings(persist_directory=...), embedder.py:164-168):
+        collections saved there are loaded now, `persist()` writes them back."""
         self.device = device
         self.keep_f32_master = keep_f32_master
         self.default_capacity = default_capacity
+        self.path = path
         self._collections: dict[str, B200Collection] = {}
         self._lock = threading.Lock()
         _lib.load()    # fail now, loudly, if the CUDA library is absent
+        if path and os.path.isdir(path):
+            for fn in sorted(os.listdir(path)):
+                if fn.endswith(".tables.json"):
+                    name = fn[: -len(".tables.json")]
+                    self._collections[name] = B200Collection.load(path, name, device=device, capacity=default_capacity)
+
+    def persist(self) -> None:
+        """Write every collection to the persist directory (chromadb's client.persist())."""
+        if not self.path:
+            raise ValueError("this client was created without a persist directory")
+        with self._lock:
+            for c in self._collections.values():
+                c.save(self.path)
 
     def create_collection(self, name, metadata=None, get_or_create=False, **kw):
         with self._lock:
@@ -393,6 +462,12 @@ class B200Client:
             if name not in self._collections:
                 raise ValueError(f"Collection {name} does not exist.")
             self._collections.pop(name).close()
+            if self.path:
+                for ext in (".b2r", ".tables.json"):
+                    try:
+                        os.remove(os.path.join(self.path, name + ext))
+                    except FileNotFoundError:
+                        pass
 
     def list_collections(self):
         with self._lock:

@@ -2,6 +2,7 @@
 // staging and kernel dispatch.  No compute happens on the host.
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -157,10 +158,11 @@ extern "C" int b2r_destroy(b2r_handle h) {
     cudaFree(h->corpus); cudaFree(h->master); cudaFree(h->bias); cudaFree(h->type_code);
     cudaFree(h->max_norm2); cudaFree(h->counters); cudaFree(h->tickets); cudaFree(h->need_ctl);
     DevBuf *bufs[] = {&h->x_stage, &h->t_stage, &h->q_raw, &h->q_prep, &h->allow, &h->rows_stage, &h->gather_out,
-                      &h->o_rows, &h->o_dist, &h->o_dist64, &h->o_count, &h->need_list, &h->scan_lists,
+                      &h->o_pack, &h->need_list, &h->scan_lists,
                       &h->exact_lists, &h->q_bf16, &h->q_err, &h->pass_bits, &h->gthr, &h->gemm_lists, &h->gemm_regions,
                       &h->gemm_samples, &h->q_eps};
     for (DevBuf *b : bufs) release(*b);
+    if (h->o_host) cudaFreeHost(h->o_host);
     for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete h;
@@ -283,7 +285,8 @@ extern "C" int b2r_ingest_f32(b2r_handle h, const float *x, int64_t n, const uin
     p.bias = h->bias ? h->bias + h->rows : nullptr;
     p.type_out = h->type_code + h->rows;
     p.type_in = td;
-    p.max_norm2 = h->max_norm2; p.qerr = nullptr; p.zero = nullptr; p.zero_words = 0; p.q_eps = nullptr; p.norms = nullptr; p.eps_rel = 0.f;
+    p.max_norm2 = h->max_norm2; p.qerr = nullptr; p.q_eps = nullptr; p.norms = nullptr; p.eps_rel = 0.f;
+    for (int z = 0; z < 3; ++z) { p.zero[z] = nullptr; p.zero_words[z] = 0; }
     const int wpb = INGEST_THREADS / 32;
     int grid = (int)std::min<int64_t>((n + wpb - 1) / wpb, (int64_t)h->sm_count * 16);
     const bool vec = (h->dim % 8 == 0) && (((uintptr_t)xd & 15) == 0);
@@ -346,6 +349,129 @@ extern "C" int b2r_get_rows_f32(b2r_handle h, const int64_t *rows, int64_t n, fl
     h->n_launches++;
     if (!dev_out) B2R_CUDA(cudaMemcpyAsync(out, od, (size_t)n * h->dim * 4, cudaMemcpyDeviceToHost, s));
     B2R_CUDA(cudaStreamSynchronize(s));
+    return B2R_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// persistence: the shard as it sits in HBM <-> one file
+// ---------------------------------------------------------------------------------
+namespace {
+struct ShardHeader {               // 128 bytes, little endian
+    char magic[4];                 // "B2RS"
+    uint32_t version;              // 1
+    int32_t dim, dp, space;
+    uint32_t flags;
+    int64_t rows, live, row_base;
+    float max_norm2[2];
+    uint64_t checksum;             // sum of the payload as little-endian u64 words (tail bytes zero-extended) + byte count
+    uint64_t payload_bytes;
+    unsigned char reserved[56];
+};
+static_assert(sizeof(ShardHeader) == 128, "header layout");
+constexpr size_t IO_CHUNK = 64u << 20;
+
+uint64_t sum_words(const unsigned char *p, size_t n) {
+    uint64_t s = 0;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; std::memcpy(&w, p + i, 8); s += w; }
+    if (i < n) { uint64_t w = 0; std::memcpy(&w, p + i, n - i); s += w; }
+    return s;
+}
+struct PinnedBuf {
+    void *p = nullptr;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+struct FileCloser {
+    FILE *f = nullptr;
+    ~FileCloser() { if (f) fclose(f); }
+};
+}  // namespace
+
+extern "C" int b2r_save(b2r_handle h, const char *path, void *stream) {
+    B2R_REQUIRE(h && path, "b2r_save: NULL argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    B2R_CUDA(cudaStreamSynchronize(s));
+    ShardHeader hd;
+    std::memset(&hd, 0, sizeof(hd));
+    std::memcpy(hd.magic, "B2RS", 4);
+    hd.version = 1; hd.dim = h->dim; hd.dp = h->dp; hd.space = h->space; hd.flags = h->flags;
+    hd.rows = h->rows; hd.live = h->live; hd.row_base = h->row_base;
+    B2R_CUDA(cudaMemcpy(hd.max_norm2, h->max_norm2, 8, cudaMemcpyDeviceToHost));
+    const std::string tmp = std::string(path) + ".tmp";
+    FileCloser fc;
+    fc.f = fopen(tmp.c_str(), "wb");
+    if (!fc.f) { set_error(std::string("b2r_save: cannot open ") + tmp); return B2R_EINVAL; }
+    if (fwrite(&hd, sizeof(hd), 1, fc.f) != 1) { set_error("b2r_save: write failed"); return B2R_EINVAL; }
+    PinnedBuf pb;
+    B2R_CUDA(cudaHostAlloc(&pb.p, IO_CHUNK, cudaHostAllocDefault));
+    const struct { const void *ptr; size_t bytes; } sect[4] = {
+        {h->corpus, (size_t)h->rows * h->dp * 2},
+        {h->master, h->master ? (size_t)h->rows * h->dp * 4 : 0},
+        {h->bias, h->bias ? (size_t)h->rows * 4 : 0},
+        {h->type_code, (size_t)h->rows}};
+    uint64_t sum = 0, total = 0;
+    for (const auto &sc : sect) {
+        for (size_t off = 0; off < sc.bytes; off += IO_CHUNK) {
+            const size_t n = std::min(IO_CHUNK, sc.bytes - off);
+            B2R_CUDA(cudaMemcpyAsync(pb.p, (const char *)sc.ptr + off, n, cudaMemcpyDeviceToHost, s));
+            B2R_CUDA(cudaStreamSynchronize(s));
+            sum += sum_words((const unsigned char *)pb.p, n);      // chunks are multiples of 8 except a section's last
+            if (fwrite(pb.p, 1, n, fc.f) != n) { set_error("b2r_save: write failed (disk full?)"); return B2R_EINVAL; }
+            total += n;
+        }
+    }
+    hd.checksum = sum + total; hd.payload_bytes = total;
+    if (fseek(fc.f, 0, SEEK_SET) != 0 || fwrite(&hd, sizeof(hd), 1, fc.f) != 1 || fflush(fc.f) != 0) {
+        set_error("b2r_save: write failed"); return B2R_EINVAL;
+    }
+    fclose(fc.f); fc.f = nullptr;
+    if (rename(tmp.c_str(), path) != 0) { set_error(std::string("b2r_save: cannot rename to ") + path); return B2R_EINVAL; }
+    return B2R_OK;
+}
+
+extern "C" int b2r_load(const char *path, int device, int64_t capacity_rows, b2r_handle *out) {
+    B2R_REQUIRE(path && out, "b2r_load: NULL argument");
+    *out = nullptr;
+    FileCloser fc;
+    fc.f = fopen(path, "rb");
+    if (!fc.f) { set_error(std::string("b2r_load: cannot open ") + path); return B2R_EINVAL; }
+    ShardHeader hd;
+    if (fread(&hd, sizeof(hd), 1, fc.f) != 1 || std::memcmp(hd.magic, "B2RS", 4) != 0) {
+        set_error(std::string("b2r_load: ") + path + " is not a b2r shard file"); return B2R_EINVAL;
+    }
+    B2R_REQUIRE(hd.version == 1, "b2r_load: unknown shard file version");
+    B2R_REQUIRE(hd.dim >= 1 && hd.dim <= 8192 && hd.dp == round_up(hd.dim, 64) && hd.space >= 0 && hd.space <= 2 &&
+                    hd.rows >= 0 && hd.live >= 0 && hd.live <= hd.rows, "b2r_load: corrupt header");
+    const bool has_master = !(hd.flags & B2R_FLAG_NO_F32_MASTER), has_bias = hd.space == B2R_SPACE_L2;
+    const size_t sect_bytes[4] = {(size_t)hd.rows * hd.dp * 2, has_master ? (size_t)hd.rows * hd.dp * 4 : 0,
+                                  has_bias ? (size_t)hd.rows * 4 : 0, (size_t)hd.rows};
+    B2R_REQUIRE(hd.payload_bytes == sect_bytes[0] + sect_bytes[1] + sect_bytes[2] + sect_bytes[3],
+                "b2r_load: payload size does not match the header");
+    b2r_handle h = nullptr;
+    int rc = b2r_create(hd.dim, hd.space, std::max<int64_t>(capacity_rows, hd.rows), device, hd.flags, &h);
+    if (rc != B2R_OK) return rc;
+    PinnedBuf pb;
+    cudaError_t ce = cudaHostAlloc(&pb.p, IO_CHUNK, cudaHostAllocDefault);
+    if (ce != cudaSuccess) { b2r_destroy(h); set_error("b2r_load: cudaHostAlloc failed"); return B2R_ENOMEM; }
+    void *dst[4] = {h->corpus, h->master, h->bias, h->type_code};
+    uint64_t sum = 0, total = 0;
+    for (int i = 0; i < 4; ++i) {
+        for (size_t off = 0; off < sect_bytes[i]; off += IO_CHUNK) {
+            const size_t n = std::min(IO_CHUNK, sect_bytes[i] - off);
+            if (fread(pb.p, 1, n, fc.f) != n) { b2r_destroy(h); set_error("b2r_load: file is truncated"); return B2R_EINVAL; }
+            sum += sum_words((const unsigned char *)pb.p, n);
+            ce = cudaMemcpy((char *)dst[i] + off, pb.p, n, cudaMemcpyHostToDevice);
+            if (ce != cudaSuccess) { b2r_destroy(h); set_error(std::string("b2r_load: ") + cudaGetErrorString(ce)); return B2R_ECUDA; }
+            total += n;
+        }
+    }
+    if (sum + total != hd.checksum) { b2r_destroy(h); set_error("b2r_load: checksum mismatch (file is corrupt)"); return B2R_EINVAL; }
+    ce = cudaMemcpy(h->max_norm2, hd.max_norm2, 8, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { b2r_destroy(h); set_error(std::string("b2r_load: ") + cudaGetErrorString(ce)); return B2R_ECUDA; }
+    h->rows = hd.rows; h->live = hd.live; h->row_base = hd.row_base; h->mut_gen++;
+    *out = h;
     return B2R_OK;
 }
 
@@ -556,15 +682,20 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     if ((rc = ensure(h->need_list, (size_t)nq * 4)) != B2R_OK) return rc;
     if ((rc = ensure(h->q_eps, (size_t)nq * 16)) != B2R_OK) return rc;
     long long *o_rows = (long long *)out_rows; float *o_dist = out_dist; double *o_dist64 = out_dist64; int *o_count = out_count;
+    // host outputs: one packed device buffer [rows | dist64 | dist | count] -> ONE device-to-host copy into a pinned
+    // mirror -> the caller's arrays (three or four small copies would each pay the PCIe round trip)
+    const size_t off_d64 = (size_t)nq * k * 8, off_d = off_d64 + (out_dist64 ? (size_t)nq * k * 8 : 0),
+                 off_c = off_d + (size_t)nq * k * 4, pack_bytes = off_c + (size_t)nq * 4;
     if (!dev_out) {
-        if ((rc = ensure(h->o_rows, (size_t)nq * k * 8)) != B2R_OK) return rc;
-        if ((rc = ensure(h->o_dist, (size_t)nq * k * 4)) != B2R_OK) return rc;
-        if ((rc = ensure(h->o_count, (size_t)nq * 4)) != B2R_OK) return rc;
-        o_rows = (long long *)h->o_rows.p; o_dist = (float *)h->o_dist.p; o_count = (int *)h->o_count.p;
-        if (out_dist64) {
-            if ((rc = ensure(h->o_dist64, (size_t)nq * k * 8)) != B2R_OK) return rc;
-            o_dist64 = (double *)h->o_dist64.p;
+        if ((rc = ensure(h->o_pack, pack_bytes)) != B2R_OK) return rc;
+        if (h->o_host_bytes < pack_bytes) {
+            if (h->o_host) { cudaFreeHost(h->o_host); h->o_host = nullptr; h->o_host_bytes = 0; }
+            B2R_CUDA(cudaHostAlloc(&h->o_host, std::max(pack_bytes, (size_t)4096), cudaHostAllocDefault));
+            h->o_host_bytes = std::max(pack_bytes, (size_t)4096);
         }
+        char *b = (char *)h->o_pack.p;
+        o_rows = (long long *)b; o_dist = (float *)(b + off_d); o_count = (int *)(b + off_c);
+        if (out_dist64) o_dist64 = (double *)(b + off_d64);
     }
 
     // ---- choose the scoring path ----
@@ -597,12 +728,15 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
         // (dp+8) * 2^-24 for K2's FFMA chain, 4x that for the tensor core's accumulator.
         p.q_eps = (double *)h->q_eps.p; p.norms = h->max_norm2;
         p.eps_rel = (float)(h->dp + 8) * 5.9604645e-8f * (path == 2 ? 4.f : 1.f) * 1.01f;
-        p.zero = nullptr; p.zero_words = 0;
-        if (path == 2) {   // K3's per-call shared state: [bounds | cursors | seed flags][q-blocks * 128], [arrivals][q-blocks]
+        // per-call shared state, cleared by the preparation: the fix-up work list control, K5's slot generations, ...
+        p.zero[0] = (unsigned *)h->need_ctl; p.zero_words[0] = 2;
+        p.zero[1] = h->tickets + 1 + EXACT_MAX_BATCH; p.zero_words[1] = EXACT_MAX_BATCH;
+        p.zero[2] = nullptr; p.zero_words[2] = 0;
+        if (path == 2) {   // ... and K3's [bounds | cursors | seed flags][q-blocks * 128], [arrivals][q-blocks]
             const int qblocks = (nq + GEMM_BM - 1) / GEMM_BM;
-            p.zero_words = qblocks * (GEMM_BM * 3 + 1);
-            if ((rc = ensure(h->gthr, (size_t)p.zero_words * 4)) != B2R_OK) return rc;
-            p.zero = (unsigned *)h->gthr.p;
+            p.zero_words[2] = qblocks * (GEMM_BM * 3 + 1);
+            if ((rc = ensure(h->gthr, (size_t)p.zero_words[2] * 4)) != B2R_OK) return rc;
+            p.zero[2] = (unsigned *)h->gthr.p;
         }
         const int wpb = INGEST_THREADS / 32;
         int grid = std::min((nq + wpb - 1) / wpb, h->sm_count * 8);
@@ -638,11 +772,13 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     h->n_queries += nq;
 
     if (!dev_out) {
-        B2R_CUDA(cudaMemcpyAsync(out_rows, o_rows, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
-        B2R_CUDA(cudaMemcpyAsync(out_dist, o_dist, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
-        B2R_CUDA(cudaMemcpyAsync(out_count, o_count, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
-        if (out_dist64) B2R_CUDA(cudaMemcpyAsync(out_dist64, o_dist64, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
+        B2R_CUDA(cudaMemcpyAsync(h->o_host, h->o_pack.p, pack_bytes, cudaMemcpyDeviceToHost, s));
         B2R_CUDA(cudaStreamSynchronize(s));
+        const char *b = (const char *)h->o_host;
+        std::memcpy(out_rows, b, (size_t)nq * k * 8);
+        if (out_dist64) std::memcpy(out_dist64, b + off_d64, (size_t)nq * k * 8);
+        std::memcpy(out_dist, b + off_d, (size_t)nq * k * 4);
+        std::memcpy(out_count, b + off_c, (size_t)nq * 4);
     } else if (q_raw != q || (f.allow_bits && allow_dev != f.allow_bits)) {
         B2R_CUDA(cudaStreamSynchronize(s));   // host inputs were staged through reusable buffers
     }

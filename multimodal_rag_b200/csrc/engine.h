@@ -94,7 +94,8 @@ struct b2r_index {
 
     // scratch (device), grown on demand
     b2r::DevBuf x_stage, t_stage, q_raw, q_prep, allow, rows_stage, gather_out;
-    b2r::DevBuf o_rows, o_dist, o_dist64, o_count, need_list;
+    b2r::DevBuf o_pack, need_list;  // packed outputs of a query with host result arrays
+    void *o_host = nullptr; size_t o_host_bytes = 0;   // pinned mirror of o_pack
     int *need_ctl = nullptr;        // [4]: failed-certificate count, exit ticket (reset by K5 itself)
     b2r::DevBuf scan_lists, exact_lists;
     b2r::DevBuf q_bf16, q_err, pass_bits, gthr, gemm_lists, gemm_regions, gemm_samples;   // K3 scratch

@@ -98,15 +98,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
         }
         __syncthreads();
     }
-    // ---- leave the control block clean for the next call (last CTA out) ----
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd((unsigned *)&p.fin.need_ctl[1], 1u) == gridDim.x - 1) {
-            for (int i = 0; i < EXACT_MAX_BATCH; ++i) slot_gen[i] = 0u;
-            p.fin.need_ctl[0] = 0;
-            p.fin.need_ctl[1] = 0;
-        }
-    }
+    // the work list control and the slot generations are cleared by the next call's query preparation
 }
 
 inline size_t exact_smem_bytes(int EPL, int dp) {

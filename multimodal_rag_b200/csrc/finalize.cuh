@@ -35,7 +35,7 @@ struct FinalizeParams {
     float *out_dist;            // [nq, k]
     double *out_dist64;         // [nq, k] or nullptr
     int *out_count;             // [nq]
-    int *need_ctl;              // [0] = number of queries whose certificate failed (this call), [1] = exit ticket
+    int *need_ctl;              // [0] = number of queries whose certificate failed (this call; the query preparation clears it)
     int *need_list;             // [nq]: those queries, in arrival order; the exact scan (K5) redoes them
 };
 

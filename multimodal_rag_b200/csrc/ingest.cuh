@@ -23,8 +23,9 @@ struct IngestParams {
     double *q_eps;             // query preparation: [n][2] = { error bound eps of the scan scores, |q|^2 } (finalize.cuh) ...
     const float *norms;        // ... from the stored rows' max |x|^2, max |x - bf16(x)|^2 ...
     float eps_rel;             // ... and the scoring kernel's accumulation slop; qerr == nullptr: queries are not rounded
-    unsigned *zero;            // query preparation: K3's per-call shared state (bounds, cursors, flags, counters) ...
-    int zero_words;            // ... is cleared here, after the previous query's kernels have finished with it
+    unsigned *zero[3];         // query preparation: per-call shared state (K3's bounds, cursors, flags, counters; the
+    int zero_words[3];         // fix-up work list control; K5's slot generations) is cleared here, after the previous
+                               // query's kernels have finished with it
 };
 
 // 1/(sqrt(s)+1e-30) exactly as hnswlib's normalize_vector does it in fp32
@@ -46,7 +47,9 @@ __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(const IngestPara
     const int d = p.d, dp = p.dp, chunks = dp / 8;
     pdl_wait();          // query preparation overwrites buffers the previous query's kernels may still read
     pdl_trigger();
-    for (int i = blockIdx.x * INGEST_THREADS + threadIdx.x; i < p.zero_words; i += gridDim.x * INGEST_THREADS) p.zero[i] = 0u;
+#pragma unroll
+    for (int z = 0; z < 3; ++z)
+        for (int i = blockIdx.x * INGEST_THREADS + threadIdx.x; i < p.zero_words[z]; i += gridDim.x * INGEST_THREADS) p.zero[z][i] = 0u;
     for (long long r = gw; r < p.n; r += nw) {
         const float *xr = p.x + r * d;
         float inv = 1.0f;

@@ -39,7 +39,7 @@ _EMPTY = {"ids": [], "distances": [], "metadatas": [], "documents": []}
 class B200EmbeddingManager:
     def __init__(self, encoder: Callable[[List[str]], Any], collection_name: str = "multimodal_rag", *,
                  space: Optional[str] = None, device: int = 0, max_retries: int = 3, client: Optional[B200Client] = None,
-                 model_name: str = "injected-encoder", capacity: int = 0):
+                 model_name: str = "injected-encoder", capacity: int = 0, persist_directory: Optional[str] = None):
         self.encoder = encoder
         self.collection_name = collection_name
         self.space = space                       # None = Chroma's default (l2), as the reference's create_collection
@@ -47,6 +47,7 @@ class B200EmbeddingManager:
         self.max_retries = max_retries
         self.model_name = model_name
         self.capacity = capacity
+        self.persist_directory = persist_directory     # settings.CHROMA_PERSIST_DIR in the reference (embedder.py:164-168)
         self.client = client
         self.collection = None
         self.is_initialized = False
@@ -63,12 +64,16 @@ class B200EmbeddingManager:
         if self.is_initialized:
             return
         if self.client is None:
-            self.client = B200Client(device=self.device, default_capacity=self.capacity)
+            self.client = B200Client(device=self.device, default_capacity=self.capacity, path=self.persist_directory)
         try:
             self.collection = await asyncio.to_thread(self.client.get_collection, self.collection_name)
         except ValueError:
             self.collection = await asyncio.to_thread(self.client.create_collection, self.collection_name, self._metadata())
         self.is_initialized = True
+
+    async def persist(self):
+        """Write the collection to the persist directory (Chroma persists on its own; here it is an explicit call)."""
+        await asyncio.to_thread(self.client.persist)
 
     async def _embed(self, texts: List[str]):
         emb = await asyncio.to_thread(self.encoder, texts)

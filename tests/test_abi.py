@@ -71,3 +71,20 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in src.replace("the oracle's tie-break key", ""), f"{fn} mentions the oracle"
+
+
+def test_load_rejects_non_shard_files_without_a_gpu(tmp_path):
+    """b2r_load validates the file before it touches the device: a missing file or a foreign file is EINVAL
+    (-> ValueError upstream), whatever the machine."""
+    import ctypes
+    from multimodal_rag_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.b2r_load(str(tmp_path / "nope.b2r").encode(), 0, 0, ctypes.byref(h)) == _lib.B2R_EINVAL
+    assert b"cannot open" in lib.b2r_last_error()
+    bad = tmp_path / "bad.b2r"
+    bad.write_bytes(b"SQLite format 3\x00" + bytes(200))
+    assert lib.b2r_load(str(bad).encode(), 0, 0, ctypes.byref(h)) == _lib.B2R_EINVAL
+    assert b"not a b2r shard file" in lib.b2r_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(lib.b2r_load(str(bad).encode(), 0, 0, ctypes.byref(h)))
