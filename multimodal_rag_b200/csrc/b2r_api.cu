@@ -133,6 +133,7 @@ extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device,
     if (const char *e = getenv("B2R_NO_SEED")) h->no_seed = atoi(e) != 0;      // development: K3 without in-kernel seeding
     h->seed_min_batch = GEMM_SEED_MIN_BATCH;
     if (const char *e = getenv("B2R_SEED_MIN_BATCH")) h->seed_min_batch = atoi(e);
+    if (const char *e = getenv("B2R_SEED_TILES")) h->seed_tiles_override = atoi(e);   // development: seeding tiles per CTA
     int rc = B2R_OK;
     do {
         if (cudaMalloc(&h->max_norm2, 256) != cudaSuccess || cudaMalloc(&h->counters, 256) != cudaSuccess ||
@@ -628,6 +629,7 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
             const int tiles_per_cta = tiles_total / gp.n_slices;
             const int want = std::max((128 + gp.n_slices - 1) / gp.n_slices, std::min(tiles_per_cta / 64, 8));
             gp.seed_tiles = (!pool_mode && !h->no_seed && nq >= h->seed_min_batch && tiles_per_cta >= 8 * want) ? want : 0;
+            if (gp.seed_tiles && h->seed_tiles_override > 0) gp.seed_tiles = std::min(h->seed_tiles_override, tiles_per_cta / 2);
         }
         un.max_entries = pool_mode ? GEMM_POOL_CAP : gp.n_slices * GEMM_HALVES * L;
         KernelTimer kt(h, s);

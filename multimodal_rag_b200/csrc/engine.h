@@ -113,7 +113,7 @@ struct b2r_index {
     // kernel launches on the caller's stream, resolved lazily by b2r_kernel_time_ms
     bool timing = false;
     bool no_seed = false;
-    int seed_min_batch = 0;
+    int seed_min_batch = 0, seed_tiles_override = 0;
     int timing_stage = 0;           // which launch the events bracket: 0 scoring (default); B2R_TIME_STAGE=1..5 (development):
                                     // 1 prepare, 2 sampling pass, 3 sample reducer, 4 finalize, 5 exact fix-up
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
