@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B2R_ABI_VERSION 1
+#define B2R_ABI_VERSION 2
 
 typedef struct b2r_index *b2r_handle;
 
@@ -53,10 +53,34 @@ typedef enum { B2R_SPACE_L2 = 0, B2R_SPACE_COSINE = 1, B2R_SPACE_IP = 2 } b2r_sp
 /* Row filter (Chroma `where`, embedder.py:543,599).  The host evaluates the clause on
  * its metadata tables and hands the device either a type-code mask (fast path for
  * {"type": ...}) or a general allow bitmap.  Tombstoned rows never match.             */
+#define B2R_MAX_COLUMNS 16      /* dictionary-encoded metadata columns kept on the device */
+#define B2R_WHERE_MAX_NODES 32  /* nodes of one compiled where clause                      */
+
+/* A compiled `where` clause, evaluated on the device against dictionary-encoded metadata columns
+ * (b2r_column_set): the clause tree in postfix order.  A leaf tests one column: the row's code c
+ * (-1 = key absent -> false) passes iff bit c of the leaf's look-up table is set; the host builds
+ * that table by applying the comparison ($eq/$ne/$gt/$gte/$lt/$lte/$in/$nin) to the column's
+ * DISTINCT values, so the device never compares strings or numbers.  AND / OR pop two, push one. */
+typedef enum { B2R_WHERE_LEAF = 0, B2R_WHERE_AND = 1, B2R_WHERE_OR = 2 } b2r_where_op;
+typedef struct {
+    int32_t op;                 /* b2r_where_op                                          */
+    int32_t column;             /* leaf: device column 0..B2R_MAX_COLUMNS-1              */
+    uint32_t lut_offset;        /* leaf: first word of its table in `lut`                */
+    uint32_t lut_values;        /* leaf: codes 0..lut_values-1 are covered by the table  */
+} b2r_where_node;
+typedef struct {
+    int32_t n_nodes;            /* 1..B2R_WHERE_MAX_NODES, postfix                        */
+    b2r_where_node nodes[B2R_WHERE_MAX_NODES];
+    const uint32_t *lut;        /* all leaf tables, host or device                        */
+    int64_t lut_words;
+} b2r_where;
+
 typedef struct {
     uint64_t type_mask;         /* bit c set = rows with type_code c pass; ~0 = all    */
     const uint32_t *allow_bits; /* NULL, or ceil(rows/32) words, host or device:
                                    bit (r&31) of word r>>5 set = row r passes          */
+    const b2r_where *where;     /* NULL, or a compiled clause (host struct); a row must
+                                   pass the type mask AND allow_bits AND the clause      */
 } b2r_filter;
 
 typedef struct {
@@ -95,6 +119,17 @@ int b2r_reserve(b2r_handle h, int64_t capacity_rows);
  * later call on the same stream.  *first_row_out = row number given to x[0].        */
 int b2r_ingest_f32(b2r_handle h, const float *x, int64_t n, const uint8_t *type_code,
                    int64_t *first_row_out, void *stream);
+
+/* Metadata column `column` for rows [first_row, first_row + n): codes[i] = index of the row's value in the
+ * host's dictionary of that key's distinct values, -1 = the row has no such key.  Rows never set read as -1.
+ * This is the device half of Chroma's metadata segment for `where` (collection.query(where=...),
+ * app/utils/embedder.py:599; collection.get(where={"doc_id": ...}), :632): the host keeps the dictionaries,
+ * the device keeps one int32 per row per key and evaluates compiled clauses (b2r_where) in a bitmap kernel.  */
+int b2r_column_set(b2r_handle h, int column, int64_t first_row, int64_t n, const int32_t *codes, void *stream);
+/* Evaluate a filter exactly as b2r_query would and return the pass bitmap (ceil(rows/32) words, host or device):
+ * live rows that pass the type mask, the allow bitmap and the clause.  Used by get(where=...) / delete(where=...)
+ * and by the parity tests of the clause kernel.                                                              */
+int b2r_filter_eval(b2r_handle h, const b2r_filter *filter, uint32_t *out_bits, void *stream);
 
 /* replaces the vector half of collection.delete (app/utils/embedder.py:639-642) and the
  * overwrite half of upsert: rows (host array) stop matching any query.               */

@@ -20,12 +20,26 @@ ABI_SYMBOLS = (
     "b2r_abi_version", "b2r_last_error", "b2r_create", "b2r_destroy", "b2r_clear", "b2r_reserve",
     "b2r_ingest_f32", "b2r_tombstone", "b2r_query", "b2r_query_ex", "b2r_get_rows_f32", "b2r_count",
     "b2r_get_stats", "b2r_set_row_base", "b2r_merge_shards", "b2r_merge_shards_packed", "b2r_set_path", "b2r_launch_count",
-    "b2r_set_kernel_timing", "b2r_kernel_time_ms", "b2r_save", "b2r_load",
+    "b2r_set_kernel_timing", "b2r_kernel_time_ms", "b2r_save", "b2r_load", "b2r_column_set", "b2r_filter_eval",
 )
 
 
+MAX_COLUMNS, WHERE_MAX_NODES = 16, 32
+WHERE_LEAF, WHERE_AND, WHERE_OR = 0, 1, 2
+
+
+class B2RWhereNode(ctypes.Structure):
+    _fields_ = [("op", ctypes.c_int32), ("column", ctypes.c_int32), ("lut_offset", ctypes.c_uint32),
+                ("lut_values", ctypes.c_uint32)]
+
+
+class B2RWhere(ctypes.Structure):
+    _fields_ = [("n_nodes", ctypes.c_int32), ("nodes", B2RWhereNode * WHERE_MAX_NODES), ("lut", ctypes.c_void_p),
+                ("lut_words", ctypes.c_int64)]
+
+
 class B2RFilter(ctypes.Structure):
-    _fields_ = [("type_mask", ctypes.c_uint64), ("allow_bits", ctypes.c_void_p)]
+    _fields_ = [("type_mask", ctypes.c_uint64), ("allow_bits", ctypes.c_void_p), ("where", ctypes.POINTER(B2RWhere))]
 
 
 class B2RStats(ctypes.Structure):
@@ -73,6 +87,8 @@ def load() -> ctypes.CDLL:
         "b2r_kernel_time_ms": (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]),
         "b2r_save": (i32, [vp, ctypes.c_char_p, vp]),
         "b2r_load": (i32, [ctypes.c_char_p, i32, i64, ctypes.POINTER(vp)]),
+        "b2r_column_set": (i32, [vp, i32, i64, i64, vp, vp]),
+        "b2r_filter_eval": (i32, [vp, ctypes.POINTER(B2RFilter), vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -91,6 +91,7 @@ class B200Collection:
         self._alive = np.zeros(0, dtype=bool)
         self._row_of: dict[str, int] = {}
         self._meta = MetaTable()
+        self.device_where = True      # general where clauses run on the device (False: host-evaluated bitmaps)
         if dimension is not None:
             self._open(int(dimension))
 
@@ -181,6 +182,17 @@ class B200Collection:
             self._docs.append(None if documents is None else documents[i])
             self._meta.append(metas[j])
         self._alive = np.concatenate([self._alive, np.ones(len(sel), dtype=bool)])
+        self._push_columns(first.value, len(sel), {k for md in metas if md for k in md})
+
+    def _push_columns(self, first: int, n: int, keys):
+        """Mirror the dictionary codes of rows [first, first + n) of the touched metadata keys to the device
+        columns (b2r_column_set); keys beyond the 16 device columns stay host-only."""
+        for key in keys:
+            ci = self._meta.device_column(key)
+            if ci is None:
+                continue
+            codes = np.ascontiguousarray(self._meta.cols[key].codes[first: first + n], dtype=np.int32)
+            _lib.check(self._lib.b2r_column_set(self._h, ci, first, n, codes.ctypes.data, 0), "b2r_column_set")
 
     def _kill_rows(self, rows):
         if not rows:
@@ -275,16 +287,35 @@ class B200Collection:
 
     def _filter(self, where):
         """where -> (B2RFilter, keep-alive object).  None when nothing can match."""
-        f = _lib.B2RFilter(type_mask=(1 << 64) - 1, allow_bits=None)
+        f = _lib.B2RFilter(type_mask=(1 << 64) - 1, allow_bits=None, where=None)
         if not where:
             return f, None
         tm = self._meta.type_only_mask(where)
         if tm is not None:
             f.type_mask = tm
             return f, None
-        bits = pack_bits(self._meta.mask(where))
+        prog = self._meta.compile(where) if self.device_where else None
+        if prog is not None:                 # the clause runs on the device against the metadata columns
+            nodes, lut = prog
+            w = _lib.B2RWhere(n_nodes=len(nodes), lut=lut.ctypes.data if lut.size else None, lut_words=int(lut.size))
+            for i, (op, col, off, nv) in enumerate(nodes):
+                w.nodes[i] = _lib.B2RWhereNode(op, col, off, nv)
+            f.where = ctypes.pointer(w)
+            return f, (w, lut)
+        bits = pack_bits(self._meta.mask(where))      # clause the device cannot run: host-evaluated bitmap
         f.allow_bits = bits.ctypes.data
         return f, bits
+
+    def filter_bits(self, where=None) -> np.ndarray:
+        """The pass bitmap the device derives for `where` (bool per row: live AND matching) -- b2r_filter_eval."""
+        with self._lock:
+            n = len(self._ids)
+            words = np.zeros((n + 31) // 32, dtype=np.uint32)
+            if self._h is not None and n:
+                f, keep = self._filter(where)
+                _lib.check(self._lib.b2r_filter_eval(self._h, ctypes.byref(f), words.ctypes.data, 0), "b2r_filter_eval")
+                del keep
+            return np.unpackbits(words.view(np.uint8), bitorder="little")[:n].astype(bool)
 
     def query_rows(self, query_embeddings, n_results=10, where=None, want_dist64=False):
         """Device query returning numpy arrays: rows [nq,k] int64 (-1 pad), dist [nq,k] fp32,
@@ -387,6 +418,7 @@ class B200Collection:
         c._alive[np.asarray(t["dead_rows"], dtype=np.int64)] = False
         c._row_of = {id_: r for r, id_ in enumerate(c._ids) if c._alive[r]}
         if c._h is not None:
+            c._push_columns(0, len(c._ids), list(c._meta.cols))
             st = c.stats()
             if st["rows"] != len(c._ids) or st["live"] != len(c._row_of) or st["dim"] != c._dim:
                 c.close()

@@ -91,8 +91,21 @@ int grow(b2r_index *h, int64_t cap, cudaStream_t s) {
         if (bias) B2R_CUDA(cudaMemcpyAsync(bias, h->bias, (size_t)h->rows * 4, cudaMemcpyDeviceToDevice, s));
         B2R_CUDA(cudaMemcpyAsync(tc, h->type_code, (size_t)h->rows, cudaMemcpyDeviceToDevice, s));
     }
+    int32_t *cols[B2R_MAX_COLUMNS] = {};
+    for (int c = 0; c < B2R_MAX_COLUMNS; ++c) {
+        if (!h->cols[c]) continue;
+        cudaError_t e = cudaMalloc(&cols[c], (size_t)cap * 4);
+        if (e != cudaSuccess) {
+            for (int j = 0; j < c; ++j) cudaFree(cols[j]);
+            cudaFree(corpus); cudaFree(master); cudaFree(bias); cudaFree(tc);
+            B2R_CUDA(e);
+        }
+        cudaMemsetAsync(cols[c], 0xff, (size_t)cap * 4, s);
+        if (h->rows > 0) cudaMemcpyAsync(cols[c], h->cols[c], (size_t)h->rows * 4, cudaMemcpyDeviceToDevice, s);
+    }
     B2R_CUDA(cudaStreamSynchronize(s));
     cudaFree(h->corpus); cudaFree(h->master); cudaFree(h->bias); cudaFree(h->type_code);
+    for (int c = 0; c < B2R_MAX_COLUMNS; ++c) { cudaFree(h->cols[c]); h->cols[c] = cols[c]; }
     h->corpus = corpus; h->master = master; h->bias = bias; h->type_code = tc;
     h->capacity = cap;
     return B2R_OK;
@@ -158,10 +171,11 @@ extern "C" int b2r_destroy(b2r_handle h) {
     cudaDeviceSynchronize();
     cudaFree(h->corpus); cudaFree(h->master); cudaFree(h->bias); cudaFree(h->type_code);
     cudaFree(h->max_norm2); cudaFree(h->counters); cudaFree(h->tickets); cudaFree(h->need_ctl);
+    for (int c = 0; c < B2R_MAX_COLUMNS; ++c) cudaFree(h->cols[c]);
     DevBuf *bufs[] = {&h->x_stage, &h->t_stage, &h->q_raw, &h->q_prep, &h->allow, &h->rows_stage, &h->gather_out,
                       &h->o_pack, &h->need_list, &h->scan_lists,
                       &h->exact_lists, &h->q_bf16, &h->q_err, &h->pass_bits, &h->gthr, &h->gemm_lists, &h->gemm_regions,
-                      &h->gemm_samples, &h->q_eps};
+                      &h->gemm_samples, &h->q_eps, &h->where_lut, &h->where_bits, &h->col_stage};
     for (DevBuf *b : bufs) release(*b);
     if (h->o_host) cudaFreeHost(h->o_host);
     for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -177,6 +191,8 @@ extern "C" int b2r_clear(b2r_handle h) {
     B2R_CUDA(cudaDeviceSynchronize());
     h->rows = 0; h->live = 0; h->mut_gen++;
     B2R_CUDA(cudaMemset(h->max_norm2, 0, 8));
+    for (int c = 0; c < B2R_MAX_COLUMNS; ++c)
+        if (h->cols[c]) B2R_CUDA(cudaMemset(h->cols[c], 0xff, (size_t)h->capacity * 4));
     return B2R_OK;
 }
 
@@ -349,6 +365,159 @@ extern "C" int b2r_get_rows_f32(b2r_handle h, const int64_t *rows, int64_t n, fl
     B2R_CUDA(cudaGetLastError());
     h->n_launches++;
     if (!dev_out) B2R_CUDA(cudaMemcpyAsync(out, od, (size_t)n * h->dim * 4, cudaMemcpyDeviceToHost, s));
+    B2R_CUDA(cudaStreamSynchronize(s));
+    return B2R_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// metadata columns and compiled where clauses
+// ---------------------------------------------------------------------------------
+extern "C" int b2r_column_set(b2r_handle h, int column, int64_t first_row, int64_t n, const int32_t *codes, void *stream) {
+    B2R_REQUIRE(h, "b2r_column_set: NULL handle");
+    B2R_REQUIRE(column >= 0 && column < B2R_MAX_COLUMNS, "b2r_column_set: column must be 0..15");
+    B2R_REQUIRE(n >= 0 && first_row >= 0 && (n == 0 || codes), "b2r_column_set: bad arguments");
+    std::lock_guard<std::mutex> g(h->mu);
+    B2R_REQUIRE(first_row + n <= h->rows, "b2r_column_set: rows must have been ingested first");
+    if (n == 0) return B2R_OK;
+    B2R_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h->cols[column]) {
+        B2R_CUDA(cudaMalloc(&h->cols[column], (size_t)h->capacity * 4));
+        B2R_CUDA(cudaMemsetAsync(h->cols[column], 0xff, (size_t)h->capacity * 4, s));
+    }
+    const bool dev = is_device_ptr(codes);
+    B2R_CUDA(cudaMemcpyAsync(h->cols[column] + first_row, codes, (size_t)n * 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    if (!dev) B2R_CUDA(cudaStreamSynchronize(s));      // the caller's host array may go away
+    h->mut_gen++;
+    return B2R_OK;
+}
+
+namespace {
+struct WhereProg {
+    int n_nodes;
+    b2r_where_node node[B2R_WHERE_MAX_NODES];
+    const int32_t *cols[B2R_MAX_COLUMNS];     // nullptr: no row carries this key
+};
+
+// One thread per row, one output word per warp.  The clause is a postfix program over look-up-table leaves, the
+// same for every row, so control flow is uniform; the operand stack is a bit field in one register.
+__global__ void __launch_bounds__(256)
+where_bits_kernel(const WhereProg prog, const uint32_t *__restrict__ lut, const uint32_t *__restrict__ allow_in,
+                  unsigned n, unsigned n_words, uint32_t *__restrict__ out) {
+    const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned nthreads = gridDim.x * blockDim.x;
+    for (unsigned long long r = gt; r < (unsigned long long)n_words * 32; r += nthreads) {
+        bool ok = r < n;
+        if (ok) {
+            unsigned stack = 0;
+            int sp = 0;
+            for (int i = 0; i < prog.n_nodes; ++i) {
+                const b2r_where_node nd = prog.node[i];
+                if (nd.op == B2R_WHERE_LEAF) {
+                    unsigned bit = 0;
+                    const int32_t *col = prog.cols[nd.column];
+                    if (col) {
+                        const int code = col[r];
+                        if (code >= 0 && (unsigned)code < nd.lut_values) bit = (lut[nd.lut_offset + ((unsigned)code >> 5)] >> (code & 31)) & 1u;
+                    }
+                    stack |= bit << sp;
+                    ++sp;
+                } else {
+                    const unsigned a = (stack >> (sp - 1)) & 1u, b = (stack >> (sp - 2)) & 1u;
+                    const unsigned v = nd.op == B2R_WHERE_AND ? (a & b) : (a | b);
+                    sp -= 2;
+                    stack = (stack & ~(3u << sp)) | (v << sp);
+                    ++sp;
+                }
+            }
+            ok = (stack & 1u) != 0u;
+            if (allow_in) ok = ok && ((allow_in[r >> 5] >> (r & 31)) & 1u);
+        }
+        const unsigned w = __ballot_sync(FULL_MASK, ok);
+        if ((threadIdx.x & 31) == 0) out[r >> 5] = w;
+    }
+}
+
+// Validate `w`, stage its tables, and write the clause bitmap (ANDed with allow_dev when given) for the
+// first n_words * 32 rows into h->where_bits.
+int run_where(b2r_index *h, const b2r_where *w, const uint32_t *allow_dev, unsigned n_words, cudaStream_t s) {
+    B2R_REQUIRE(w->n_nodes >= 1 && w->n_nodes <= B2R_WHERE_MAX_NODES, "where: clause has too many nodes (max 32)");
+    B2R_REQUIRE(w->lut_words >= 0 && (w->lut_words == 0 || w->lut), "where: missing look-up tables");
+    WhereProg prog;
+    prog.n_nodes = w->n_nodes;
+    int depth = 0;
+    for (int i = 0; i < w->n_nodes; ++i) {
+        const b2r_where_node &nd = w->nodes[i];
+        prog.node[i] = nd;
+        if (nd.op == B2R_WHERE_LEAF) {
+            B2R_REQUIRE(nd.column >= 0 && nd.column < B2R_MAX_COLUMNS, "where: leaf column out of range");
+            B2R_REQUIRE((uint64_t)nd.lut_offset + (nd.lut_values + 31) / 32 <= (uint64_t)w->lut_words, "where: leaf table out of range");
+            ++depth;
+        } else {
+            B2R_REQUIRE(nd.op == B2R_WHERE_AND || nd.op == B2R_WHERE_OR, "where: unknown node");
+            B2R_REQUIRE(depth >= 2, "where: malformed postfix clause");
+            --depth;
+        }
+        B2R_REQUIRE(depth <= 32, "where: clause nests too deep");
+    }
+    B2R_REQUIRE(depth == 1, "where: malformed postfix clause");
+    for (int c = 0; c < B2R_MAX_COLUMNS; ++c) prog.cols[c] = h->cols[c];
+    int rc;
+    const uint32_t *lut_dev = w->lut;
+    if (w->lut_words > 0 && !is_device_ptr(w->lut)) {
+        if ((rc = ensure(h->where_lut, (size_t)w->lut_words * 4)) != B2R_OK) return rc;
+        B2R_CUDA(cudaMemcpyAsync(h->where_lut.p, w->lut, (size_t)w->lut_words * 4, cudaMemcpyHostToDevice, s));
+        lut_dev = (const uint32_t *)h->where_lut.p;
+    }
+    if ((rc = ensure(h->where_bits, (size_t)std::max(n_words, 1u) * 4)) != B2R_OK) return rc;
+    const unsigned blocks = std::max(1u, std::min((n_words * 32 + 255) / 256, (unsigned)h->sm_count * 8));
+    where_bits_kernel<<<blocks, 256, 0, s>>>(prog, lut_dev, allow_dev, (unsigned)h->rows, n_words, (uint32_t *)h->where_bits.p);
+    B2R_CUDA(cudaGetLastError());
+    h->n_launches++;
+    return B2R_OK;
+}
+
+// host allow bitmap -> h->allow (device)
+int stage_allow(b2r_index *h, const b2r_filter &f, const uint32_t **allow_dev, cudaStream_t s) {
+    *allow_dev = f.allow_bits;
+    if (f.allow_bits && !is_device_ptr(f.allow_bits)) {
+        const size_t words = (size_t)((h->rows + 31) / 32);
+        int rc = ensure(h->allow, std::max<size_t>(words, 1) * 4);
+        if (rc != B2R_OK) return rc;
+        B2R_CUDA(cudaMemcpyAsync(h->allow.p, f.allow_bits, words * 4, cudaMemcpyHostToDevice, s));
+        *allow_dev = (const uint32_t *)h->allow.p;
+    }
+    return B2R_OK;
+}
+}  // namespace
+
+extern "C" int b2r_filter_eval(b2r_handle h, const b2r_filter *filter, uint32_t *out_bits, void *stream) {
+    B2R_REQUIRE(h && out_bits, "b2r_filter_eval: NULL argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    b2r_filter f; f.type_mask = ~0ull; f.allow_bits = nullptr; f.where = nullptr;
+    if (filter) f = *filter;
+    f.type_mask &= ~(1ull << B2R_TYPE_DEAD);
+    const unsigned n_words = (unsigned)((h->rows + 31) / 32);
+    if (n_words == 0) return B2R_OK;
+    const uint32_t *allow_dev = nullptr;
+    int rc;
+    if ((rc = stage_allow(h, f, &allow_dev, s)) != B2R_OK) return rc;
+    if (f.where) {
+        if ((rc = run_where(h, f.where, allow_dev, n_words, s)) != B2R_OK) return rc;
+        allow_dev = (const uint32_t *)h->where_bits.p;
+    }
+    const bool dev_out = is_device_ptr(out_bits);
+    uint32_t *od = out_bits;
+    if (!dev_out) {
+        if ((rc = ensure(h->pass_bits, (size_t)n_words * 4 + 16)) != B2R_OK) return rc;
+        od = (uint32_t *)h->pass_bits.p;
+        h->pb_buf = nullptr;                     // the cached query bitmap lived here
+    }
+    B2R_CUDA(pass_bits_launch(h->type_code, f.type_mask, allow_dev, (unsigned)h->rows, n_words, od, h->sm_count, s));
+    h->n_launches++;
+    if (!dev_out) B2R_CUDA(cudaMemcpyAsync(out_bits, od, (size_t)n_words * 4, cudaMemcpyDeviceToHost, s));
     B2R_CUDA(cudaStreamSynchronize(s));
     return B2R_OK;
 }
@@ -661,7 +830,7 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     B2R_REQUIRE(dev_out == is_device_ptr(out_dist) && dev_out == is_device_ptr(out_count) &&
                     (!out_dist64 || dev_out == is_device_ptr(out_dist64)),
                 "b2r_query: outputs must all be host or all be device pointers");
-    b2r_filter f; f.type_mask = ~0ull; f.allow_bits = nullptr;
+    b2r_filter f; f.type_mask = ~0ull; f.allow_bits = nullptr; f.where = nullptr;
     if (filter) f = *filter;
     f.type_mask &= ~(1ull << B2R_TYPE_DEAD);
 
@@ -673,12 +842,12 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
         B2R_CUDA(cudaMemcpyAsync(h->q_raw.p, q, (size_t)nq * h->dim * 4, cudaMemcpyHostToDevice, s));
         q_raw = (const float *)h->q_raw.p;
     }
-    const uint32_t *allow_dev = f.allow_bits;
-    if (f.allow_bits && !is_device_ptr(f.allow_bits)) {
-        size_t words = (size_t)((h->rows + 31) / 32);
-        if ((rc = ensure(h->allow, std::max<size_t>(words, 1) * 4)) != B2R_OK) return rc;
-        B2R_CUDA(cudaMemcpyAsync(h->allow.p, f.allow_bits, words * 4, cudaMemcpyHostToDevice, s));
-        allow_dev = (const uint32_t *)h->allow.p;
+    const uint32_t *allow_dev = nullptr;
+    if ((rc = stage_allow(h, f, &allow_dev, s)) != B2R_OK) return rc;
+    const bool staged_host_filter = (f.allow_bits && allow_dev != f.allow_bits) || (f.where && f.where->lut_words > 0 && !is_device_ptr(f.where->lut));
+    if (f.where && h->rows > 0) {     // compiled clause -> device bitmap (ANDed with the allow bitmap), then it IS the allow bitmap
+        if ((rc = run_where(h, f.where, allow_dev, (unsigned)((h->rows + 31) / 32), s)) != B2R_OK) return rc;
+        allow_dev = (const uint32_t *)h->where_bits.p;
     }
     if ((rc = ensure(h->q_prep, (size_t)nq * h->dp * 4)) != B2R_OK) return rc;
     if ((rc = ensure(h->need_list, (size_t)nq * 4)) != B2R_OK) return rc;
@@ -781,7 +950,7 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
         if (out_dist64) std::memcpy(out_dist64, b + off_d64, (size_t)nq * k * 8);
         std::memcpy(out_dist, b + off_d, (size_t)nq * k * 4);
         std::memcpy(out_count, b + off_c, (size_t)nq * 4);
-    } else if (q_raw != q || (f.allow_bits && allow_dev != f.allow_bits)) {
+    } else if (q_raw != q || staged_host_filter) {
         B2R_CUDA(cudaStreamSynchronize(s));   // host inputs were staged through reusable buffers
     }
     return B2R_OK;

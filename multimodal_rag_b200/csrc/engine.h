@@ -91,6 +91,7 @@ struct b2r_index {
     uint8_t *type_code = nullptr;   // [capacity]
     float *max_norm2 = nullptr;     // [2]: max |x|^2, max |x - bf16(x)|^2 over the stored rows
     unsigned long long *counters = nullptr;   // [0] = rows killed by tombstone, [1] = exact fallbacks
+    int32_t *cols[B2R_MAX_COLUMNS] = {};      // dictionary-encoded metadata columns [capacity], -1 = key absent; allocated on first use
 
     // scratch (device), grown on demand
     b2r::DevBuf x_stage, t_stage, q_raw, q_prep, allow, rows_stage, gather_out;
@@ -99,6 +100,7 @@ struct b2r_index {
     int *need_ctl = nullptr;        // [4]: failed-certificate count, exit ticket (reset by K5 itself)
     b2r::DevBuf scan_lists, exact_lists;
     b2r::DevBuf q_bf16, q_err, pass_bits, gthr, gemm_lists, gemm_regions, gemm_samples;   // K3 scratch
+    b2r::DevBuf where_lut, where_bits, col_stage;   // compiled-clause tables, clause bitmap, column upload staging
     b2r::DevBuf q_eps;              // [nq][2] fp64: per-query error bound and |q|^2 (query preparation)
 
     // TMA tensor maps (K3), re-encoded when the buffer they describe moves or grows

@@ -74,12 +74,17 @@ class _Column:
         return out
 
 
+MAX_DEVICE_COLUMNS = 16      # include/b2r.h B2R_MAX_COLUMNS
+MAX_WHERE_NODES = 32         # include/b2r.h B2R_WHERE_MAX_NODES
+LEAF, AND, OR = 0, 1, 2
+
+
 class MetaTable:
     """Per-collection metadata store (row-aligned with the device corpus)."""
 
     def __init__(self):
         self.nrows = 0
-        self.cols: dict[str, _Column] = {}
+        self.cols: dict[str, _Column] = {}        # insertion order = device column number (the first 16 keys)
         self.meta: list[dict | None] = []       # original dicts, returned verbatim by query/get
         self.type_codes: dict[str, int] = {}    # value of the `type` key -> device code
         self.type_overflow = False              # more distinct type values than device codes
@@ -168,6 +173,81 @@ class MetaTable:
             return np.zeros(self.nrows, dtype=bool)
         fn = _CMP[op]
         return col.lut_mask(self.nrows, lambda v, kd: kd == vk and fn(v, val))
+
+    # ---- where, compiled for the device (include/b2r.h b2r_where) --------------------------------
+    def device_column(self, key: str) -> int | None:
+        """Device column number of `key` (its position among the first 16 keys seen), else None."""
+        for i, k in enumerate(self.cols):
+            if i >= MAX_DEVICE_COLUMNS:
+                return None
+            if k == key:
+                return i
+        return None
+
+    def _leaf_pred(self, key, cond):
+        """(column or None, predicate over (value, kind)) of one `{key: cond}` leaf -- the same rules as _eval."""
+        if not isinstance(cond, dict):
+            cond = {"$eq": cond}
+        if len(cond) != 1:
+            raise ValueError(f"Expected operator expression to have exactly one operator, got {cond}")
+        (op, val), = cond.items()
+        col = self.cols.get(key)
+        if op in ("$in", "$nin"):
+            if not isinstance(val, (list, tuple)) or not val:
+                raise ValueError(f"Expected where value for {op} to be a non-empty list")
+            wanted = {(_kind(v), v) for v in val}
+            hit = lambda v, kd: (kd, v) in wanted
+            return col, (hit if op == "$in" else (lambda v, kd: not hit(v, kd)))
+        if op not in _CMP:
+            raise ValueError(f"Expected where operator to be one of {sorted(_CMP)} or $in/$nin, got {op}")
+        vk = _kind(val)
+        if op in ("$gt", "$gte", "$lt", "$lte") and vk != 1:
+            raise ValueError(f"Expected operand value to be an int or a float for operator {op}")
+        fn = _CMP[op]
+        return col, (lambda v, kd: kd == vk and fn(v, val))
+
+    def compile(self, where: dict | None):
+        """`where` -> (nodes, lut): the clause in postfix order as (op, column, lut_offset, lut_values) tuples and
+        the concatenated leaf look-up tables (uint32 words; bit c of a leaf's table = its comparison holds for the
+        column's c-th distinct value).  None when the clause cannot run on the device (a key beyond the 16 device
+        columns, more than 32 nodes); the caller then hands the device a host-evaluated bitmap instead."""
+        if not where:
+            return None
+        nodes, luts = [], []
+
+        def walk(w):
+            if not isinstance(w, dict) or len(w) != 1:
+                raise ValueError(f"Expected where to have exactly one operator, got {w}")
+            (key, cond), = w.items()
+            if key in ("$and", "$or"):
+                if not isinstance(cond, (list, tuple)) or len(cond) < 1:
+                    raise ValueError(f"Expected where value for {key} to be a non-empty list")
+                ok = walk(cond[0])
+                for sub in cond[1:]:
+                    ok = walk(sub) and ok
+                    nodes.append((AND if key == "$and" else OR, 0, 0, 0))
+                return ok
+            if key.startswith("$"):
+                raise ValueError(f"Expected where operator to be one of $and, $or, got {key}")
+            col, pred = self._leaf_pred(key, cond)
+            off = sum(len(x) for x in luts)
+            if col is None:                       # no row carries the key: an empty table on column 0 is always false
+                nodes.append((LEAF, 0, off, 0))
+                return True
+            ci = self.device_column(key)
+            if ci is None:
+                return False
+            bits = np.zeros(((len(col.values) + 31) // 32) * 32, dtype=bool)
+            for c, (v, kd) in enumerate(zip(col.values, col.kinds)):
+                bits[c] = bool(pred(v, kd))
+            luts.append(np.packbits(bits, bitorder="little").view("<u4"))
+            nodes.append((LEAF, ci, off, len(col.values)))
+            return True
+
+        if not walk(where) or len(nodes) > MAX_WHERE_NODES:
+            return None
+        lut = np.concatenate(luts).astype(np.uint32) if luts else np.zeros(0, dtype=np.uint32)
+        return nodes, np.ascontiguousarray(lut)
 
     def type_only_mask(self, where: dict | None) -> int | None:
         """If `where` only constrains the `type` key by equality / $in on string values that all

@@ -1,0 +1,133 @@
+"""The device where-engine: compiled clauses (include/b2r.h b2r_where) evaluated by where_bits_kernel against the
+dictionary-encoded metadata columns must give, bit for bit, the rows Chroma's grammar selects
+(oracle.exact_oracle.where_match, the per-row restatement) -- and queries restricted by them must match the oracle."""
+import numpy as np
+import pytest
+
+from conftest import make_unit
+
+pytestmark = pytest.mark.gpu
+
+CLAUSES = [
+    {"type": {"$ne": "text"}}, {"type": {"$nin": ["image"]}}, {"doc_id": "doc_0007"}, {"page": {"$gte": 5}},
+    {"page": {"$lt": 3}}, {"page": 4}, {"page": 4.0}, {"score": {"$gt": 20.5}}, {"flag": True}, {"flag": {"$ne": True}},
+    {"page": {"$ne": "4"}}, {"missing": "x"}, {"missing": {"$ne": "x"}}, {"type": "video"},
+    {"$and": [{"type": "text"}, {"page": {"$lte": 2}}]},
+    {"$or": [{"type": "image"}, {"$and": [{"doc_id": "doc_0003"}, {"page": {"$in": [1, 2, 3]}}]}]},
+    {"page": {"$in": [1, "1", True]}},
+    {"$and": [{"doc_id": {"$in": ["doc_0001", "doc_0002", "doc_0009"]}}, {"type": {"$ne": "table"}}, {"page": {"$gte": 1}}]},
+    {"$or": [{"missing": 1}, {"flag": False}]},
+]
+
+
+def _metas(n, seed=0):
+    rng = np.random.default_rng(seed)
+    metas = []
+    for i in range(n):
+        m = {"doc_id": f"doc_{i % 17:04d}", "item_id": f"text_{i}", "type": str(rng.choice(["text", "table", "image"]))}
+        if i % 3:
+            m["page"] = int(i % 11)
+        if i % 5 == 0:
+            m["score"] = float(i) / 7
+        if i % 7 == 0:
+            m["flag"] = bool(i % 2)
+        if i % 50 == 0:
+            m = None
+        metas.append(m)
+    return metas
+
+
+@pytest.fixture(scope="module")
+def coll():
+    from multimodal_rag_b200 import B200Collection
+    n, d = 5000, 384
+    X = make_unit(n, d, 4)
+    metas = _metas(n)
+    c = B200Collection("w", {"hnsw:space": "cosine"})
+    for s in range(0, n, 1700):                       # several batches: columns appear and grow over time
+        c.add(ids=[f"id{i}" for i in range(s, min(n, s + 1700))], embeddings=X[s:s + 1700], metadatas=metas[s:s + 1700])
+    dead = list(range(0, n, 9))
+    c.delete(ids=[f"id{i}" for i in dead])
+    alive = np.ones(n, dtype=bool)
+    alive[dead] = False
+    yield c, X, metas, alive
+    c.close()
+
+
+@pytest.mark.parametrize("where", CLAUSES)
+def test_device_clause_bitmap_is_bit_exact(coll, where):
+    from oracle.exact_oracle import where_match
+    c, X, metas, alive = coll
+    assert c._meta.compile(where) is not None, "this clause should run on the device"
+    want = np.array([where_match(m, where) for m in metas]) & alive
+    np.testing.assert_array_equal(c.filter_bits(where), want)
+    c.device_where = False                            # the host-evaluated bitmap path gives the same rows
+    try:
+        np.testing.assert_array_equal(c.filter_bits(where), want)
+    finally:
+        c.device_where = True
+
+
+@pytest.mark.parametrize("where", CLAUSES[::3])
+@pytest.mark.parametrize("nq", [1, 40])
+def test_filtered_queries_match_oracle(coll, where, nq):
+    from oracle import exact_oracle as eo
+    c, X, metas, alive = coll
+    mask = np.array([eo.where_match(m, where) for m in metas]) & alive
+    Q = make_unit(nq, 384, 11)
+    rows, dist, cnt = c.query_rows(Q, 10, where)
+    er, ed = eo.topk_exact(eo.normalize_f32(Q), eo.normalize_f32(X), 10, "cosine", allowed=mask)
+    for i in range(nq):
+        assert cnt[i] == len(er[i])
+        np.testing.assert_array_equal(rows[i, : cnt[i]], er[i])
+        np.testing.assert_allclose(dist[i, : cnt[i]], ed[i], rtol=1e-5, atol=1e-7)
+
+
+def test_keys_beyond_the_device_columns_fall_back_to_a_host_bitmap():
+    from multimodal_rag_b200 import B200Collection
+    n = 600
+    X = make_unit(n, 384, 8)
+    metas = [{f"k{j}": int((i + j) % 4) for j in range(20)} for i in range(n)]
+    c = B200Collection("wide", {"hnsw:space": "l2"})
+    c.add(ids=[f"r{i}" for i in range(n)], embeddings=X, metadatas=metas)
+    assert c._meta.compile({"k3": 1}) is not None and c._meta.compile({"k19": 1}) is None
+    for where in ({"k3": 1}, {"k19": 1}, {"$and": [{"k2": {"$gte": 2}}, {"k18": {"$ne": 0}}]}):
+        want = np.array([all(_leaf(m, k, v) for k, v in _flatten(where)) for m in metas])
+        np.testing.assert_array_equal(c.filter_bits(where), want)
+    c.close()
+
+
+def _flatten(where):
+    if "$and" in where:
+        for w in where["$and"]:
+            yield from _flatten(w)
+    else:
+        yield from where.items()
+
+
+def _leaf(m, k, cond):
+    if not isinstance(cond, dict):
+        return m.get(k) == cond
+    (op, v), = cond.items()
+    return {"$gte": lambda a: a >= v, "$ne": lambda a: a != v}[op](m[k])
+
+
+def test_malformed_programs_are_rejected(coll):
+    import ctypes
+    from multimodal_rag_b200 import _lib
+    c, *_ = coll
+    lib = _lib.load()
+    out = np.zeros(200, dtype=np.uint32)
+
+    def run(nodes, lut_words=0):
+        w = _lib.B2RWhere(n_nodes=len(nodes), lut=None, lut_words=lut_words)
+        for i, nd in enumerate(nodes):
+            w.nodes[i] = _lib.B2RWhereNode(*nd)
+        f = _lib.B2RFilter(type_mask=(1 << 64) - 1, allow_bits=None, where=ctypes.pointer(w))
+        return lib.b2r_filter_eval(c.handle, ctypes.byref(f), out.ctypes.data, 0)
+
+    assert run([(_lib.WHERE_AND, 0, 0, 0)]) == _lib.B2R_EINVAL                                  # operator without operands
+    assert run([(_lib.WHERE_LEAF, 0, 0, 0), (_lib.WHERE_LEAF, 0, 0, 0)]) == _lib.B2R_EINVAL     # two results left
+    assert run([(_lib.WHERE_LEAF, 99, 0, 0)]) == _lib.B2R_EINVAL                                # column out of range
+    assert run([(_lib.WHERE_LEAF, 0, 0, 64)]) == _lib.B2R_EINVAL                                # table outside lut
+    assert run([(_lib.WHERE_LEAF, 0, 0, 0)]) == _lib.B2R_OK and not out.any()                   # empty table: nothing passes

@@ -74,3 +74,45 @@ def test_bad_clauses_raise(bad):
     t, _ = _table(20)
     with pytest.raises(ValueError):
         t.mask(bad)
+
+
+def _run_program(t, nodes, lut):
+    """Host model of where_bits_kernel: the compiled postfix program over the dictionary codes."""
+    cols = list(t.cols.values())
+    stack = []
+    for op, col, off, nv in nodes:
+        if op == 0:
+            bit = np.zeros(t.nrows, dtype=bool)
+            if nv:
+                codes = np.full(t.nrows, -1, dtype=np.int64)
+                codes[: cols[col].n] = cols[col].codes[: cols[col].n]
+                ok = (codes >= 0) & (codes < nv)
+                c = np.where(ok, codes, 0)
+                bit = ok & (((lut[off + (c >> 5)] >> (c & 31).astype(np.uint32)) & 1) == 1)
+            stack.append(bit)
+        else:
+            b, a = stack.pop(), stack.pop()
+            stack.append(a & b if op == 1 else a | b)
+    assert len(stack) == 1
+    return stack[0]
+
+
+@pytest.mark.parametrize("where", CLAUSES)
+def test_compiled_program_matches_host_mask(where):
+    t, metas = _table()
+    prog = t.compile(where)
+    assert prog is not None
+    nodes, lut = prog
+    assert lut.dtype == np.uint32 and len(nodes) <= 32
+    np.testing.assert_array_equal(_run_program(t, nodes, lut), t.mask(where))
+
+
+def test_compile_gives_up_on_host_only_columns_and_long_clauses():
+    t = MetaTable()
+    for i in range(40):
+        t.append({f"k{j}": i % (j + 2) for j in range(20)})
+    assert t.compile({"k15": 1}) is not None and t.compile({"k16": 1}) is None
+    assert t.compile({"$or": [{"k1": i} for i in range(17)]}) is None          # 17 leaves + 16 ORs = 33 nodes
+    assert t.compile({"$or": [{"k1": i} for i in range(16)]}) is not None
+    with pytest.raises(ValueError):
+        t.compile({"k1": {"$gt": "a"}})
