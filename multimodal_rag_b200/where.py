@@ -45,6 +45,7 @@ class _Column:
         self.values: list = []
         self.kinds: list[int] = []
         self.index: dict = {}
+        self.kinds_np = None       # cache of `kinds` as an array (compiled $ne leaves)
 
     def _grow(self, n):
         if n > self.codes.shape[0]:
@@ -206,6 +207,35 @@ class MetaTable:
         fn = _CMP[op]
         return col, (lambda v, kd: kd == vk and fn(v, val))
 
+    @staticmethod
+    def _leaf_table(col: _Column, cond, pred) -> np.ndarray:
+        """bool per distinct value of `col` (padded to a multiple of 32): does the leaf's comparison hold for it?
+        Equality-style operators go through the column's value index (O(operands), not O(distinct values) --
+        a doc_id column has one value per document); ranges test every distinct value."""
+        nv = len(col.values)
+        bits = np.zeros(((nv + 31) // 32) * 32, dtype=bool)
+        if not isinstance(cond, dict):
+            cond = {"$eq": cond}
+        (op, val), = cond.items()
+        if op in ("$eq", "$in", "$nin"):
+            for v in ([val] if op == "$eq" else val):
+                c = col.index.get((_kind(v), v))
+                if c is not None:
+                    bits[c] = True
+            if op == "$nin":
+                bits[:nv] = ~bits[:nv]
+        elif op == "$ne":
+            if col.kinds_np is None or col.kinds_np.shape[0] != nv:
+                col.kinds_np = np.asarray(col.kinds, dtype=np.int8)
+            bits[:nv] = col.kinds_np == _kind(val)
+            c = col.index.get((_kind(val), val))
+            if c is not None:
+                bits[c] = False
+        else:
+            for c, (v, kd) in enumerate(zip(col.values, col.kinds)):
+                bits[c] = bool(pred(v, kd))
+        return bits
+
     def compile(self, where: dict | None):
         """`where` -> (nodes, lut): the clause in postfix order as (op, column, lut_offset, lut_values) tuples and
         the concatenated leaf look-up tables (uint32 words; bit c of a leaf's table = its comparison holds for the
@@ -237,10 +267,7 @@ class MetaTable:
             ci = self.device_column(key)
             if ci is None:
                 return False
-            bits = np.zeros(((len(col.values) + 31) // 32) * 32, dtype=bool)
-            for c, (v, kd) in enumerate(zip(col.values, col.kinds)):
-                bits[c] = bool(pred(v, kd))
-            luts.append(np.packbits(bits, bitorder="little").view("<u4"))
+            luts.append(np.packbits(self._leaf_table(col, cond, pred), bitorder="little").view("<u4"))
             nodes.append((LEAF, ci, off, len(col.values)))
             return True
 
