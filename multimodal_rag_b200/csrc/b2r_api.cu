@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <new>
 #include <vector>
 
@@ -53,6 +54,21 @@ int ensure(DevBuf &b, size_t bytes) {
 void release(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int ingest_ctas_per_sm(ingest_fn fn) {
+    static std::mutex mu;
+    static std::map<const void *, int> cache;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find((const void *)fn);
+    if (it != cache.end()) return it->second;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, INGEST_THREADS, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 4;
+    }
+    cache[(const void *)fn] = per_sm;
+    return per_sm;
+}
 
 // entries-per-lane of the candidate lists for a fast-path query: KP = 32*EPL >= 2k
 int epl_scored(int k) { return k <= 16 ? 1 : k <= 32 ? 2 : k <= 64 ? 4 : k <= 128 ? 8 : 0; }
@@ -305,10 +321,10 @@ extern "C" int b2r_ingest_f32(b2r_handle h, const float *x, int64_t n, const uin
     p.max_norm2 = h->max_norm2; p.qerr = nullptr; p.q_eps = nullptr; p.norms = nullptr; p.eps_rel = 0.f;
     for (int z = 0; z < 3; ++z) { p.zero[z] = nullptr; p.zero_words[z] = 0; }
     const int wpb = INGEST_THREADS / 32;
-    int grid = (int)std::min<int64_t>((n + wpb - 1) / wpb, (int64_t)h->sm_count * 16);
-    const bool vec = (h->dim % 8 == 0) && (((uintptr_t)xd & 15) == 0);
-    if (vec) ingest_kernel<true><<<grid, INGEST_THREADS, 0, s>>>(p);
-    else ingest_kernel<false><<<grid, INGEST_THREADS, 0, s>>>(p);
+    const ingest_fn fn = ingest_lookup(h->dim, h->dp, xd);
+    // one full wave of resident CTAs, every warp walks its share of the rows (no tail wave)
+    int grid = (int)std::min<int64_t>((n + wpb - 1) / wpb, (int64_t)h->sm_count * ingest_ctas_per_sm(fn));
+    fn<<<grid, INGEST_THREADS, 0, s>>>(p);
     B2R_CUDA(cudaGetLastError());
     h->n_launches++;
     if (xd != x || td != type_code) B2R_CUDA(cudaStreamSynchronize(s));   // staging buffers are reused
@@ -911,10 +927,8 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
         }
         const int wpb = INGEST_THREADS / 32;
         int grid = std::min((nq + wpb - 1) / wpb, h->sm_count * 8);
-        const bool vec = (h->dim % 8 == 0) && (((uintptr_t)q_raw & 15) == 0);
         KernelTimer kt1(h, s, 1);
-        if (vec) B2R_CUDA(launch_pdl(ingest_kernel<true>, dim3(grid), dim3(INGEST_THREADS), 0, s, p));
-        else B2R_CUDA(launch_pdl(ingest_kernel<false>, dim3(grid), dim3(INGEST_THREADS), 0, s, p));
+        B2R_CUDA(launch_pdl(ingest_lookup(h->dim, h->dp, q_raw), dim3(grid), dim3(INGEST_THREADS), 0, s, p));
         kt1.stop();
         h->n_launches++;
     }
