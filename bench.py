@@ -102,6 +102,24 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries that print there (NCCL's version banner, OpenMP notices)
+    are sent to stderr: fd 1 is pointed at fd 2 for the life of the process, the JSON line goes to the saved fd."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -162,6 +180,7 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
+    claim_stdout()
     import numpy as np
     from oracle import c_oracle
     c_oracle.build()
@@ -182,15 +201,14 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
 def run_gpu(args):
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    claim_stdout()                                  # NCCL prints its version banner on stdout
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -478,7 +496,7 @@ def run_gpu(args):
         line["sharded"] = sharded
     if sharded_c4 is not None:
         line["sharded_c4"] = sharded_c4
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
