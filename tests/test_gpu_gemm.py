@@ -36,9 +36,9 @@ def test_gemm_batch_crosses_query_blocks():
     assert c.stats()["n_exact_fallbacks"] == 0
 
 
-def test_gemm_sampling_pass_seeds_thresholds():
-    """>= 256 tiles: the strided sampling pass runs first; results must still equal the oracle,
-    including when the planted neighbours sit in rows the sample does not visit."""
+def test_gemm_mid_size_shard_planted_neighbours():
+    """274 tiles (too few per CTA for the in-kernel seeding, which tests/test_gpu_seeding.py covers): results must
+    equal the oracle, including for planted neighbours at the edges of slices."""
     n, d = 70001, 384
     c, X, _ = _mk("cosine", d, n, seed=19)
     Q = make_unit(24, d, 20)
