@@ -733,13 +733,12 @@ constexpr int GEMM_MIN_BATCH = 5;        // below this the scan reads the corpus
 constexpr int GEMM_MAX_QBLOCKS = 8;      // 128-query blocks per launch (1024 queries per corpus pass)
 constexpr int GEMM_REGION_CAP = 256;       // pool mode: entries per private (query, slice, half) region
 constexpr int GEMM_POOL_CAP = 16384;        // pool mode: compact pool entries per query (>= SMs*2*32 for the sampling pass)
-constexpr int GEMM_POOL_SAMPLE_RANK = 32;  // pool mode: the bound is the 32nd best sampled score
 
 int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams &fin, const b2r_filter &f,
                       const uint32_t *allow_dev, cudaStream_t s) {
     const int L = gemm_list_len(k);                    // 8 / 16 / 32, or 0 = pool mode (32 < k <= 128)
     const bool pool_mode = L == 0;
-    const int L_sample = pool_mode ? GEMM_POOL_SAMPLE_RANK : L;
+    const int L_seed = pool_mode ? GEMM_POOL_SAMPLE_RANK : L;     // rank of the sampled score that becomes the bound
     const int BN = gemm_tile_rows(h->dp);
     const int tiles_total = (int)((h->rows + BN - 1) / BN);
     const unsigned n_words = (unsigned)tiles_total * (unsigned)(BN / 32);
@@ -774,15 +773,11 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         if ((rc = gemm_encode_map(&h->tm_query, h->q_bf16.p, h->dp, (uint64_t)nq, GEMM_BM)) != B2R_OK) return rc;
         h->tm_query_base = h->q_bf16.p; h->tm_query_rows = nq;
     }
-    // Threshold seeding.
-    //   list mode: in-kernel -- every CTA first scans a few tiles of its slice in sampling mode and posts the step
-    //              maxima, the epilogue warps turn the posts into gthr[q] (GemmParams::seed_tiles; no extra launch);
-    //   pool mode: a sampling PASS over 1/32 of the shard (>= 4 tiles) whenever a slice could overflow a private
-    //              region without a bound -- the expected pool is then 32 * 32 = 1024 entries per query whatever
-    //              the shard size.
-    const int sample_tiles = (pool_mode && tiles_total >= 8) ? std::max(4, tiles_total / 32) : 0;
-    if (!pool_mode && (rc = ensure(h->gemm_samples, sizeof(unsigned) * (size_t)GEMM_BM * h->sm_count * GEMM_HALVES * L)) != B2R_OK)
-        return rc;
+    // Threshold seeding happens inside K3 (GemmParams::seed_tiles): every CTA first scans a few tiles of its slice in
+    // sampling mode and posts the step maxima, the epilogue warps fold the posts into gthr[q].  List mode: the L-th best
+    // post.  Pool mode: the 32nd best, which must be in place before the first append -- the expected pool is then
+    // 32 * (shard rows / sampled rows) entries per query whatever the shard size.
+    if ((rc = ensure(h->gemm_samples, sizeof(unsigned) * (size_t)GEMM_BM * h->sm_count * GEMM_HALVES * L_seed)) != B2R_OK) return rc;
     for (int qb0 = 0; qb0 < qblocks_total; qb0 += GEMM_MAX_QBLOCKS) {
         GemmParams gp;
         gp.n = (unsigned)h->rows; gp.nq = nq; gp.qblock0 = qb0;
@@ -797,24 +792,22 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         un.lists = gp.lists; un.list_stride = list_stride; un.gthr = gp.gthr; un.cnt = gp.cnt;
         un.pool_stats = h->counters + 2;
         const int q0 = qb0 * GEMM_BM, nq_here = std::min(nq - q0, gp.n_qblocks * GEMM_BM);
-        if (sample_tiles) {
-            gp.tiles_total = sample_tiles; gp.tile_mul = tiles_total / sample_tiles; gp.sample_mode = 1;
-            gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, sample_tiles));
-            KernelTimer kt2(h, s, 2);
-            B2R_CUDA(gemm_launch(h->dp, L_sample, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
-            kt2.stop();
-            KernelTimer kt3(h, s, 3);
-            B2R_CUDA(sample_threshold_launch(gp.lists, list_stride, gp.n_slices * GEMM_HALVES * L_sample, L_sample, gp.gthr, gp.cnt, q0, nq_here, s));
-            kt3.stop();
-            h->n_launches += 2;
-        }
-        gp.tiles_total = tiles_total; gp.tile_mul = 1; gp.sample_mode = 0;
+        gp.tiles_total = tiles_total;
         gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, tiles_total));
         {   // seeding tiles per CTA: >= 128 tiles (32k rows) over the block's slices, more on long slices (<= 1/64 extra work)
             const int tiles_per_cta = tiles_total / gp.n_slices;
             const int want = std::max((128 + gp.n_slices - 1) / gp.n_slices, std::min(tiles_per_cta / 64, 8));
-            gp.seed_tiles = (!pool_mode && !h->no_seed && nq >= h->seed_min_batch && tiles_per_cta >= 8 * want) ? want : 0;
-            if (gp.seed_tiles && h->seed_tiles_override > 0) gp.seed_tiles = std::min(h->seed_tiles_override, tiles_per_cta / 2);
+            gp.seed_stride = 1;
+            if (pool_mode) {   // always, when there is anything to sample: max(4 tiles, 1/32 of the shard) spread over the slices, so
+                               // that the 32nd best sample leaves ~1024 candidates per query -- far more than k, or the
+                               // certificate (k-th exact candidate vs the bound) could not hold
+                const int sample_tiles = tiles_total >= 8 ? std::max(4, tiles_total / 32) : 0;
+                gp.seed_tiles = sample_tiles ? std::max(1, sample_tiles / gp.n_slices) : 0;
+                if (sample_tiles && sample_tiles < gp.n_slices) gp.seed_stride = gp.n_slices / sample_tiles;
+            } else {
+                gp.seed_tiles = (!h->no_seed && nq >= h->seed_min_batch && tiles_per_cta >= 8 * want) ? want : 0;
+            }
+            if (gp.seed_tiles && h->seed_tiles_override > 0) gp.seed_tiles = std::min(h->seed_tiles_override, std::max(1, tiles_per_cta / 2));
         }
         un.max_entries = pool_mode ? GEMM_POOL_CAP : gp.n_slices * GEMM_HALVES * L;
         KernelTimer kt(h, s);

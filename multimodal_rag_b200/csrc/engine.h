@@ -64,8 +64,6 @@ cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const
                         const GemmParams &p, cudaStream_t s);
 cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_mask, const uint32_t *allow_bits,
                              unsigned n, unsigned n_words, uint32_t *out, int sm_count, cudaStream_t s);
-cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
-                                    unsigned *cnt, int q0, int nq, cudaStream_t s);
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const UnionParams &u, int q0, int nq, cudaStream_t s);
 
 struct DevBuf {
@@ -116,8 +114,8 @@ struct b2r_index {
     bool timing = false;
     bool no_seed = false;
     int seed_min_batch = 0, seed_tiles_override = 0;
-    int timing_stage = 0;           // which launch the events bracket: 0 scoring (default); B2R_TIME_STAGE=1..5 (development):
-                                    // 1 prepare, 2 sampling pass, 3 sample reducer, 4 finalize, 5 exact fix-up
+    int timing_stage = 0;           // which launch the events bracket: 0 scoring (default); B2R_TIME_STAGE=1, 4, 5 (development):
+                                    // 1 prepare, 4 finalize, 5 exact fix-up
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
     double scoring_ms = 0.0;
     int64_t scoring_launches = 0;

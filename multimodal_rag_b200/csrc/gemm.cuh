@@ -32,6 +32,7 @@ namespace b2r {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_POOL_SAMPLE_RANK = 32;  // pool mode: the bound is the 32nd best sampled score
 constexpr unsigned long long GEMM_SEED_TIMEOUT_NS = 50000ull;   // bound on every wait of the in-kernel seeding phase
 constexpr int GEMM_HALVES = 2;          // epilogue warps w and w+4 share a TMEM lane quadrant and split a tile's columns
 constexpr int GEMM_SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA
@@ -51,9 +52,7 @@ struct GemmParams {
     int qblock0;                 // first 128-query block of this launch (batches > 8 blocks are chunked)
     int n_qblocks, n_slices;     // grid = n_slices * n_qblocks (blockIdx = slice * n_qblocks + qblock)
     int list_stride;             // KeyS entries reserved per query in `lists` (>= n_slices * 2 * L)
-    int tiles_total;             // tiles this launch covers (main pass: ceil(n / BN); sampling pass: the sample size)
-    int tile_mul;                // launch tile t is corpus tile t * tile_mul (1 = main pass; > 1 = strided sample)
-    int sample_mode;             // 1 = sampling pass: keep only the best scores seen (one per 32-row step), no hit path
+    int tiles_total;             // tiles of the shard: ceil(n / BN)
     const uint32_t *pass_bits;   // bit r = row r is live and passes the filter; 0 for r >= n
     const float *bias;           // [n] -|x|^2/2 (l2) or nullptr
     unsigned *gthr;              // [n_qblocks*128] shared per-query bound, KeyS::ord encoding, 0 = none yet
@@ -67,6 +66,7 @@ struct GemmParams {
     // the posts of their share of the block's queries into gthr[q] (the L-th best post) and raise seeded[q]; every
     // epilogue thread waits (bounded) for its own query's flag, then the slice is scanned with that bound.
     int seed_tiles;              // 0 = off
+    int seed_stride;             // slices 0, stride, 2*stride, ... sample; the others post nothing (small shards in pool mode)
     unsigned *samples;           // [launch queries (padded to 128)][n_slices*2][2 .. L] ordered score keys, 0 = empty
     unsigned *seeded;            // [all queries] 0 = not seeded yet, 1 = seeded without a bound, else the seed (= gthr[q] then)
     unsigned *arrive;            // [all q-blocks] CTAs that have posted (0 between calls: the query preparation clears it)
@@ -619,8 +619,9 @@ __device__ __forceinline__ unsigned warp_lth_largest(const unsigned *vals, int n
 // ---------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------
-// SAMPLE = the sampling-pass build of the kernel (separate instantiation: the main build's hot loop stays small)
-template <int KB, int L, bool HAS_BIAS, bool SAMPLE>
+template <int KB, int L, bool HAS_BIAS>
+// 10 warps = 3 on some SM sub-partition, whose register file is 16K: 168 registers per thread is the hard cap
+// (measured: __maxnreg__(192) compiles without spills but cannot launch)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
     constexpr int BN = gemm_bn(KB);
@@ -647,8 +648,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const int qb = p.qblock0 + blockIdx.x % p.n_qblocks, slice = blockIdx.x / p.n_qblocks;
     const int t0 = (int)((long long)p.tiles_total * slice / p.n_slices);
     const int t1 = (int)((long long)p.tiles_total * (slice + 1) / p.n_slices);
-    constexpr bool SEED = L > 0 && !SAMPLE;                 // list-mode main pass: in-kernel threshold seeding
-    const int S = SEED ? min(p.seed_tiles, t1 - t0) : 0;    // seeding tiles in front of the slice
+    // in-kernel threshold seeding: sampling tiles in front of the slice (every seed_stride-th slice samples, all post)
+    const int S = (p.seed_tiles > 0 && slice % p.seed_stride == 0) ? min(p.seed_tiles, t1 - t0) : 0;
     const int n_iter = S + (t1 - t0);
 
     if (threadIdx.x == 0) {
@@ -681,7 +682,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     mbar_expect_tx(&bar_full[stage], STAGE_BYTES);
                     if (!A_RES) tma_load_2d(smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES, &tm_q, &bar_full[stage], kb * 64, qb * GEMM_BM);
-                    tma_load_2d(smB + (size_t)stage * STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * p.tile_mul * BN);
+                    tma_load_2d(smB + (size_t)stage * STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -719,7 +720,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const int half = (warp - 2) >> 2;                            // which half of a tile's columns
         const int q = qb * GEMM_BM + quad * 32 + lane;
         const bool publish = q < p.nq;
-        constexpr int LL = L > 0 ? L : 1;                          // pool mode (L = 0) keeps no list
+        constexpr int LL = L > 0 ? L : 1;                          // pool mode (L = 0) keeps no list during the scan ...
+        constexpr int LS = L > 0 ? L : GEMM_POOL_SAMPLE_RANK;      // ... but seeds its bound from the 32nd best sample
         RegList<LL> list; list.init();
         float thr = q >= p.nq ? INFINITY : -INFINITY;                // padding lanes admit nothing
         KeyS *region = nullptr;
@@ -728,10 +730,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             region = p.regions + ((size_t)(q - p.qblock0 * GEMM_BM) * (p.n_slices * GEMM_HALVES) + (size_t)(slice * GEMM_HALVES + half)) * p.region_cap;
         unsigned g_seen = 0;
         unsigned *gq = p.gthr + q;
-        unsigned g_next = *reinterpret_cast<volatile unsigned *>(gq);   // seeded by the sampling pass (pool mode)
+        unsigned g_next = *reinterpret_cast<volatile unsigned *>(gq);
 
         // one tile: TMEM -> registers in 32-column steps, two register buffers so the next load flies under this step
-        auto run_tile = [&](int t, int it, auto sample_c) {
+        auto run_tile = [&](int t, int it, auto sample_c, auto &slist) {
             constexpr bool SMP = decltype(sample_c)::value;
             const int buf = it & 1;
             if (!SMP && g_next > g_seen) { g_seen = g_next; thr = fmaxf(thr, KeyS::unord(g_next)); }
@@ -740,20 +742,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             // the other slices' progress on this query: loaded now, consumed at the top of the next tile
             if (!SMP) g_next = *reinterpret_cast<volatile unsigned *>(gq);
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * NC * 32);
-            const unsigned row0 = (unsigned)(t * p.tile_mul) * BN + (unsigned)(half * NC * 32);
+            const unsigned row0 = (unsigned)t * BN + (unsigned)(half * NC * 32);
             uint32_t va[32], vb[32];
             tmem_ld_x32(trow, va);
 #pragma unroll 1
             for (int c = 0; c < NC; c += 2) {
                 tmem_ld_wait(va);
                 tmem_ld_x32(trow + (c + 1) * 32, vb);
-                if constexpr (SMP) epi_chunk_sample<LL, HAS_BIAS>(va, row0 + c * 32, p, list);
+                if constexpr (SMP) epi_chunk_sample<LS, HAS_BIAS>(va, row0 + c * 32, p, slist);
                 else if constexpr (L == 0) epi_chunk_pool<HAS_BIAS>(va, row0 + c * 32, p, thr, region, rcount);
                 else epi_chunk<LL, HAS_BIAS>(va, row0 + c * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
                 tmem_ld_wait(vb);
                 if (c + 2 < NC) tmem_ld_x32(trow + (c + 2) * 32, va);
-                if constexpr (SMP) epi_chunk_sample<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list);
+                if constexpr (SMP) epi_chunk_sample<LS, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, slist);
                 else if constexpr (L == 0) epi_chunk_pool<HAS_BIAS>(vb, row0 + (c + 1) * 32, p, thr, region, rcount);
                 else epi_chunk<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
@@ -764,29 +766,30 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         };
 
         int it = 0;
-        if constexpr (SEED) {
-            if (S > 0) {
+        {
+            if (p.seed_tiles > 0) {
                 // ---- seeding phase (see GemmParams::seed_tiles) ----
                 // 1. the first S tiles of the slice in sampling mode: the list collects the best step maxima
-                for (int i = 0; i < S; ++i, ++it) run_tile(t0 + i, it, std::true_type());
+                RegList<LS> slist; slist.init();
+                for (int i = 0; i < S; ++i, ++it) run_tile(t0 + i, it, std::true_type(), slist);
                 // 2. post them, count this CTA in
-                // values posted per thread: its 2 (4) best when the block's slices then still post >= 4 L (2 L) between
+                // values posted per thread: its 2 (4) best when the block's sampling slices then still post >= 4 L (2 L) between
                 // them -- the L-th best of that union is as good a bound -- else all it has (S * NC step maxima at most)
-                const int pv = p.n_slices >= LL ? 2 : p.n_slices * GEMM_HALVES >= LL ? 4 : min(LL, (S * NC + 3) & ~3);
+                const int n_samp = (p.n_slices + p.seed_stride - 1) / p.seed_stride;      // slices that sample
+                const int pv = n_samp >= LS ? 2 : n_samp * GEMM_HALVES >= LS ? 4 : min(LS, (p.seed_tiles * NC + 3) & ~3);
                 if (publish) {
                     unsigned *dst = p.samples + ((size_t)(q - p.qblock0 * GEMM_BM) * (p.n_slices * GEMM_HALVES) +
                                                  (size_t)(slice * GEMM_HALVES + half)) * pv;
 #pragma unroll
-                    for (int i = 0; i < LL; i += 2) {
+                    for (int i = 0; i < LS; i += 2) {
                         if (i >= pv) break;
                         uint2 o;
-                        o.x = list.r[i] != 0xffffffffu ? KeyS::ord(list.s[i]) : 0u;
-                        o.y = list.r[i + 1] != 0xffffffffu ? KeyS::ord(list.s[i + 1]) : 0u;
+                        o.x = slist.r[i] != 0xffffffffu ? KeyS::ord(slist.s[i]) : 0u;
+                        o.y = slist.r[i + 1] != 0xffffffffu ? KeyS::ord(slist.s[i + 1]) : 0u;
                         *reinterpret_cast<uint2 *>(dst + i) = o;
                     }
                     __threadfence();
                 }
-                list.init();
                 epi_bar_sync();                                   // every epilogue thread's post is fenced
                 if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(p.arrive + qb, 1u); }
                 // 3. this CTA's share of the block's queries, one per epilogue warp: once every slice has posted,
@@ -804,7 +807,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                         __nanosleep(64);
                     }
                     if (!posted) break;
-                    const unsigned v = warp_lth_largest<LL>(p.samples + (size_t)(qs - p.qblock0 * GEMM_BM) * per_q, per_q, lane);
+                    const unsigned v = warp_lth_largest<LS>(p.samples + (size_t)(qs - p.qblock0 * GEMM_BM) * per_q, per_q, lane);
                     if (lane == 0) {
                         if (v != 0u) atomicMax(p.gthr + qs, v);       // the finalize reads the bound from gthr[q]
                         __threadfence();
@@ -824,7 +827,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 __syncwarp();
             }
         }
-        for (int t = t0; t < t1; ++t, ++it) run_tile(t, it, std::integral_constant<bool, SAMPLE>());
+        for (int t = t0; t < t1; ++t, ++it) run_tile(t, it, std::false_type(), list);
 
         if (L == 0) {
             if (q < p.nq && rcount > 0) {     // compact the private region into the query's pool
@@ -840,14 +843,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             // entries below the bound published so far need not travel: whatever is dropped here scores
             // <= the final gthr[q], which is all the certificate asks of a row outside the pool
             int nv = 0;
-            if constexpr (SAMPLE) {
+            const unsigned g_now = *reinterpret_cast<volatile unsigned *>(gq);
 #pragma unroll
-                for (int i = 0; i < LL; ++i) nv += list.r[i] != 0xffffffffu ? 1 : 0;
-            } else {
-                const unsigned g_now = *reinterpret_cast<volatile unsigned *>(gq);
-#pragma unroll
-                for (int i = 0; i < LL; ++i) nv += (list.r[i] != 0xffffffffu && KeyS::ord(list.s[i]) >= g_now) ? 1 : 0;
-            }
+            for (int i = 0; i < LL; ++i) nv += (list.r[i] != 0xffffffffu && KeyS::ord(list.s[i]) >= g_now) ? 1 : 0;
             if (nv) {
                 KeyS *dst = p.lists + (size_t)q * p.list_stride + atomicAdd(&p.cnt[q], (unsigned)nv);
 #pragma unroll
@@ -860,42 +858,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
-}
-
-// ---------------------------------------------------------------------------------
-// sampling pass epilogue: one warp per query folds that query's sample lists and seeds the shared
-// bound with the L-th best sampled score -- a real row's score, so at least L rows are >= it and
-// nothing that scores below it can be among the L best of the shard.
-// ---------------------------------------------------------------------------------
-template <int DUMMY>
-__global__ void __launch_bounds__(256) sample_threshold_kernel(const KeyS *__restrict__ lists, int list_stride, int max_entries,
-                                                               int L, unsigned *gthr, unsigned *cnt, int q0) {
-    // one CTA per query: the L-th largest score key by bitwise bisection on CTA-wide counts
-    extern __shared__ unsigned sm_keys[];                 // [max_entries]
-    __shared__ int s_count[3];
-    const int lane = threadIdx.x & 31;
-    const int qi = q0 + blockIdx.x;
-    const KeyS *src = lists + (size_t)qi * list_stride;
-    pdl_wait();
-    pdl_trigger();
-    const int entries = min((int)cnt[qi], max_entries);
-    for (int i = threadIdx.x; i < entries; i += 256) sm_keys[i] = (unsigned)(src[i].v >> 32);   // ord(score)
-    if (threadIdx.x == 0) s_count[0] = s_count[1] = s_count[2] = 0;
-    __syncthreads();
-    if (threadIdx.x == 0) cnt[qi] = 0u;                   // the main pass appends from scratch
-    unsigned t = 0;
-#pragma unroll 1
-    for (int bit = 31, it = 0; bit >= 10; --bit, ++it) {  // 22 bits: sign, exponent, 13 mantissa bits (a lower bound)
-        const unsigned cand = t | (1u << bit);
-        int c = 0;
-        for (int i = threadIdx.x; i < entries; i += 256) c += sm_keys[i] >= cand ? 1 : 0;
-        c = __reduce_add_sync(FULL_MASK, c);
-        if (lane == 0 && c) atomicAdd(&s_count[it % 3], c);
-        if (threadIdx.x == 0) s_count[(it + 1) % 3] = 0;
-        __syncthreads();
-        if (s_count[it % 3] >= L) t = cand;
-    }
-    if (threadIdx.x == 0 && t != 0u) atomicMax(&gthr[qi], t);
 }
 
 }  // namespace b2r

@@ -13,26 +13,22 @@ typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmParams);
 #ifdef B2R_KB
 #define B2R_CAT2(a, b) a##b
 #define B2R_CAT(a, b) B2R_CAT2(a, b)
-gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias, bool sample) {
-    if (sample) {        // sampling-pass build (lists of step maxima): pool mode only, L = 32 (list mode seeds in-kernel)
-        if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true, true> : gemm_topk_kernel<B2R_KB, 32, false, true>;
-        return nullptr;
-    }
-    if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true, false> : gemm_topk_kernel<B2R_KB, 8, false, false>;
-    if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true, false> : gemm_topk_kernel<B2R_KB, 16, false, false>;
-    if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true, false> : gemm_topk_kernel<B2R_KB, 32, false, false>;
-    if (L == 0) return bias ? gemm_topk_kernel<B2R_KB, 0, true, false> : gemm_topk_kernel<B2R_KB, 0, false, false>;   // pool mode
+gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias) {
+    if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true> : gemm_topk_kernel<B2R_KB, 8, false>;
+    if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true> : gemm_topk_kernel<B2R_KB, 16, false>;
+    if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true> : gemm_topk_kernel<B2R_KB, 32, false>;
+    if (L == 0) return bias ? gemm_topk_kernel<B2R_KB, 0, true> : gemm_topk_kernel<B2R_KB, 0, false>;   // pool mode
     return nullptr;
 }
 }  // namespace b2r
 #else
-gemm_fn gemm_lookup_2(int, bool, bool);
-gemm_fn gemm_lookup_4(int, bool, bool);
-gemm_fn gemm_lookup_6(int, bool, bool);
-gemm_fn gemm_lookup_8(int, bool, bool);
-gemm_fn gemm_lookup_12(int, bool, bool);
-gemm_fn gemm_lookup_16(int, bool, bool);
-gemm_fn gemm_lookup_24(int, bool, bool);
+gemm_fn gemm_lookup_2(int, bool);
+gemm_fn gemm_lookup_4(int, bool);
+gemm_fn gemm_lookup_6(int, bool);
+gemm_fn gemm_lookup_8(int, bool);
+gemm_fn gemm_lookup_12(int, bool);
+gemm_fn gemm_lookup_16(int, bool);
+gemm_fn gemm_lookup_24(int, bool);
 
 // ---------------------------------------------------------------------------------
 // pass bitmap: bit r of word r>>5 = row r is live, passes the type mask and the allow bitmap.
@@ -52,15 +48,15 @@ static __global__ void pass_bits_kernel(const uint8_t *__restrict__ type_code, u
 
 
 namespace {
-gemm_fn lookup(int kb, int L, bool bias, bool sample) {
+gemm_fn lookup(int kb, int L, bool bias) {
     switch (kb) {
-        case 2:  return gemm_lookup_2(L, bias, sample);
-        case 4:  return gemm_lookup_4(L, bias, sample);
-        case 6:  return gemm_lookup_6(L, bias, sample);     // all-MiniLM-L6-v2 (384)
-        case 8:  return gemm_lookup_8(L, bias, sample);     // CLIP ViT-B/32 shape (512)
-        case 12: return gemm_lookup_12(L, bias, sample);    // 768
-        case 16: return gemm_lookup_16(L, bias, sample);    // 1024
-        case 24: return gemm_lookup_24(L, bias, sample);    // 1536
+        case 2:  return gemm_lookup_2(L, bias);
+        case 4:  return gemm_lookup_4(L, bias);
+        case 6:  return gemm_lookup_6(L, bias);     // all-MiniLM-L6-v2 (384)
+        case 8:  return gemm_lookup_8(L, bias);     // CLIP ViT-B/32 shape (512)
+        case 12: return gemm_lookup_12(L, bias);    // 768
+        case 16: return gemm_lookup_16(L, bias);    // 1024
+        case 24: return gemm_lookup_24(L, bias);    // 1536
         default: return nullptr;
     }
 }
@@ -100,7 +96,7 @@ encode_fn get_encode() {
 // per-thread list length for n_results = k; 0 = pool mode (no lists, 32 < k <= 128); -1 = unsupported
 int gemm_list_len(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : k <= 128 ? 0 : -1; }
 int gemm_tile_rows(int dp) { return gemm_bn(dp / 64); }
-bool gemm_supported(int dp, int k) { return dp % 64 == 0 && lookup(dp / 64, 8, false, false) != nullptr && gemm_list_len(k) >= 0; }
+bool gemm_supported(int dp, int k) { return dp % 64 == 0 && lookup(dp / 64, 8, false) != nullptr && gemm_list_len(k) >= 0; }
 
 // [rows, dp] bf16 row-major -> 2-D tensor map, box = 64 elements (128 B, one swizzle row) x box_rows
 int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, int box_rows) {
@@ -120,7 +116,7 @@ int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, i
 cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
                         const GemmParams &p, cudaStream_t s) {
     const int kb = dp / 64;
-    gemm_fn f = lookup(kb, L, bias, p.sample_mode != 0);
+    gemm_fn f = lookup(kb, L, bias);
     if (!f) return cudaErrorInvalidValue;
     const size_t smem = smem_of(kb);
     static std::mutex mu;
@@ -146,13 +142,6 @@ cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_m
     if (blocks == 0) blocks = 1;
     pass_bits_kernel<<<blocks, 256, 0, s>>>(type_code, type_mask, allow_bits, n, n_words, out);
     return cudaGetLastError();
-}
-
-cudaError_t sample_threshold_launch(const KeyS *lists, int list_stride, int entries_per_query, int L, unsigned *gthr,
-                                    unsigned *cnt, int q0, int nq, cudaStream_t s) {
-    const size_t smem = (size_t)entries_per_query * 4;
-    if (smem > 40 * 1024) return cudaErrorInvalidValue;   // 148 SMs x 2 halves x L=32 x 4 B = 37.9 KB at most
-    return launch_pdl(sample_threshold_kernel<0>, dim3(nq), dim3(256), smem, s, lists, list_stride, entries_per_query, L, gthr, cnt, q0);
 }
 
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const UnionParams &u, int q0, int nq, cudaStream_t s) {
