@@ -197,3 +197,30 @@ class B200EmbeddingManager:
                     "embedding_dim": self.collection.dimension, "stats": dict(self.stats), "engine": self.collection.stats()}
         except Exception as e:                          # noqa: BLE001
             return {"name": self.collection_name, "count": 0, "error": str(e)}
+
+
+# ---- what the reference does with a result --------------------------------------------
+# Not part of the engine, restated here so the contract it imposes on the engine's output is executable: ids must come
+# back verbatim (the Redis key is parsed out of them) and distances must be in the collection's space with "smaller is
+# closer", because the server turns them into a relevance score.
+
+def sources_from_result(search_results: Dict[str, Any]) -> List[Dict[str, Any]]:
+    """The `sources` list `/query` returns (reference: app/server/api.py:384-396): rank from 1, the Chroma id as
+    `doc_id`, `relevance_score = round(1 - min(distance, 1), 3)`, the item's `type` (or 'unknown')."""
+    out = []
+    triples = zip(search_results["ids"], search_results["distances"], search_results["metadatas"])
+    for rank, (item_id, distance, meta) in enumerate(triples, start=1):
+        score = 1.0 - (distance if distance < 1.0 else 1.0)
+        out.append({"rank": rank, "doc_id": item_id, "relevance_score": round(float(score), 3),
+                    "type": (meta or {}).get("type", "unknown")})
+    return out
+
+
+def redis_key_for(item_id: str) -> str:
+    """Docstore key of a Chroma id (reference: MultiVectorRetriever._item_id_to_redis_key, app/utils/retriever.py:610-637):
+    `doc_<hex>_<item...>` -> `doc:doc_<hex>:<item...>`; ids with fewer than three `_`-separated parts -> `doc:<id>`."""
+    head, sep, rest = item_id.partition("_")
+    second, sep2, item_part = rest.partition("_")
+    if not (sep and sep2):
+        return f"doc:{item_id}"
+    return f"doc:{head}_{second}:{item_part}"
