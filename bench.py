@@ -323,13 +323,18 @@ def run_gpu(args):
     for i in range(W):
         step_host(i)
     barrier()
+    lat = []
     t0 = time.perf_counter()
     for i in range(K):
-        step_host(i)
+        t1 = time.perf_counter()
+        step_host(i)                      # returns with the results in the host arrays (the call synchronises)
+        lat.append(time.perf_counter() - t1)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
     e2e = world * nq * K / e2e_s
     assert int(h_cnt.min()) == k
+    lat.sort()
+    e2e_latency_us = {"p50": lat[len(lat) // 2] * 1e6, "max": lat[-1] * 1e6, "calls": len(lat)}
 
     # ---- batch-1 scan (the HBM-bound headline of north_star), same corpus ----
     q1 = [q[:1].contiguous() for q in Qd]
@@ -487,7 +492,8 @@ def run_gpu(args):
                    "l2_policy": "corpus (768 MB) is larger than L2 (126 MB); query batches rotate",
                    "parallelism": "corpus replicated, queries sharded" if world > 1 else "single GPU"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nq * DIM * 4,
-                "d2h_bytes_per_step": nq * k * 12 + nq * 4},
+                "d2h_bytes_per_step": nq * k * 12 + nq * 4, "latency_us_per_call": e2e_latency_us,
+                "transport": "pinned host buffers: one H2D copy of the query batch, kernels, ONE packed D2H copy, stream sync"},
         "gpu_launches": gpu_launches, "roofline": roof, "batch1": batch1, "ingest": ingest, "clocks": clocks,
     }
     if cpu is not None:
