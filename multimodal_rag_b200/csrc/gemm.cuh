@@ -15,10 +15,16 @@
 // best score to gthr[q] (atomicMax); all slices of the same query read it once per tile, so the
 // admission rate falls with the rows seen by the WHOLE grid, not by one slice.
 //
-// What leaves the kernel: per (query, slice) the L best admitted rows (KeyS: score, local row) and the
-// final gthr[q].  Invariant used by the certificate (finalize_union_kernel): a row that is not in any
-// list was rejected by, or evicted below, a value that was published to gthr[q] or is some list's final
-// L-th best (also published) -- so its bf16 score is <= the final gthr[q].
+// The scan starts from a seeded bound: every CTA first scans a few tiles of its slice in sampling mode, the
+// CTAs of a query block exchange their best samples through global memory and fold them into gthr[q] while
+// the tensor pipe already works on the real tiles (GemmParams::seed_tiles).  Pool mode (32 < k <= 128)
+// keeps no lists: rows above the seeded bound go to private regions.
+//
+// What leaves the kernel: per query a compact pool of the admitted rows that still reach the published bound
+// (KeyS: score, local row) and the final gthr[q].  Invariant used by the certificate (finalize_union_kernel):
+// a row that is not in the pool was rejected by, evicted below, or filtered against a value that was
+// published to gthr[q] -- a real row's L-th-best score, or some list's L-th best -- so its bf16 score is
+// <= the final gthr[q].
 #pragma once
 #include <cuda.h>
 
@@ -60,11 +66,11 @@ struct GemmParams {
     KeyS *lists;                 // [nq][list_stride]: every thread appends its valid entries (atomic cursor cnt[q])
     KeyS *regions;               // pool mode (L = 0): [nq][n_slices*2][region_cap] private append regions
     int region_cap;              // entries per private region; overflow sets bit 31 of cnt[q] (-> exact fix-up)
-    // in-kernel threshold seeding (list mode, main pass).  Before its slice every CTA scans the slice's first
-    // seed_tiles tiles in sampling mode (best score of every 32-row step), posts the best L of them per thread and
-    // bumps arrive[qblock]; once all n_slices CTAs of the block have posted, the epilogue warps of each CTA fold
-    // the posts of their share of the block's queries into gthr[q] (the L-th best post) and raise seeded[q]; every
-    // epilogue thread waits (bounded) for its own query's flag, then the slice is scanned with that bound.
+    // in-kernel threshold seeding.  Before its slice every CTA scans the slice's first seed_tiles tiles in sampling
+    // mode (best score of every 32-row step), posts its best few per thread and bumps arrive[qblock]; once all
+    // n_slices CTAs of the block have posted, the epilogue warps of each CTA fold the posts of their share of the
+    // block's queries into gthr[q] (the L-th best post; pool mode: the 32nd best) and raise seeded[q]; every epilogue
+    // thread waits (bounded) for its own query's word, then the slice is scanned with that bound.
     int seed_tiles;              // 0 = off
     int seed_stride;             // slices 0, stride, 2*stride, ... sample; the others post nothing (small shards in pool mode)
     unsigned *samples;           // [launch queries (padded to 128)][n_slices*2][2 .. L] ordered score keys, 0 = empty
