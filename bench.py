@@ -335,6 +335,36 @@ def run_gpu(args):
     assert int(h_cnt.min()) == k
     lat.sort()
     e2e_latency_us = {"p50": lat[len(lat) // 2] * 1e6, "max": lat[-1] * 1e6, "calls": len(lat)}
+    e2e_sync = e2e
+
+    # the same through the pipelined form of the call (b2r_query_async / b2r_wait): two batches in flight, the copies
+    # of one overlap the kernels of the other; every step still moves its own inputs and results inside the timed region
+    h_out = [(torch.empty((nq, k), dtype=torch.int64).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+              torch.empty((nq,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+
+    def run_pipelined(steps):
+        prev = None
+        for i in range(steps):
+            q = Qh[i % n_batches]
+            r_, d_, c_ = h_out[i % 2]
+            t = ctypes.c_uint64()
+            _lib.check(lib.b2r_query_async(shard.h, q.data_ptr(), nq, k, None, r_.data_ptr(), d_.data_ptr(), c_.data_ptr(),
+                                           stream, ctypes.byref(t)), "b2r_query_async")
+            if prev is not None:
+                _lib.check(lib.b2r_wait(shard.h, prev), "b2r_wait")
+            prev = t.value
+        _lib.check(lib.b2r_wait(shard.h, prev), "b2r_wait")
+
+    run_pipelined(W)
+    barrier()
+    t0 = time.perf_counter()
+    run_pipelined(K)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
+    e2e = world * nq * K / e2e_s
+    assert int(h_out[0][2].min()) == k and int(h_out[1][2].min()) == k
+    step_host(K - 1)                              # the blocking call on the last batch must give the same rows
+    assert torch.equal(h_out[(K - 1) % 2][0], h_rows)
 
     # ---- batch-1 scan (the HBM-bound headline of north_star), same corpus ----
     q1 = [q[:1].contiguous() for q in Qd]
@@ -362,6 +392,32 @@ def run_gpu(args):
               "roofline": {"bound": "hbm", "kernel": "gemm_topk_kernel (K3 streams the corpus for batch 1 too)", "achieved": corpus_bytes / (b1_kern_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                            "unit": "GB/s", "frac": corpus_bytes / (b1_kern_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                            "kernel_us": b1_kern_ms * 1e3, "peak_src": pk["src"]}}
+
+    # ---- configs[0]: the reference's own CPU-runnable case (10k x 384, one cosine query, top_k 5) on the GPU ----
+    config0 = None
+    if rank == 0:
+        c0 = DeviceShard(DIM, "cosine", capacity=10_000, row_base=0, device=local_rank)
+        g0 = torch.Generator(device=dev).manual_seed(0xC0)
+        c0.ingest(torch.nn.functional.normalize(torch.randn(10_000, DIM, generator=g0, device=dev), dim=1))
+
+        def step_c0(i):
+            q = q1[i % n_batches]
+            _lib.check(lib.b2r_query(c0.h, q.data_ptr(), 1, k, None, o1["rows"].data_ptr(), o1["dist"].data_ptr(),
+                                     o1["cnt"].data_ptr(), stream), "b2r_query")
+
+        for i in range(10):
+            step_c0(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(200):
+            step_c0(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us0 = e0.elapsed_time(e1) / 200 * 1e3
+        config0 = {"workload": "configs[0]: 10000x384, one cosine query, top_k=5 (latency-bound: 7.7 MB of corpus)",
+                   "us_per_query": us0, "qps": 1e6 / us0}
+        c0.close()
 
     if rank == 0 and len(sampler.lines) < 3:
         # the timed regions are a few milliseconds: keep the GPU under the same load until nvidia-smi has sampled it
@@ -457,6 +513,7 @@ def run_gpu(args):
                          "exhaustive fp32 scan (oracle/exact_topk.c, OpenMP)"}
         if not args.no_hnsw:
             cpu["hnsw"] = cpu_hnsw_leg(Xh, Qh[0].numpy(), k, HNSW_ROWS)
+            cpu["hnsw_config0"] = cpu_hnsw_leg(Xh, Qh[0].numpy(), k, 10_000)     # configs[0]: the reference's own size
         try:
             from oracle import exact_oracle as eo
             t0 = time.perf_counter()
@@ -492,9 +549,10 @@ def run_gpu(args):
                    "l2_policy": "corpus (768 MB) is larger than L2 (126 MB); query batches rotate",
                    "parallelism": "corpus replicated, queries sharded" if world > 1 else "single GPU"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nq * DIM * 4,
-                "d2h_bytes_per_step": nq * k * 12 + nq * 4, "latency_us_per_call": e2e_latency_us,
-                "transport": "pinned host buffers: one H2D copy of the query batch, kernels, ONE packed D2H copy, stream sync"},
-        "gpu_launches": gpu_launches, "roofline": roof, "batch1": batch1, "ingest": ingest, "clocks": clocks,
+                "d2h_bytes_per_step": nq * k * 12 + nq * 4, "api": "b2r_query_async + b2r_wait, two batches in flight (copies of one overlap the kernels of the other)",
+                "blocking_call": {"value": e2e_sync, "unit": UNIT, "latency_us_per_call": e2e_latency_us,
+                                  "api": "b2r_query with host arrays: H2D copy, kernels, ONE packed D2H copy, stream sync"}},
+        "gpu_launches": gpu_launches, "roofline": roof, "batch1": batch1, "ingest": ingest, "config0": config0, "clocks": clocks,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

@@ -150,6 +150,17 @@ int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b2r_filter *
                  int64_t *out_rows, float *out_dist, double *out_dist64, int32_t *out_count,
                  void *stream);
 
+/* Pipelined form of b2r_query for HOST buffers: returns as soon as the work is enqueued -- the query batch travels on
+ * an internal upload stream, the kernels run on `stream`, the results travel back on an internal download stream -- so that with two
+ * calls in flight the transfers of one overlap the kernels of the other (the reference fires its queries concurrently,
+ * app/utils/embedder.py:809-815; this is the batched equivalent).  q and the outputs are host arrays (page-locked
+ * arrays are used in place, pageable ones go through pinned mirrors) and must stay valid until b2r_wait(ticket)
+ * returns, which is also when the outputs are filled.  At most two tickets are outstanding per handle: a third call
+ * first completes the oldest.  A filter, if given, must only use device-resident or type-mask forms.                */
+int b2r_query_async(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter, int64_t *out_rows,
+                    float *out_dist, int32_t *out_count, void *stream, uint64_t *ticket_out);
+int b2r_wait(b2r_handle h, uint64_t ticket);
+
 /* replaces collection.get(ids, include=['embeddings']) (app/utils/embedder.py:887-891):
  * the stored fp32 rows (normalised in cosine space, as hnswlib stores them).         */
 int b2r_get_rows_f32(b2r_handle h, const int64_t *rows, int64_t n, float *out, void *stream);

@@ -20,7 +20,7 @@ ABI_SYMBOLS = (
     "b2r_abi_version", "b2r_last_error", "b2r_create", "b2r_destroy", "b2r_clear", "b2r_reserve",
     "b2r_ingest_f32", "b2r_tombstone", "b2r_query", "b2r_query_ex", "b2r_get_rows_f32", "b2r_count",
     "b2r_get_stats", "b2r_set_row_base", "b2r_merge_shards", "b2r_merge_shards_packed", "b2r_set_path", "b2r_launch_count",
-    "b2r_set_kernel_timing", "b2r_kernel_time_ms", "b2r_save", "b2r_load", "b2r_column_set", "b2r_filter_eval",
+    "b2r_set_kernel_timing", "b2r_kernel_time_ms", "b2r_save", "b2r_load", "b2r_column_set", "b2r_filter_eval", "b2r_query_async", "b2r_wait",
 )
 
 
@@ -89,6 +89,8 @@ def load() -> ctypes.CDLL:
         "b2r_load": (i32, [ctypes.c_char_p, i32, i64, ctypes.POINTER(vp)]),
         "b2r_column_set": (i32, [vp, i32, i64, i64, vp, vp]),
         "b2r_filter_eval": (i32, [vp, ctypes.POINTER(B2RFilter), vp, vp]),
+        "b2r_query_async": (i32, [vp, vp, i32, i32, ctypes.POINTER(B2RFilter), vp, vp, vp, vp, ctypes.POINTER(ctypes.c_uint64)]),
+        "b2r_wait": (i32, [vp, ctypes.c_uint64]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

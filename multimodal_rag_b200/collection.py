@@ -342,6 +342,38 @@ class B200Collection:
             del keep
             return (rows, dist, cnt, d64) if want_dist64 else (rows, dist, cnt)
 
+    def query_rows_pipelined(self, batches, n_results=10, where=None):
+        """Several query batches through the pipelined form of the call (b2r_query_async / b2r_wait): two batches in
+        flight, the host<->device copies of one overlap the kernels of the other.  `batches` = host arrays [nq_i, dim];
+        returns a list of (rows, dist, count) like `query_rows`.  Only unfiltered or `{"type": ...}` queries take this
+        route; any other clause is answered batch by batch."""
+        with self._lock:
+            if not isinstance(n_results, int) or isinstance(n_results, bool) or n_results <= 0:
+                raise ValueError(f"Expected n_results to be a positive integer, got {n_results}")
+            f, keep = self._filter(where)
+            if self._h is None or not self._row_of or f.allow_bits or f.where:
+                return [self.query_rows(b, n_results, where) for b in batches]
+            k, out, pending = n_results, [], []
+            for b in batches:
+                m = _Matrix(b, "query_embeddings")
+                if m.is_cuda:
+                    raise ValueError("query_rows_pipelined takes host batches; device batches only enqueue anyway")
+                if m.n == 0 or m.d != self._dim:
+                    raise ValueError(f"Query dimension {m.d} does not match collection dimensionality {self._dim}")
+                rows = np.empty((m.n, k), dtype=np.int64)
+                dist = np.empty((m.n, k), dtype=np.float32)
+                cnt = np.empty((m.n,), dtype=np.int32)
+                t = ctypes.c_uint64()
+                _lib.check(self._lib.b2r_query_async(self._h, m.ptr, m.n, k, ctypes.byref(f), rows.ctypes.data,
+                                                     dist.ctypes.data, cnt.ctypes.data, 0, ctypes.byref(t)), "b2r_query_async")
+                pending.append((t.value, m))                      # keep the batch alive until its ticket is waited for
+                out.append((rows, dist, cnt))
+                if len(pending) == 2:
+                    _lib.check(self._lib.b2r_wait(self._h, pending.pop(0)[0]), "b2r_wait")
+            for t, _ in pending:
+                _lib.check(self._lib.b2r_wait(self._h, t), "b2r_wait")
+            return out
+
     def query(self, query_embeddings=None, n_results=10, where=None, where_document=None,
               include=_INCLUDE_QUERY, query_texts=None):
         """Chroma ``Collection.query``: nested lists, one inner list per query, ascending

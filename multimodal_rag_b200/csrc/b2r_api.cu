@@ -194,6 +194,14 @@ extern "C" int b2r_destroy(b2r_handle h) {
                       &h->gemm_samples, &h->q_eps, &h->where_lut, &h->where_bits, &h->col_stage};
     for (DevBuf *b : bufs) release(*b);
     if (h->o_host) cudaFreeHost(h->o_host);
+    for (auto &sl : h->aslot) {
+        release(sl.q_dev); release(sl.o_dev);
+        if (sl.in_host) cudaFreeHost(sl.in_host);
+        if (sl.out_host) cudaFreeHost(sl.out_host);
+        if (sl.ev_h2d) { cudaEventDestroy(sl.ev_h2d); cudaEventDestroy(sl.ev_kernels); cudaEventDestroy(sl.ev_d2h); }
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->copy_stream_out) cudaStreamDestroy(h->copy_stream_out);
     for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     delete h;
@@ -824,15 +832,14 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
 
 }  // namespace
 
-extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
-                            int64_t *out_rows, float *out_dist, double *out_dist64, int32_t *out_count,
-                            void *stream) {
-    B2R_REQUIRE(h, "b2r_query: NULL handle");
+// the query itself; the caller holds h->mu
+static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
+                        int64_t *out_rows, float *out_dist, double *out_dist64, int32_t *out_count,
+                        void *stream) {
     B2R_REQUIRE(nq >= 1 && q, "b2r_query: need at least one query");
     B2R_REQUIRE(k >= 1, "b2r_query: n_results must be a positive integer");
     B2R_REQUIRE(out_rows && out_dist && out_count, "b2r_query: NULL output");
     if (epl_exact(k) == 0) { set_error("b2r_query: k > 256 is not supported"); return B2R_EUNSUPPORTED; }
-    std::lock_guard<std::mutex> g(h->mu);
     B2R_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     const bool dev_out = is_device_ptr(out_rows);
@@ -963,9 +970,117 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     return B2R_OK;
 }
 
+extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
+                            int64_t *out_rows, float *out_dist, double *out_dist64, int32_t *out_count,
+                            void *stream) {
+    B2R_REQUIRE(h, "b2r_query: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    return query_locked(h, q, nq, k, filter, out_rows, out_dist, out_dist64, out_count, stream);
+}
+
 extern "C" int b2r_query(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
                          int64_t *out_rows, float *out_dist, int32_t *out_count, void *stream) {
     return b2r_query_ex(h, q, nq, k, filter, out_rows, out_dist, nullptr, out_count, stream);
+}
+
+// ---------------------------------------------------------------------------------
+// pipelined host-buffer queries
+// ---------------------------------------------------------------------------------
+namespace {
+// results of a finished slot -> the caller's arrays; the slot becomes free.  h->mu held, ev_d2h already reached.
+void async_deliver(b2r_index::AsyncSlot &sl) {
+    const size_t nk = (size_t)sl.nq * sl.k;
+    const char *b = (const char *)sl.out_host;
+    std::memcpy(sl.u_rows, b, nk * 8);
+    std::memcpy(sl.u_dist, b + nk * 8, nk * 4);
+    std::memcpy(sl.u_count, b + nk * 12, (size_t)sl.nq * 4);
+    sl.ticket = 0;
+}
+int pinned_grow(void **p, size_t *have, size_t want) {
+    if (*have >= want) return B2R_OK;
+    if (*p) { cudaFreeHost(*p); *p = nullptr; *have = 0; }
+    want = std::max(want, (size_t)4096);
+    B2R_CUDA(cudaHostAlloc(p, want, cudaHostAllocDefault));
+    *have = want;
+    return B2R_OK;
+}
+bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+extern "C" int b2r_query_async(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter, int64_t *out_rows,
+                               float *out_dist, int32_t *out_count, void *stream, uint64_t *ticket_out) {
+    B2R_REQUIRE(h && ticket_out, "b2r_query_async: NULL argument");
+    B2R_REQUIRE(nq >= 1 && q && k >= 1 && out_rows && out_dist && out_count, "b2r_query_async: bad arguments");
+    B2R_REQUIRE(!is_device_ptr(q) && !is_device_ptr(out_rows) && !is_device_ptr(out_dist) && !is_device_ptr(out_count),
+                "b2r_query_async: buffers must be host arrays (device buffers: b2r_query only enqueues anyway)");
+    B2R_REQUIRE(!filter || ((!filter->allow_bits || is_device_ptr(filter->allow_bits)) && !filter->where),
+                "b2r_query_async: only type-mask or device-resident filters");
+    std::unique_lock<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    // one stream per direction: on a single copy stream the next batch's upload would queue behind this batch's
+    // download, which waits for this batch's kernels -- and nothing would overlap
+    if (!h->copy_stream) B2R_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->copy_stream_out) B2R_CUDA(cudaStreamCreateWithFlags(&h->copy_stream_out, cudaStreamNonBlocking));
+    // the slot: a free one, else the older of the two is completed first
+    int si = h->aslot[0].ticket == 0 ? 0 : h->aslot[1].ticket == 0 ? 1 : (h->aslot[0].ticket < h->aslot[1].ticket ? 0 : 1);
+    b2r_index::AsyncSlot &sl = h->aslot[si];
+    if (sl.ticket != 0) {
+        B2R_CUDA(cudaEventSynchronize(sl.ev_d2h));
+        async_deliver(sl);
+    }
+    if (!sl.ev_h2d) {
+        B2R_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+        B2R_CUDA(cudaEventCreateWithFlags(&sl.ev_kernels, cudaEventDisableTiming));
+        B2R_CUDA(cudaEventCreateWithFlags(&sl.ev_d2h, cudaEventDisableTiming));
+    }
+    const size_t q_bytes = (size_t)nq * h->dim * 4, nk = (size_t)nq * k, o_bytes = nk * 12 + (size_t)nq * 4;
+    int rc;
+    if ((rc = ensure(sl.q_dev, q_bytes)) != B2R_OK) return rc;
+    if ((rc = ensure(sl.o_dev, o_bytes)) != B2R_OK) return rc;
+    if ((rc = pinned_grow(&sl.out_host, &sl.out_bytes, o_bytes)) != B2R_OK) return rc;
+    const void *src = q;
+    if (!is_pinned_host(q)) {                 // pageable: through the pinned mirror (a host memcpy, hidden behind the GPU's work)
+        if ((rc = pinned_grow(&sl.in_host, &sl.in_bytes, q_bytes)) != B2R_OK) return rc;
+        std::memcpy(sl.in_host, q, q_bytes);
+        src = sl.in_host;
+    }
+    B2R_CUDA(cudaMemcpyAsync(sl.q_dev.p, src, q_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    B2R_CUDA(cudaEventRecord(sl.ev_h2d, h->copy_stream));
+    B2R_CUDA(cudaStreamWaitEvent(s, sl.ev_h2d, 0));
+    char *ob = (char *)sl.o_dev.p;
+    rc = query_locked(h, (const float *)sl.q_dev.p, nq, k, filter, (int64_t *)ob, (float *)(ob + nk * 8), nullptr,
+                      (int32_t *)(ob + nk * 12), stream);
+    if (rc != B2R_OK) return rc;
+    B2R_CUDA(cudaEventRecord(sl.ev_kernels, s));
+    B2R_CUDA(cudaStreamWaitEvent(h->copy_stream_out, sl.ev_kernels, 0));
+    B2R_CUDA(cudaMemcpyAsync(sl.out_host, sl.o_dev.p, o_bytes, cudaMemcpyDeviceToHost, h->copy_stream_out));
+    B2R_CUDA(cudaEventRecord(sl.ev_d2h, h->copy_stream_out));
+    sl.ticket = h->next_ticket++;
+    sl.u_rows = out_rows; sl.u_dist = out_dist; sl.u_count = out_count; sl.nq = nq; sl.k = k;
+    *ticket_out = sl.ticket;
+    return B2R_OK;
+}
+
+extern "C" int b2r_wait(b2r_handle h, uint64_t ticket) {
+    B2R_REQUIRE(h, "b2r_wait: NULL handle");
+    std::unique_lock<std::mutex> g(h->mu);
+    B2R_CUDA(cudaSetDevice(h->device));
+    for (int si = 0; si < 2; ++si) {
+        b2r_index::AsyncSlot &sl = h->aslot[si];
+        if (sl.ticket != ticket || ticket == 0) continue;
+        cudaEvent_t ev = sl.ev_d2h;
+        g.unlock();                               // other threads may enqueue while this one waits
+        B2R_CUDA(cudaEventSynchronize(ev));
+        g.lock();
+        if (sl.ticket == ticket) async_deliver(sl);   // (a third call may have completed it meanwhile)
+        return B2R_OK;
+    }
+    return B2R_OK;                                // already delivered
 }
 
 // ---------------------------------------------------------------------------------

@@ -120,5 +120,19 @@ struct b2r_index {
     double scoring_ms = 0.0;
     int64_t scoring_launches = 0;
 
+    // pipelined queries with host buffers (b2r_query_async / b2r_wait): two slots, each with its own device staging
+    // and pinned mirrors, copies on an internal stream so that the transfers of one call overlap the kernels of another
+    struct AsyncSlot {
+        b2r::DevBuf q_dev, o_dev;
+        void *in_host = nullptr, *out_host = nullptr;       // pinned mirrors (in: pageable queries are staged through it)
+        size_t in_bytes = 0, out_bytes = 0;
+        cudaEvent_t ev_h2d = nullptr, ev_kernels = nullptr, ev_d2h = nullptr;
+        uint64_t ticket = 0;                                 // 0 = free
+        int64_t *u_rows = nullptr; float *u_dist = nullptr; int32_t *u_count = nullptr;   // the caller's host arrays
+        int nq = 0, k = 0;
+    } aslot[2];
+    cudaStream_t copy_stream = nullptr, copy_stream_out = nullptr;   // uploads / downloads
+    uint64_t next_ticket = 1;
+
     std::mutex mu;
 };
