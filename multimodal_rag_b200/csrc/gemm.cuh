@@ -591,7 +591,7 @@ __device__ __forceinline__ unsigned warp_lth_largest(const unsigned *vals, int n
     unsigned top[L];
 #pragma unroll
     for (int i = 0; i < L; ++i) top[i] = 0u;
-    constexpr int UN = 8;                                // independent L2 loads in flight per lane
+    constexpr int UN = 16;                               // independent L2 loads in flight per lane (the usual 296-592 posts: one or two rounds)
     for (int b = lane; b < n; b += 32 * UN) {
         unsigned x[UN];
 #pragma unroll
