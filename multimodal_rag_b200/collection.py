@@ -92,6 +92,7 @@ class B200Collection:
         self._row_of: dict[str, int] = {}
         self._meta = MetaTable()
         self.device_where = True      # general where clauses run on the device (False: host-evaluated bitmaps)
+        self._where_cache: dict = {}  # (clause as JSON, table rows) -> compiled clause
         if dimension is not None:
             self._open(int(dimension))
 
@@ -294,14 +295,29 @@ class B200Collection:
         if tm is not None:
             f.type_mask = tm
             return f, None
-        prog = self._meta.compile(where) if self.device_where else None
-        if prog is not None:                 # the clause runs on the device against the metadata columns
-            nodes, lut = prog
-            w = _lib.B2RWhere(n_nodes=len(nodes), lut=lut.ctypes.data if lut.size else None, lut_words=int(lut.size))
-            for i, (op, col, off, nv) in enumerate(nodes):
-                w.nodes[i] = _lib.B2RWhereNode(op, col, off, nv)
-            f.where = ctypes.pointer(w)
-            return f, (w, lut)
+        if self.device_where:                # the clause runs on the device against the metadata columns
+            # compiled clauses are kept while the table does not grow (a chat session repeats its filter; the device
+            # side recognises the repeat by the clause's hash and re-uses its bitmaps)
+            try:
+                key = (json.dumps(where, sort_keys=True, default=repr), self._meta.nrows)
+            except (TypeError, ValueError):
+                key = None
+            hit = self._where_cache.get(key) if key is not None else None
+            if hit is None:
+                prog = self._meta.compile(where)
+                if prog is not None:
+                    nodes, lut = prog
+                    w = _lib.B2RWhere(n_nodes=len(nodes), lut=lut.ctypes.data if lut.size else None, lut_words=int(lut.size))
+                    for i, (op, col, off, nv) in enumerate(nodes):
+                        w.nodes[i] = _lib.B2RWhereNode(op, col, off, nv)
+                    hit = (w, lut)
+                    if key is not None:
+                        if len(self._where_cache) >= 64:
+                            self._where_cache.clear()
+                        self._where_cache[key] = hit
+            if hit is not None:
+                f.where = ctypes.pointer(hit[0])
+                return f, hit
         bits = pack_bits(self._meta.mask(where))      # clause the device cannot run: host-evaluated bitmap
         f.allow_bits = bits.ctypes.data
         return f, bits

@@ -501,6 +501,21 @@ int run_where(b2r_index *h, const b2r_where *w, const uint32_t *allow_dev, unsig
     return B2R_OK;
 }
 
+// identity of a compiled clause with host-resident tables: FNV-1a over nodes and tables (never 0)
+uint64_t where_key(const b2r_where *w) {
+    if (!w || w->n_nodes < 1 || w->n_nodes > B2R_WHERE_MAX_NODES || w->lut_words < 0 || (w->lut_words && is_device_ptr(w->lut))) return 0;
+    uint64_t hsh = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) {
+        const unsigned char *b = (const unsigned char *)p;
+        for (size_t i = 0; i < n; ++i) { hsh ^= b[i]; hsh *= 1099511628211ull; }
+    };
+    mix(&w->n_nodes, sizeof(w->n_nodes));
+    mix(w->nodes, sizeof(b2r_where_node) * (size_t)w->n_nodes);
+    mix(&w->lut_words, sizeof(w->lut_words));
+    if (w->lut_words) mix(w->lut, (size_t)w->lut_words * 4);
+    return hsh ? hsh : 1;
+}
+
 // host allow bitmap -> h->allow (device)
 int stage_allow(b2r_index *h, const b2r_filter &f, const uint32_t **allow_dev, cudaStream_t s) {
     *allow_dev = f.allow_bits;
@@ -530,6 +545,7 @@ extern "C" int b2r_filter_eval(b2r_handle h, const b2r_filter *filter, uint32_t 
     if ((rc = stage_allow(h, f, &allow_dev, s)) != B2R_OK) return rc;
     if (f.where) {
         if ((rc = run_where(h, f.where, allow_dev, n_words, s)) != B2R_OK) return rc;
+        h->wb_key = 0;                           // the remembered clause bitmap lived here
         allow_dev = (const uint32_t *)h->where_bits.p;
     }
     const bool dev_out = is_device_ptr(out_bits);
@@ -746,7 +762,7 @@ constexpr int GEMM_REGION_CAP = 256;       // pool mode: entries per private (qu
 constexpr int GEMM_POOL_CAP = 16384;        // pool mode: compact pool entries per query (>= SMs*2*32 for the sampling pass)
 
 int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams &fin, const b2r_filter &f,
-                      const uint32_t *allow_dev, cudaStream_t s) {
+                      const uint32_t *allow_dev, uint64_t filter_key, cudaStream_t s) {
     const int L = gemm_list_len(k);                    // 8 / 16 / 32, or 0 = pool mode (32 < k <= 128)
     const bool pool_mode = L == 0;
     const int L_seed = pool_mode ? GEMM_POOL_SAMPLE_RANK : L;     // rank of the sampled score that becomes the bound
@@ -767,14 +783,16 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
     if (pool_mode &&
         (rc = ensure(h->gemm_regions, sizeof(KeyS) * (size_t)nq_launch_max * h->sm_count * GEMM_HALVES * GEMM_REGION_CAP)) != B2R_OK)
         return rc;
-    const bool pb_hit = !allow_dev && h->pb_buf == h->pass_bits.p && h->pb_gen == h->mut_gen && h->pb_rows == h->rows &&
-                        h->pb_mask == f.type_mask && h->pb_bn == BN;
+    // cacheable: no bitmap at all (key 0), or a remembered clause's bitmap (its hash); a caller's own allow bitmap is not
+    const bool cacheable = !allow_dev || filter_key != 0;
+    const bool pb_hit = cacheable && h->pb_buf == h->pass_bits.p && h->pb_gen == h->mut_gen && h->pb_rows == h->rows &&
+                        h->pb_mask == f.type_mask && h->pb_bn == BN && h->pb_key == filter_key;
     if (!pb_hit) {
         B2R_CUDA(pass_bits_launch(h->type_code, f.type_mask, allow_dev, (unsigned)h->rows, n_words,
                                   (uint32_t *)h->pass_bits.p, h->sm_count, s));
         h->n_launches++;
-        h->pb_buf = allow_dev ? nullptr : h->pass_bits.p;
-        h->pb_gen = h->mut_gen; h->pb_rows = h->rows; h->pb_mask = f.type_mask; h->pb_bn = BN;
+        h->pb_buf = cacheable ? h->pass_bits.p : nullptr;
+        h->pb_gen = h->mut_gen; h->pb_rows = h->rows; h->pb_mask = f.type_mask; h->pb_bn = BN; h->pb_key = filter_key;
     }
     if (h->tm_corpus_base != h->corpus || h->tm_corpus_rows != h->capacity) {
         if ((rc = gemm_encode_map(&h->tm_corpus, h->corpus, h->dp, (uint64_t)h->capacity, BN)) != B2R_OK) return rc;
@@ -863,9 +881,17 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
     }
     const uint32_t *allow_dev = nullptr;
     if ((rc = stage_allow(h, f, &allow_dev, s)) != B2R_OK) return rc;
-    const bool staged_host_filter = (f.allow_bits && allow_dev != f.allow_bits) || (f.where && f.where->lut_words > 0 && !is_device_ptr(f.where->lut));
+    bool staged_host_filter = (f.allow_bits && allow_dev != f.allow_bits);
+    // A clause on its own (no allow bitmap beside it) is remembered by its hash: a session that keeps asking with the same
+    // filter re-uses the clause bitmap and the pass bitmap until rows / tombstones / columns change (mut_gen).
+    uint64_t filter_key = (f.where && !f.allow_bits) ? where_key(f.where) : 0;
     if (f.where && h->rows > 0) {     // compiled clause -> device bitmap (ANDed with the allow bitmap), then it IS the allow bitmap
-        if ((rc = run_where(h, f.where, allow_dev, (unsigned)((h->rows + 31) / 32), s)) != B2R_OK) return rc;
+        const bool hit = filter_key && h->wb_key == filter_key && h->wb_gen == h->mut_gen && h->wb_rows == h->rows && h->where_bits.p;
+        if (!hit) {
+            if ((rc = run_where(h, f.where, allow_dev, (unsigned)((h->rows + 31) / 32), s)) != B2R_OK) return rc;
+            h->wb_key = filter_key; h->wb_gen = h->mut_gen; h->wb_rows = h->rows;
+            staged_host_filter = staged_host_filter || (f.where->lut_words > 0 && !is_device_ptr(f.where->lut));
+        }
         allow_dev = (const uint32_t *)h->where_bits.p;
     }
     if ((rc = ensure(h->q_prep, (size_t)nq * h->dp * 4)) != B2R_OK) return rc;
@@ -952,7 +978,7 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
         if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
     } else if (path == 2) {
         // candidates kept by the finalize: KP = 32 / 64 / 128 / 128 / 256 for k <= 8 / 16 / 32 / 64 / 128 (>= 2k beyond 8)
-        if ((rc = launch_gemm_batch(h, nq, k, k <= 8 ? 1 : k <= 16 ? 2 : k <= 64 ? 4 : 8, fin, f, allow_dev, s)) != B2R_OK) return rc;
+        if ((rc = launch_gemm_batch(h, nq, k, k <= 8 ? 1 : k <= 16 ? 2 : k <= 64 ? 4 : 8, fin, f, allow_dev, filter_key, s)) != B2R_OK) return rc;
         if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
     } else {
         if ((rc = launch_exact_batch(h, nq, k, 1, fin, f, allow_dev, s)) != B2R_OK) return rc;

@@ -107,6 +107,8 @@ struct b2r_index {
     const void *tm_query_base = nullptr; int64_t tm_query_rows = -1;
     // the pass bitmap is reused while (rows, type mask, tombstones) are unchanged and no allow bitmap is given
     int64_t mut_gen = 0, pb_gen = -1, pb_rows = -1; unsigned long long pb_mask = 0; const void *pb_buf = nullptr; int pb_bn = 0;
+    // ... and so is a compiled clause's bitmap: filter_key = hash of the clause (0 = no clause), kept with the bitmaps it produced
+    uint64_t pb_key = 0, wb_key = 0; int64_t wb_gen = -1, wb_rows = -1;
     unsigned *tickets = nullptr;    // [1 + 2*EXACT_MAX_BATCH]: scan ticket, exact tickets, exact slot generations
 
     // optional per-kernel timing (bench.py roofline): CUDA events recorded around the scoring

@@ -131,3 +131,40 @@ def test_malformed_programs_are_rejected(coll):
     assert run([(_lib.WHERE_LEAF, 99, 0, 0)]) == _lib.B2R_EINVAL                                # column out of range
     assert run([(_lib.WHERE_LEAF, 0, 0, 64)]) == _lib.B2R_EINVAL                                # table outside lut
     assert run([(_lib.WHERE_LEAF, 0, 0, 0)]) == _lib.B2R_OK and not out.any()                   # empty table: nothing passes
+
+
+def test_repeated_clause_reuses_its_bitmaps(coll):
+    """A session that keeps asking with the same filter pays for the clause once: the clause bitmap and the pass bitmap
+    are remembered by the clause's hash until rows, tombstones or columns change."""
+    from oracle import exact_oracle as eo
+    c, X, metas, alive = coll
+    where = {"$and": [{"type": "text"}, {"page": {"$lte": 6}}]}
+    other = {"$and": [{"type": "text"}, {"page": {"$lte": 5}}]}
+    Q = make_unit(12, 384, 21)
+    c.set_path(2)
+
+    def launches(w):
+        before = c.stats()["launches"]
+        out = c.query_rows(Q, 5, w)
+        return c.stats()["launches"] - before, out
+
+    n1, r1 = launches(where)
+    n2, r2 = launches(where)
+    assert n2 == n1 - 2, (n1, n2)                      # no clause kernel, no pass-bitmap kernel the second time
+    np.testing.assert_array_equal(r1[0], r2[0])
+    n3, r3 = launches(other)                            # a different clause is evaluated again ...
+    assert n3 == n1
+    mask = np.array([eo.where_match(m, other) for m in metas]) & alive
+    er, _ = eo.topk_exact(eo.normalize_f32(Q), eo.normalize_f32(X), 5, "cosine", allowed=mask)
+    for i in range(Q.shape[0]):
+        np.testing.assert_array_equal(r3[0][i, : r3[2][i]], er[i])
+    n4, r4 = launches(where)                            # ... and so is the first one after it
+    assert n4 == n1
+    np.testing.assert_array_equal(r4[0], r1[0])
+    # a mutation invalidates: delete the best hit of query 0, the next answer must not contain it
+    victim = int(r1[0][0, 0])
+    c.delete(ids=[f"id{victim}"])
+    alive[victim] = False
+    n5, r5 = launches(where)
+    assert n5 >= n1 and victim not in r5[0][0]
+    c.set_path(0)
