@@ -192,7 +192,9 @@ class B200Collection:
             ci = self._meta.device_column(key)
             if ci is None:
                 continue
-            codes = np.ascontiguousarray(self._meta.cols[key].codes[first: first + n], dtype=np.int32)
+            have = self._meta.cols[key].codes[first: first + n]      # the column may end before the batch does
+            codes = np.full(n, -1, dtype=np.int32)
+            codes[: have.shape[0]] = have
             _lib.check(self._lib.b2r_column_set(self._h, ci, first, n, codes.ctypes.data, 0), "b2r_column_set")
 
     def _kill_rows(self, rows):

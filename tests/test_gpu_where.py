@@ -168,3 +168,22 @@ def test_repeated_clause_reuses_its_bitmaps(coll):
     n5, r5 = launches(where)
     assert n5 >= n1 and victim not in r5[0][0]
     c.set_path(0)
+
+
+def test_sparse_keys_that_end_before_the_batch_does():
+    """A key carried by the first row of a batch only: its host column is shorter than the batch, the device column
+    must still be written for the whole batch (-1 = absent) and later batches must not inherit anything."""
+    from multimodal_rag_b200 import B200Collection
+    n = 3000
+    X = make_unit(2 * n, 384, 12)
+    c = B200Collection("sparse", {"hnsw:space": "cosine"})
+    c.add(ids=[f"a{i}" for i in range(n)], embeddings=X[:n], metadatas=[{"first": 1} if i == 0 else {"other": i % 3} for i in range(n)])
+    c.add(ids=[f"b{i}" for i in range(n)], embeddings=X[n:], metadatas=[{"late": True} if i == n - 1 else None for i in range(n)])
+    want_first = np.zeros(2 * n, dtype=bool); want_first[0] = True
+    want_late = np.zeros(2 * n, dtype=bool); want_late[2 * n - 1] = True
+    np.testing.assert_array_equal(c.filter_bits({"first": 1}), want_first)
+    np.testing.assert_array_equal(c.filter_bits({"late": True}), want_late)
+    np.testing.assert_array_equal(c.filter_bits({"other": {"$in": [0, 1, 2]}}), (np.arange(2 * n) > 0) & (np.arange(2 * n) < n))
+    r = c.query(query_embeddings=X[5:6].tolist(), n_results=3, where={"first": 1})
+    assert r["ids"] == [["a0"]]
+    c.close()
