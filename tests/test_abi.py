@@ -88,3 +88,34 @@ def test_load_rejects_non_shard_files_without_a_gpu(tmp_path):
     assert b"not a b2r shard file" in lib.b2r_last_error()
     with pytest.raises(ValueError):
         _lib.check(lib.b2r_load(str(bad).encode(), 0, 0, ctypes.byref(h)))
+
+
+def test_load_validates_the_header_before_touching_the_device(tmp_path):
+    """Shard file header (include/b2r.h): 128 bytes = "B2RS", version, dim, padded dim, space, flags,
+    rows, live, row base, two norms, checksum, payload bytes.  Every inconsistency is EINVAL, with or without a GPU."""
+    import ctypes
+    import struct
+    from multimodal_rag_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+
+    def header(version=1, dim=384, dp=384, space=1, flags=0, rows=10, live=10, payload=None):
+        if payload is None:
+            payload = max(0, rows * dp * 2 + rows * dp * 4 + rows)    # corpus + master + type codes (cosine: no bias)
+        b = b"B2RS" + struct.pack("<IiiiIqqq", version, dim, dp, space, flags, rows, live, 0) + struct.pack("<ff", 1.0, 1e-6)
+        b += struct.pack("<QQ", 0, payload)
+        return b + bytes(128 - len(b))
+
+    def load(blob):
+        p = tmp_path / "x.b2r"
+        p.write_bytes(blob)
+        rc = lib.b2r_load(str(p).encode(), 0, 0, ctypes.byref(h))
+        return rc, lib.b2r_last_error()
+
+    assert len(header()) == 128
+    assert load(header(version=7)) == (_lib.B2R_EINVAL, b"b2r_load: unknown shard file version")
+    for bad in (header(dim=0), header(dp=400), header(space=5), header(rows=-1), header(rows=3, live=4)):
+        rc, msg = load(bad)
+        assert rc == _lib.B2R_EINVAL and b"corrupt header" in msg
+    rc, msg = load(header(payload=12345))
+    assert rc == _lib.B2R_EINVAL and b"payload size" in msg
