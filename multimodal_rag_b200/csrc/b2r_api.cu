@@ -423,42 +423,56 @@ struct WhereProg {
     const int32_t *cols[B2R_MAX_COLUMNS];     // nullptr: no row carries this key
 };
 
-// One thread per row, one output word per warp.  The clause is a postfix program over look-up-table leaves, the
-// same for every row, so control flow is uniform; the operand stack is a bit field in one register.
+// One warp = 128 consecutive rows per step (lane handles rows lane, lane+32, lane+64, lane+96 of the group: four coalesced
+// loads per leaf in flight), one output word per 32 rows.  The clause is a postfix program over look-up-table leaves, the
+// same for every row, so control flow is uniform; the operand stacks are bit fields in registers.
 __global__ void __launch_bounds__(256)
 where_bits_kernel(const WhereProg prog, const uint32_t *__restrict__ lut, const uint32_t *__restrict__ allow_in,
                   unsigned n, unsigned n_words, uint32_t *__restrict__ out) {
-    const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned nthreads = gridDim.x * blockDim.x;
-    for (unsigned long long r = gt; r < (unsigned long long)n_words * 32; r += nthreads) {
-        bool ok = r < n;
-        if (ok) {
-            unsigned stack = 0;
-            int sp = 0;
-            for (int i = 0; i < prog.n_nodes; ++i) {
-                const b2r_where_node nd = prog.node[i];
-                if (nd.op == B2R_WHERE_LEAF) {
-                    unsigned bit = 0;
-                    const int32_t *col = prog.cols[nd.column];
-                    if (col) {
-                        const int code = col[r];
-                        if (code >= 0 && (unsigned)code < nd.lut_values) bit = (lut[nd.lut_offset + ((unsigned)code >> 5)] >> (code & 31)) & 1u;
-                    }
-                    stack |= bit << sp;
-                    ++sp;
-                } else {
-                    const unsigned a = (stack >> (sp - 1)) & 1u, b = (stack >> (sp - 2)) & 1u;
-                    const unsigned v = nd.op == B2R_WHERE_AND ? (a & b) : (a | b);
-                    sp -= 2;
-                    stack = (stack & ~(3u << sp)) | (v << sp);
-                    ++sp;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x / 32);
+    const unsigned long long total = (unsigned long long)n_words * 32;
+    for (unsigned long long base = gw * 128; base < total; base += nw * 128) {
+        unsigned stack[4] = {0u, 0u, 0u, 0u};
+        int sp = 0;
+        for (int i = 0; i < prog.n_nodes; ++i) {
+            const b2r_where_node nd = prog.node[i];
+            if (nd.op == B2R_WHERE_LEAF) {
+                const int32_t *col = prog.cols[nd.column];
+                int code[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned long long r = base + lane + 32u * j;
+                    code[j] = (col && r < n) ? col[r] : -1;
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    unsigned bit = 0;
+                    if (code[j] >= 0 && (unsigned)code[j] < nd.lut_values)
+                        bit = (lut[nd.lut_offset + ((unsigned)code[j] >> 5)] >> (code[j] & 31)) & 1u;
+                    stack[j] |= bit << sp;
+                }
+                ++sp;
+            } else {
+                sp -= 2;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned a = (stack[j] >> (sp + 1)) & 1u, b = (stack[j] >> sp) & 1u;
+                    const unsigned v = nd.op == B2R_WHERE_AND ? (a & b) : (a | b);
+                    stack[j] = (stack[j] & ~(3u << sp)) | (v << sp);
+                }
+                ++sp;
             }
-            ok = (stack & 1u) != 0u;
-            if (allow_in) ok = ok && ((allow_in[r >> 5] >> (r & 31)) & 1u);
         }
-        const unsigned w = __ballot_sync(FULL_MASK, ok);
-        if ((threadIdx.x & 31) == 0) out[r >> 5] = w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned long long r = base + lane + 32u * j;
+            bool ok = r < n && (stack[j] & 1u);
+            if (ok && allow_in) ok = (allow_in[r >> 5] >> (r & 31)) & 1u;
+            const unsigned w = __ballot_sync(FULL_MASK, ok);
+            if (lane == 0 && r < total) out[r >> 5] = w;
+        }
     }
 }
 
@@ -494,7 +508,7 @@ int run_where(b2r_index *h, const b2r_where *w, const uint32_t *allow_dev, unsig
         lut_dev = (const uint32_t *)h->where_lut.p;
     }
     if ((rc = ensure(h->where_bits, (size_t)std::max(n_words, 1u) * 4)) != B2R_OK) return rc;
-    const unsigned blocks = std::max(1u, std::min((n_words * 32 + 255) / 256, (unsigned)h->sm_count * 8));
+    const unsigned blocks = std::max(1u, std::min((n_words * 32 + 1023) / 1024, (unsigned)h->sm_count * 8));   // 8 warps x 128 rows per block and step
     where_bits_kernel<<<blocks, 256, 0, s>>>(prog, lut_dev, allow_dev, (unsigned)h->rows, n_words, (uint32_t *)h->where_bits.p);
     B2R_CUDA(cudaGetLastError());
     h->n_launches++;
