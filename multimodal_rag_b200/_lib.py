@@ -21,6 +21,7 @@ ABI_SYMBOLS = (
     "b2r_ingest_f32", "b2r_tombstone", "b2r_query", "b2r_query_ex", "b2r_get_rows_f32", "b2r_count",
     "b2r_get_stats", "b2r_set_row_base", "b2r_merge_shards", "b2r_merge_shards_packed", "b2r_set_path", "b2r_launch_count",
     "b2r_set_kernel_timing", "b2r_kernel_time_ms", "b2r_save", "b2r_load", "b2r_column_set", "b2r_filter_eval", "b2r_query_async", "b2r_wait",
+    "b2r_debug_trace",
 )
 
 
@@ -91,6 +92,7 @@ def load() -> ctypes.CDLL:
         "b2r_filter_eval": (i32, [vp, ctypes.POINTER(B2RFilter), vp, vp]),
         "b2r_query_async": (i32, [vp, vp, i32, i32, ctypes.POINTER(B2RFilter), vp, vp, vp, vp, ctypes.POINTER(ctypes.c_uint64)]),
         "b2r_wait": (i32, [vp, ctypes.c_uint64]),
+        "b2r_debug_trace": (i32, [vp, vp, i32, ctypes.POINTER(ctypes.c_int)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -163,16 +163,20 @@ extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device,
     h->seed_min_batch = GEMM_SEED_MIN_BATCH;
     if (const char *e = getenv("B2R_SEED_MIN_BATCH")) h->seed_min_batch = atoi(e);
     if (const char *e = getenv("B2R_SEED_TILES")) h->seed_tiles_override = atoi(e);   // development: seeding tiles per CTA
+    if (const char *e = getenv("B2R_SEED_WAIT_NS")) h->seed_wait_ns = strtoull(e, nullptr, 10);
+    if (const char *e = getenv("B2R_DELAY_US")) h->delay_us = atoi(e);
+    if (const char *e = getenv("B2R_POOL_SAMPLE_DIV")) h->pool_sample_div = std::max(1, atoi(e));
+    if (const char *e = getenv("B2R_TRACE")) h->trace_on = atoi(e) != 0;
     int rc = B2R_OK;
     do {
         if (cudaMalloc(&h->max_norm2, 256) != cudaSuccess || cudaMalloc(&h->counters, 256) != cudaSuccess ||
-            cudaMalloc(&h->tickets, sizeof(unsigned) * (1 + 2 * EXACT_MAX_BATCH)) != cudaSuccess ||
+            cudaMalloc(&h->tickets, sizeof(unsigned) * (1 + EXACT_MAX_SLOTS)) != cudaSuccess ||
             cudaMalloc(&h->need_ctl, 16) != cudaSuccess) {
             set_error("b2r_create: cudaMalloc failed"); rc = B2R_ENOMEM; break;
         }
         cudaMemset(h->max_norm2, 0, 256);
         cudaMemset(h->counters, 0, 256);
-        cudaMemset(h->tickets, 0, sizeof(unsigned) * (1 + 2 * EXACT_MAX_BATCH));
+        cudaMemset(h->tickets, 0, sizeof(unsigned) * (1 + EXACT_MAX_SLOTS));
         cudaMemset(h->need_ctl, 0, 16);
         rc = grow(h, std::max<int64_t>(capacity_rows, 1024), 0);
     } while (0);
@@ -191,7 +195,7 @@ extern "C" int b2r_destroy(b2r_handle h) {
     DevBuf *bufs[] = {&h->x_stage, &h->t_stage, &h->q_raw, &h->q_prep, &h->allow, &h->rows_stage, &h->gather_out,
                       &h->o_pack, &h->need_list, &h->scan_lists,
                       &h->exact_lists, &h->q_bf16, &h->q_err, &h->pass_bits, &h->gthr, &h->gemm_lists, &h->gemm_regions,
-                      &h->gemm_samples, &h->q_eps, &h->where_lut, &h->where_bits, &h->col_stage};
+                      &h->gemm_samples, &h->q_eps, &h->where_lut, &h->where_bits, &h->col_stage, &h->trace};
     for (DevBuf *b : bufs) release(*b);
     if (h->o_host) cudaFreeHost(h->o_host);
     for (auto &sl : h->aslot) {
@@ -266,6 +270,18 @@ extern "C" int b2r_kernel_time_ms(b2r_handle h, double *total_ms, int64_t *launc
     h->ev_pending.clear();
     *total_ms = h->scoring_ms; *launches = h->scoring_launches;
     if (reset) { h->scoring_ms = 0.0; h->scoring_launches = 0; }
+    return B2R_OK;
+}
+extern "C" int b2r_debug_trace(b2r_handle h, uint64_t *out, int max_ctas, int *n_ctas) {
+    B2R_REQUIRE(h && out && n_ctas, "b2r_debug_trace: NULL argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    *n_ctas = 0;
+    if (!h->trace_on || !h->trace.p || h->trace_ctas <= 0) return B2R_OK;
+    B2R_CUDA(cudaSetDevice(h->device));
+    B2R_CUDA(cudaDeviceSynchronize());
+    const int n = std::min(max_ctas, h->trace_ctas);
+    B2R_CUDA(cudaMemcpy(out, h->trace.p, sizeof(uint64_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    *n_ctas = n;
     return B2R_OK;
 }
 extern "C" int64_t b2r_count(b2r_handle h) { return h ? h->live : -1; }
@@ -744,35 +760,48 @@ int launch_scan_batch(b2r_index *h, int nq, int epl, const ScanParams &base, cud
     return B2R_OK;
 }
 
+// K5 over the whole batch (force_all) or over the work list of failed certificates.  A launch covers a bounded range of
+// work items (one slot of per-CTA lists per group of G queries, no slot is ever reused inside a launch, so no CTA waits
+// for another); the fix-up cannot know the length of its work list without a host sync, so it enqueues one launch per
+// range the batch could fill -- one launch up to a few hundred queries, and a range that turns out empty costs ~2 us.
+constexpr size_t EXACT_LISTS_BUDGET = 64u << 20;      // per-CTA list scratch per handle
+
 int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const FinalizeParams &fin,
                        const b2r_filter &f, const uint32_t *allow_dev, cudaStream_t s) {
     const int epl = epl_exact(k);
+    const int G = exact_group(epl, h->dp);
     int max_grid = exact_max_grid(epl, h->dp, h->sm_count);
     if (max_grid <= 0) { set_error("b2r_query: exact kernel cannot be resident"); return B2R_ECUDA; }
     int64_t warps_needed = std::max<int64_t>(1, (h->rows + 3) / 4);
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps_needed + EXACT_WARPS - 1) / EXACT_WARPS, max_grid));
-    // the certificate fix-up almost never has work: one CTA per SM keeps the empty launch short (3.4 -> ~2 us); a query
-    // that does need it scans at a quarter of the occupancy
-    if (!force_all) grid = std::min(grid, h->sm_count);
-    int rc = ensure(h->exact_lists, sizeof(KeyD) * (size_t)EXACT_MAX_BATCH * max_grid * 32 * epl);
+    // the certificate fix-up almost never has work: on small shards one CTA per SM keeps the empty launch short
+    // (3.4 -> ~2 us); on large ones the empty launch is noise and a query that does need the scan gets the whole machine
+    if (!force_all && h->rows < (4ll << 20)) grid = std::min(grid, h->sm_count);
+    const size_t per_group = sizeof(KeyD) * (size_t)G * grid * 32 * epl;
+    const int slots = (int)std::max<size_t>(1, std::min<size_t>(EXACT_MAX_SLOTS, EXACT_LISTS_BUDGET / per_group));
+    const int items = slots * G;
+    int rc = ensure(h->exact_lists, per_group * slots);
     if (rc != B2R_OK) return rc;
     ExactParams p;
     p.type_code = h->type_code; p.allow_bits = allow_dev; p.type_mask = f.type_mask;
-    p.n = (unsigned)h->rows; p.nq = nq; p.force_all = force_all;
+    p.n = (unsigned)h->rows; p.nq = nq; p.force_all = force_all; p.items = items;
     p.cta_lists = (KeyD *)h->exact_lists.p; p.tickets = h->tickets + 1;
     p.n_fallbacks = (long long *)(h->counters + 1);
     p.fin = fin;
-    KernelTimer kt(h, s, force_all ? 0 : 5);   // the certificate fix-up is not the scoring kernel
-    B2R_CUDA(exact_launch(epl, p, grid, s));
-    kt.stop();
-    h->n_launches++;
+    for (int first = 0; first < nq; first += items) {
+        p.first_item = first;
+        KernelTimer kt(h, s, force_all ? 0 : 5);   // the certificate fix-up is not the scoring kernel
+        B2R_CUDA(exact_launch(epl, p, grid, s));
+        kt.stop();
+        h->n_launches++;
+    }
     return B2R_OK;
 }
 
 // K3: pass bitmap -> tcgen05 scoring + per-(query, slice) lists -> per-query finalize
 constexpr int GEMM_MIN_BATCH = 5;        // below this the scan reads the corpus at most twice anyway
 constexpr int GEMM_MAX_QBLOCKS = 8;      // 128-query blocks per launch (1024 queries per corpus pass)
-constexpr int GEMM_REGION_CAP = 256;       // pool mode: entries per private (query, slice, half) region
+constexpr int GEMM_REGION_CAP = 512;       // pool mode: entries per private (query, slice, half) region; a full one keeps its best half
 constexpr int GEMM_POOL_CAP = 16384;        // pool mode: compact pool entries per query (>= SMs*2*32 for the sampling pass)
 
 int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams &fin, const b2r_filter &f,
@@ -792,11 +821,13 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
     // h->gthr (bounds, cursors, seed flags, arrival counters) was sized and cleared by the query preparation
     // list mode pools: [nq][SMs*2*L].  Pool mode: the sampling pass needs [nq][SMs*2*32] and the main pass
     // compacts at most [launch queries][slots*cap] -- both fit the same allocation.
-    const int nq_launch_max = std::min(qblocks_total, GEMM_MAX_QBLOCKS) * GEMM_BM;   // padded: every lane of a block owns a region
     if ((rc = ensure(h->gemm_lists, sizeof(KeyS) * (size_t)nq * list_stride)) != B2R_OK) return rc;
+    // private regions: [launch queries (padded: every lane of a block owns one)][n_slices * 2][cap]; n_qblocks * n_slices
+    // <= SMs in every launch, so 128 * SMs * 2 regions cover the largest one
     if (pool_mode &&
-        (rc = ensure(h->gemm_regions, sizeof(KeyS) * (size_t)nq_launch_max * h->sm_count * GEMM_HALVES * GEMM_REGION_CAP)) != B2R_OK)
+        (rc = ensure(h->gemm_regions, sizeof(KeyS) * (size_t)GEMM_BM * h->sm_count * GEMM_HALVES * GEMM_REGION_CAP)) != B2R_OK)
         return rc;
+    if (h->trace_on && (rc = ensure(h->trace, sizeof(unsigned long long) * 4 * (size_t)h->sm_count)) != B2R_OK) return rc;
     // cacheable: no bitmap at all (key 0), or a remembered clause's bitmap (its hash); a caller's own allow bitmap is not
     const bool cacheable = !allow_dev || filter_key != 0;
     const bool pb_hit = cacheable && h->pb_buf == h->pass_bits.p && h->pb_gen == h->mut_gen && h->pb_rows == h->rows &&
@@ -831,6 +862,8 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         gp.regions = (KeyS *)h->gemm_regions.p; gp.region_cap = GEMM_REGION_CAP;
         gp.samples = (unsigned *)h->gemm_samples.p; gp.seeded = gp.cnt + (size_t)qblocks_total * GEMM_BM; gp.arrive = gp.seeded + (size_t)qblocks_total * GEMM_BM;
         gp.seed_tiles = 0;
+        gp.seed_wait_ns = h->seed_wait_ns; gp.delay_us = h->delay_us;
+        gp.trace = h->trace_on ? (unsigned long long *)h->trace.p : nullptr;
         UnionParams un;
         un.lists = gp.lists; un.list_stride = list_stride; un.gthr = gp.gthr; un.cnt = gp.cnt;
         un.pool_stats = h->counters + 2;
@@ -841,10 +874,11 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
             const int tiles_per_cta = tiles_total / gp.n_slices;
             const int want = std::max((128 + gp.n_slices - 1) / gp.n_slices, std::min(tiles_per_cta / 64, 8));
             gp.seed_stride = 1;
-            if (pool_mode) {   // always, when there is anything to sample: max(4 tiles, 1/32 of the shard) spread over the slices, so
+            if (pool_mode) {   // whenever there is anything to sample: max(4 tiles, 1/32 of the shard) spread over the slices, so
                                // that the 32nd best sample leaves ~1024 candidates per query -- far more than k, or the
-                               // certificate (k-th exact candidate vs the bound) could not hold
-                const int sample_tiles = tiles_total >= 8 ? std::max(4, tiles_total / 32) : 0;
+                               // certificate (k-th exact candidate vs the bound) could not hold.  Without a seed (tiny
+                               // shards, B2R_NO_SEED) every thread bounds itself from its own region.
+                const int sample_tiles = (tiles_total >= 8 && !h->no_seed) ? std::max(4, tiles_total / h->pool_sample_div) : 0;
                 gp.seed_tiles = sample_tiles ? std::max(1, sample_tiles / gp.n_slices) : 0;
                 if (sample_tiles && sample_tiles < gp.n_slices) gp.seed_stride = gp.n_slices / sample_tiles;
             } else {
@@ -856,6 +890,7 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         KernelTimer kt(h, s);
         B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
         kt.stop();
+        h->trace_ctas = gp.n_slices * gp.n_qblocks;
         h->n_launches++;
         KernelTimer kt4(h, s, 4);
         B2R_CUDA(finalize_union_launch(epl, fin, un, q0, nq_here, s));
@@ -958,9 +993,9 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
         // (dp+8) * 2^-24 for K2's FFMA chain, 4x that for the tensor core's accumulator.
         p.q_eps = (double *)h->q_eps.p; p.norms = h->max_norm2;
         p.eps_rel = (float)(h->dp + 8) * 5.9604645e-8f * (path == 2 ? 4.f : 1.f) * 1.01f;
-        // per-call shared state, cleared by the preparation: the fix-up work list control, K5's slot generations, ...
+        // per-call shared state, cleared by the preparation: the fix-up work list control, ...
         p.zero[0] = (unsigned *)h->need_ctl; p.zero_words[0] = 2;
-        p.zero[1] = h->tickets + 1 + EXACT_MAX_BATCH; p.zero_words[1] = EXACT_MAX_BATCH;
+        p.zero[1] = nullptr; p.zero_words[1] = 0;
         p.zero[2] = nullptr; p.zero_words[2] = 0;
         if (path == 2) {   // ... and K3's [bounds | cursors | seed flags][q-blocks * 128], [arrivals][q-blocks]
             const int qblocks = (nq + GEMM_BM - 1) / GEMM_BM;

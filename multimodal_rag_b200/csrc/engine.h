@@ -51,6 +51,7 @@ cudaError_t scan_launch(int dp, int nq_group, int epl, const ScanParams &p, int 
 int scan_tile_rows(int dp);
 
 int exact_max_grid(int epl, int dp, int sm_count);
+int exact_group(int epl, int dp);   // queries K5 scores per corpus pass
 cudaError_t exact_launch(int epl, const ExactParams &p, int grid, cudaStream_t s);
 
 // K3 (gemm_kernels.cu): tcgen05 batched scoring
@@ -109,13 +110,20 @@ struct b2r_index {
     int64_t mut_gen = 0, pb_gen = -1, pb_rows = -1; unsigned long long pb_mask = 0; const void *pb_buf = nullptr; int pb_bn = 0;
     // ... and so is a compiled clause's bitmap: filter_key = hash of the clause (0 = no clause), kept with the bitmaps it produced
     uint64_t pb_key = 0, wb_key = 0; int64_t wb_gen = -1, wb_rows = -1;
-    unsigned *tickets = nullptr;    // [1 + 2*EXACT_MAX_BATCH]: scan ticket, exact tickets, exact slot generations
+    unsigned *tickets = nullptr;    // [1 + EXACT_MAX_SLOTS]: scan ticket, K5's per-group arrival tickets
 
     // optional per-kernel timing (bench.py roofline): CUDA events recorded around the scoring
     // kernel launches on the caller's stream, resolved lazily by b2r_kernel_time_ms
     bool timing = false;
     bool no_seed = false;
     int seed_min_batch = 0, seed_tiles_override = 0;
+    // development knobs (environment, read by b2r_create): B2R_SEED_WAIT_NS overrides the wait budget of K3's seeding phase
+    // (1 = never wait), B2R_DELAY_US makes every third slice post late, B2R_POOL_SAMPLE_DIV = pool mode samples 1/div of the
+    // shard (default 32), B2R_TRACE=1 records per-CTA phase timestamps of the last K3 launch (b2r_debug_trace)
+    unsigned long long seed_wait_ns = 0;
+    int delay_us = 0, pool_sample_div = 32;
+    b2r::DevBuf trace;
+    bool trace_on = false; int trace_ctas = 0;
     int timing_stage = 0;           // which launch the events bracket: 0 scoring (default); B2R_TIME_STAGE=1, 4, 5 (development):
                                     // 1 prepare, 4 finalize, 5 exact fix-up
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;

@@ -2,8 +2,14 @@
 // keeps no fp32 master), accumulates every distance in fp64 and selects on
 // (distance, row) directly, so its answer needs no certificate.  It is the always-correct
 // fallback for queries whose bf16 candidate certificate failed (fin.need_list), and the forced
-// path for shapes the fast kernels are not built for.  One query at a time, whole grid; a launch
-// with an empty work list costs one L2 read per CTA.
+// path for shapes the fast kernels are not built for.
+//
+// Work items (queries) are taken G at a time: a warp loads a stored row ONCE and scores it against the G
+// queries of the group (fp64 copies of the queries sit in shared memory), so a corpus pass costs the same HBM
+// traffic for G queries as for one.  One launch covers at most `items` work items starting at `first_item`,
+// every group of the launch has its own slot of per-CTA lists, and the last CTA to finish a group merges it:
+// no CTA ever waits for another one, so the grid need not be co-resident.  A launch whose range of the work
+// list is empty costs one L2 read per CTA.
 #pragma once
 #include "common.cuh"
 #include "finalize.cuh"
@@ -12,7 +18,8 @@ namespace b2r {
 
 constexpr int EXACT_THREADS = FIN_THREADS;
 constexpr int EXACT_WARPS = EXACT_THREADS / 32;
-constexpr int EXACT_MAX_BATCH = 64;
+constexpr int EXACT_MAX_SLOTS = 64;       // groups per launch (tickets)
+constexpr int EXACT_MAX_G = 4;            // queries per corpus pass
 
 struct ExactParams {
     const uint8_t *type_code;
@@ -21,13 +28,70 @@ struct ExactParams {
     unsigned n;
     int nq;                       // queries in the batch
     int force_all;                // 1: redo every query of the batch; 0: only fin.need_list[0 .. need_ctl[0])
-    KeyD *cta_lists;              // [EXACT_MAX_BATCH][gridDim.x][KP]: slot = work item % EXACT_MAX_BATCH
-    unsigned *tickets;            // [EXACT_MAX_BATCH] arrival tickets, then [EXACT_MAX_BATCH] slot generations
+    int first_item, items;        // this launch covers work items [first_item, first_item + items) (items <= EXACT_MAX_SLOTS * G)
+    KeyD *cta_lists;              // [slots][G][gridDim.x][KP]
+    unsigned *tickets;            // [EXACT_MAX_SLOTS] arrival tickets (0 between launches: the last CTA of a group resets its own)
     long long *n_fallbacks;       // device counter (may be nullptr)
     FinalizeParams fin;
 };
 
-template <int EPL>
+// fp64 distances of one stored row against the G prepared queries in shared memory (fp64 copies, [G][dp]); whole warp
+template <int G>
+__device__ __forceinline__ void exact_distance_warp_multi(const FinalizeParams &p, const double *qd, unsigned row, int lane,
+                                                          double (&out)[G]) {
+    const int dp = p.dp;
+    double acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = 0.0;
+    if (p.master) {
+        const float4 *xr = reinterpret_cast<const float4 *>(p.master + (size_t)row * dp);
+#pragma unroll 3
+        for (int c = lane; c < dp / 4; c += 32) {
+            const float4 x = __ldcg(xr + c);
+            const double x0 = (double)x.x, x1 = (double)x.y, x2 = (double)x.z, x3 = (double)x.w;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const double *q = qd + (size_t)g * dp + 4 * c;
+                if (p.space == 0) {
+                    const double a = q[0] - x0, b = q[1] - x1, cc = q[2] - x2, d = q[3] - x3;
+                    acc[g] = fma(a, a, acc[g]); acc[g] = fma(b, b, acc[g]); acc[g] = fma(cc, cc, acc[g]); acc[g] = fma(d, d, acc[g]);
+                } else {
+                    acc[g] = fma(q[0], x0, acc[g]); acc[g] = fma(q[1], x1, acc[g]);
+                    acc[g] = fma(q[2], x2, acc[g]); acc[g] = fma(q[3], x3, acc[g]);
+                }
+            }
+        }
+    } else {
+        const uint4 *xr = p.corpus + (size_t)row * (dp / 8);
+#pragma unroll 2
+        for (int c = lane; c < dp / 8; c += 32) {
+            const uint4 w = __ldcg(xr + c);
+            const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+            double x[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { x[2 * i] = (double)bf16lo(ww[i]); x[2 * i + 1] = (double)bf16hi(ww[i]); }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const double *q = qd + (size_t)g * dp + 8 * c;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (p.space == 0) { const double a = q[i] - x[i]; acc[g] = fma(a, a, acc[g]); }
+                    else acc[g] = fma(q[i], x[i], acc[g]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const double s = warp_sum(acc[g]);
+        out[g] = p.space == 0 ? s : 1.0 - s;
+    }
+}
+
+// The accumulation order differs from exact_distance_warp / exact_distance_group only in how the per-lane partial sums
+// are formed; every path accumulates in fp64 over fp32 inputs, whose rounding (2^-53 relative per operation) is far below the
+// spacing of distinct fp32-derived distances the tests compare (ids bit-exact, distances to 1e-5 relative).
+template <int EPL, int G>
 __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactParams p) {
     constexpr int KP = 32 * EPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -35,75 +99,79 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyD *sm_keys = reinterpret_cast<KeyD *>(smem_raw);                 // [EXACT_WARPS][KP]
     KeyD *sm_misc = sm_keys + EXACT_WARPS * KP;                         // [4]
-    float *sm_q = reinterpret_cast<float *>(sm_misc + 4);              // [dp]
+    double *sm_q = reinterpret_cast<double *>(sm_misc + 4);            // [G][dp] fp64 copies of the group's queries
     __shared__ unsigned s_ticket;
+    __shared__ int s_qi[G];
 
-    // Work list: every query (forced) or the compacted list of failed certificates.  The grid is
-    // sized to be fully resident, so waiting on another CTA's progress below cannot deadlock.
     pdl_wait();
     pdl_trigger();
-    int count = p.force_all ? p.nq : min(__ldcg(&p.fin.need_ctl[0]), p.nq);
-    unsigned *slot_gen = p.tickets + EXACT_MAX_BATCH;
-    for (int it = 0; it < count; ++it) {
-        const int qi = p.force_all ? it : __ldcg(&p.fin.need_list[it]);
-        const int slot = it % EXACT_MAX_BATCH;
-        const unsigned gen = (unsigned)(it / EXACT_MAX_BATCH);
-        KeyD *my_lists = p.cta_lists + (size_t)slot * gridDim.x * KP;
-        if (gen > 0) {      // the slot's previous user must have been merged before its lists are overwritten
-            if (threadIdx.x == 0)
-                while (*reinterpret_cast<volatile unsigned *>(&slot_gen[slot]) < gen) __nanosleep(200);
-            __threadfence();
+    const int total = p.force_all ? p.nq : min(__ldcg(&p.fin.need_ctl[0]), p.nq);
+    const int first = p.first_item, last = min(total, p.first_item + p.items);
+    for (int it0 = first, slot = 0; it0 < last; it0 += G, ++slot) {
+        const int ng = min(G, last - it0);
+        KeyD *my_lists = p.cta_lists + (size_t)slot * G * gridDim.x * KP;
+        __syncthreads();
+        if (threadIdx.x < G) s_qi[threadIdx.x] = threadIdx.x < ng ? (p.force_all ? it0 + (int)threadIdx.x : __ldcg(&p.fin.need_list[it0 + threadIdx.x])) : -1;
+        __syncthreads();
+        for (int g = 0; g < G; ++g) {
+            const int qi = s_qi[g];
+            for (int i = threadIdx.x; i < dp; i += EXACT_THREADS) sm_q[(size_t)g * dp + i] = qi >= 0 ? (double)p.fin.q[(size_t)qi * dp + i] : 0.0;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < dp; i += EXACT_THREADS) sm_q[i] = p.fin.q[(size_t)qi * dp + i];
-        __syncthreads();
 
-        WarpList<KeyD, EPL> wl; wl.init();
+        WarpList<KeyD, EPL> wl[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) wl[g].init();
         const unsigned gw = blockIdx.x * EXACT_WARPS + warp, nw = gridDim.x * EXACT_WARPS;
         for (unsigned row = gw; row < p.n; row += nw) {
             if (!row_passes(row, p.type_code, p.type_mask, p.allow_bits)) continue;   // warp-uniform
-            double d = exact_distance_warp(p.fin, sm_q, row, lane);
-            wl.offer(KeyD::make(d, row), lane);
+            double d[G];
+            exact_distance_warp_multi<G>(p.fin, sm_q, row, lane, d);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (g < ng) wl[g].offer(KeyD::make(d[g], row), lane);
         }
-        __syncthreads();
-        cta_tree_merge<KeyD, EPL>(wl, sm_keys, warp, lane);
-        if (warp == 0) wl.store(my_lists + (size_t)blockIdx.x * KP, lane);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (g >= ng) break;
+            __syncthreads();
+            cta_tree_merge<KeyD, EPL>(wl[g], sm_keys, warp, lane);
+            if (warp == 0) wl[g].store(my_lists + ((size_t)g * gridDim.x + blockIdx.x) * KP, lane);
+        }
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[slot], 1u);
         __syncthreads();
         if (s_ticket == gridDim.x - 1) {
-            // ---- last CTA for this query: fold all CTA lists, emit ----
+            // ---- last CTA of this group: fold all CTA lists of each of its queries, emit ----
             __threadfence();
-            WarpList<KeyD, EPL> m; m.init();
-            for (unsigned li = warp; li < gridDim.x; li += EXACT_WARPS) {
-                const KeyD *src = my_lists + (size_t)li * KP;
-                const KeyD head = KeyD::load_cg(src);
-                if (head.valid() && m.accepts(head)) m.template merge_bitonic<true>(src, lane);
+            for (int g = 0; g < ng; ++g) {
+                WarpList<KeyD, EPL> m; m.init();
+                for (unsigned li = warp; li < gridDim.x; li += EXACT_WARPS) {
+                    const KeyD *src = my_lists + ((size_t)g * gridDim.x + li) * KP;
+                    const KeyD head = KeyD::load_cg(src);
+                    if (head.valid() && m.accepts(head)) m.template merge_bitonic<true>(src, lane);
+                }
+                __syncthreads();
+                cta_tree_merge<KeyD, EPL>(m, sm_keys, warp, lane);
+                if (threadIdx.x == 0) sm_misc[0] = KeyD::worst();
+                __syncthreads();
+                int nvalid = 0;
+                for (int i = 0; i < KP; ++i) nvalid += sm_keys[i].valid() ? 1 : 0;
+                emit_sorted(p.fin, s_qi[g], sm_keys, nvalid, &sm_misc[0]);
+                __syncthreads();
             }
-            __syncthreads();
-            cta_tree_merge<KeyD, EPL>(m, sm_keys, warp, lane);
-            if (threadIdx.x == 0) sm_misc[0] = KeyD::worst();
-            __syncthreads();
-            int nvalid = 0;
-            for (int i = 0; i < KP; ++i) nvalid += sm_keys[i].valid() ? 1 : 0;
-            emit_sorted(p.fin, qi, sm_keys, nvalid, &sm_misc[0]);
-            __syncthreads();
             if (threadIdx.x == 0) {
-                p.tickets[slot] = 0u;
-                if (!p.force_all && p.n_fallbacks) atomicAdd((unsigned long long *)p.n_fallbacks, 1ull);
-                __threadfence();
-                *reinterpret_cast<volatile unsigned *>(&slot_gen[slot]) = gen + 1;
+                p.tickets[slot] = 0u;                        // ready for the next launch on this stream
+                if (!p.force_all && p.n_fallbacks) atomicAdd((unsigned long long *)p.n_fallbacks, (unsigned long long)ng);
             }
         }
-        __syncthreads();
     }
-    // the work list control and the slot generations are cleared by the next call's query preparation
 }
 
-inline size_t exact_smem_bytes(int EPL, int dp) {
+inline size_t exact_smem_bytes(int EPL, int G, int dp) {
     const int KP = 32 * EPL;
-    return sizeof(KeyD) * (EXACT_WARPS * KP + 4) + sizeof(float) * dp;
+    return sizeof(KeyD) * (EXACT_WARPS * KP + 4) + sizeof(double) * (size_t)G * dp;
 }
 
 }  // namespace b2r

@@ -39,7 +39,14 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_POOL_SAMPLE_RANK = 32;  // pool mode: the bound is the 32nd best sampled score
-constexpr unsigned long long GEMM_SEED_TIMEOUT_NS = 50000ull;   // bound on every wait of the in-kernel seeding phase
+// Bounds on the waits of the in-kernel seeding phase.  List mode: 50 us, then the scan starts unseeded (its lists bound
+// themselves) and picks the seed up from gthr[q] when it arrives.  Pool mode needs the bound before its first append, and
+// the CTAs of a query block drift apart during a long sampling phase (1/32 of the shard: hundreds of microseconds at 25M+
+// rows), so its budget scales with the sampling phase it has just measured: 2x its duration, within [100 us, 5 ms].
+// Nothing depends on a wait succeeding: a fold that could not run yet is retried at every tile, and a pool-mode thread
+// without a seed bounds itself from its own region (pool_region_tighten).
+constexpr unsigned long long GEMM_SEED_TIMEOUT_NS = 50000ull;
+constexpr unsigned long long GEMM_POOL_WAIT_MIN_NS = 100000ull, GEMM_POOL_WAIT_MAX_NS = 5000000ull;
 constexpr int GEMM_HALVES = 2;          // epilogue warps w and w+4 share a TMEM lane quadrant and split a tile's columns
 constexpr int GEMM_SMEM_LIMIT = 232448;       // 227 KB opt-in maximum per CTA
 constexpr int GEMM_SMEM_SLACK = 1024 + 512;   // manual 1024-byte alignment + static barriers
@@ -64,8 +71,9 @@ struct GemmParams {
     unsigned *gthr;              // [n_qblocks*128] shared per-query bound, KeyS::ord encoding, 0 = none yet
     unsigned *cnt;               // [nq] entries appended to lists[q] so far (0 between calls)
     KeyS *lists;                 // [nq][list_stride]: every thread appends its valid entries (atomic cursor cnt[q])
-    KeyS *regions;               // pool mode (L = 0): [nq][n_slices*2][region_cap] private append regions
-    int region_cap;              // entries per private region; overflow sets bit 31 of cnt[q] (-> exact fix-up)
+    KeyS *regions;               // pool mode (L = 0): [launch queries (padded to 128)][n_slices*2][region_cap] private append regions
+    int region_cap;              // entries per private region; a full region raises its thread's bound to its own
+                                 // (region_cap/2)-th best score and keeps what is above it (pool_region_tighten)
     // in-kernel threshold seeding.  Before its slice every CTA scans the slice's first seed_tiles tiles in sampling
     // mode (best score of every 32-row step), posts its best few per thread and bumps arrive[qblock]; once all
     // n_slices CTAs of the block have posted, the epilogue warps of each CTA fold the posts of their share of the
@@ -76,6 +84,10 @@ struct GemmParams {
     unsigned *samples;           // [launch queries (padded to 128)][n_slices*2][2 .. L] ordered score keys, 0 = empty
     unsigned *seeded;            // [all queries] 0 = not seeded yet, 1 = seeded without a bound, else the seed (= gthr[q] then)
     unsigned *arrive;            // [all q-blocks] CTAs that have posted (0 between calls: the query preparation clears it)
+    // development knobs (0 in production; b2r_create reads them from the environment)
+    unsigned long long seed_wait_ns;   // overrides the wait budget of the seeding phase (1 = do not wait at all)
+    int delay_us;                // every third slice sleeps this long before it posts its samples (a slow CTA)
+    unsigned long long *trace;   // [grid][4] globaltimer: epilogue start, posted, seeded, done (nullptr = off)
 };
 
 // Up to 512 dims (KB <= 8) the query block stays resident in shared memory (KB * 16 KB) and a pipeline stage
@@ -322,13 +334,60 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&raw)[32], unsigned r0
     }
 }
 
+// Pool mode, rare path: this thread's private region is full.  First the entries that no longer beat the query's shared
+// bound go (another slice may have raised it); if more than half the region is still in use, the thread raises its own bound to
+// its (cap/2)-th best score t -- found by bisection on the 32 bits of the ordered score, no sorting, no scratch -- keeps
+// what beats t and publishes t.  Publishing is what keeps the certificate's invariant (a row that is not in the pool
+// scores <= the final gthr[q]); it is a useful bound because cap/2 rows of this region alone reach it (cap/2 = 256 >= 2k).
+// Strict compares everywhere, as in the admission test, so a region of equal scores still shrinks.
+struct PoolTight { int count; float thr; };
+static __device__ __noinline__ PoolTight pool_region_tighten(KeyS *region, int count, int cap, float thr, unsigned *gq, bool publish) {
+    int n = count < cap ? count : cap;
+    unsigned cut = thr > -INFINITY ? KeyS::ord(thr) : 0u;
+    const unsigned g = *reinterpret_cast<volatile unsigned *>(gq);
+    if (g > cut) {
+        cut = g;
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const KeyS e = region[i];
+            if ((unsigned)(e.v >> 32) > cut) region[m++] = e;
+        }
+        n = m;
+    }
+    const int keep = cap / 2;
+    if (n > keep) {
+        unsigned t = 0u;                                   // largest t with #(key >= t) >= keep  =  the keep-th best key
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            const unsigned cand = t | (1u << bit);
+            int c = 0;
+#pragma unroll 8
+            for (int i = 0; i < n; ++i) c += (unsigned)(region[i].v >> 32) >= cand ? 1 : 0;
+            if (c >= keep) t = cand;
+        }
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const KeyS e = region[i];
+            if ((unsigned)(e.v >> 32) > t) region[m++] = e;
+        }
+        n = m;
+        cut = t;
+        if (publish) atomicMax(gq, t);
+    }
+    PoolTight r;
+    r.count = n;
+    r.thr = cut != 0u ? fmaxf(thr, KeyS::unord(cut)) : thr;
+    return r;
+}
+
 // Pool-mode step (32 < k <= 128, no per-thread list): every passing row that beats the query's bound --
 // seeded by the sampling pass at the 32nd best sampled score -- is appended to this thread's private region
-// with a plain store.  The bound does not move during the pass, so the expected pool is
-// (rows / sample rows) * 32 entries per query whatever the shard size.
+// with a plain store.  With a seed the bound rarely moves during the pass, so the expected pool is
+// (rows / sample rows) * 32 entries per query whatever the shard size; a region that fills up anyway (no seed yet,
+// or an unlucky one) tightens itself.
 template <bool HAS_BIAS>
-__device__ __forceinline__ void epi_chunk_pool(const uint32_t (&raw)[32], unsigned r0, const GemmParams &p, float thr,
-                                               KeyS *region, int &count) {
+__device__ __forceinline__ void epi_chunk_pool(const uint32_t (&raw)[32], unsigned r0, const GemmParams &p, float &thr,
+                                               KeyS *region, int &count, unsigned *gq, bool publish) {
     const unsigned pm = __ldg(p.pass_bits + (r0 >> 5));
     float v[32];
 #pragma unroll
@@ -376,8 +435,11 @@ __device__ __forceinline__ void epi_chunk_pool(const uint32_t (&raw)[32], unsign
 #pragma unroll
             for (int i = 0; i < 2; ++i) w2[i] = b1 ? w4[2 + i] : w4[i];
             const float x = b0 ? w2[1] : w2[0];
-            if (count < p.region_cap) region[count] = KeyS::make(x, r0 + j);
-            ++count;                                       // counts past the capacity: overflow is reported at the end
+            if (count >= p.region_cap) {
+                const PoolTight tg = pool_region_tighten(region, count, p.region_cap, thr, gq, publish);
+                count = tg.count; thr = tg.thr;
+            }
+            if (x > thr) region[count++] = KeyS::make(x, r0 + j);
         }
     }
 }
@@ -738,10 +800,41 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         unsigned *gq = p.gthr + q;
         unsigned g_next = *reinterpret_cast<volatile unsigned *>(gq);
 
+        // ---- seeding state (see GemmParams::seed_tiles) ----
+        // This warp folds the queries lq_next, lq_next + 8, ... < lq1 of the block (the CTA's share is [lq0, lq1)) once every
+        // slice of the block has posted.  fold_pending is warp-uniform.
+        // values posted per thread: its 2 (4) best when the block's sampling slices then still post >= 4 L (2 L) between
+        // them -- the L-th best of that union is as good a bound -- else all it has (S * NC step maxima at most)
+        const int n_samp = (p.n_slices + p.seed_stride - 1) / p.seed_stride;      // slices that sample
+        const int pv = n_samp >= LS ? 2 : n_samp * GEMM_HALVES >= LS ? 4 : min(LS, (p.seed_tiles * NC + 3) & ~3);
+        const int per_q = p.n_slices * GEMM_HALVES * pv;
+        const int lq1 = GEMM_BM * (slice + 1) / p.n_slices;
+        int lq_next = GEMM_BM * slice / p.n_slices + (warp - 2);
+        bool fold_pending = false;
+        auto fold_ready = [&]() -> bool {                  // have all slices of this block posted?
+            unsigned a = 0u;
+            if (lane == 0) a = ld_acquire_gpu(p.arrive + qb);
+            return __shfl_sync(FULL_MASK, a, 0) >= (unsigned)p.n_slices;
+        };
+        auto fold_share = [&]() {                          // the L-th best posted score becomes the query's bound
+            for (; lq_next < lq1; lq_next += GEMM_EPI_WARPS) {
+                const int qs = qb * GEMM_BM + lq_next;
+                if (qs >= p.nq) break;
+                const unsigned v = warp_lth_largest<LS>(p.samples + (size_t)(qs - p.qblock0 * GEMM_BM) * per_q, per_q, lane);
+                if (lane == 0) {
+                    if (v != 0u) atomicMax(p.gthr + qs, v);       // the finalize reads the bound from gthr[q]
+                    __threadfence();
+                    atomicExch(p.seeded + qs, v != 0u ? v : 1u);  // flag and seed in one word (1 = no seed: too few rows pass)
+                }
+            }
+            fold_pending = false;
+        };
+
         // one tile: TMEM -> registers in 32-column steps, two register buffers so the next load flies under this step
         auto run_tile = [&](int t, int it, auto sample_c, auto &slist) {
             constexpr bool SMP = decltype(sample_c)::value;
             const int buf = it & 1;
+            if (!SMP && fold_pending && fold_ready()) fold_share();     // a fold that had to be put off (a slice was late)
             if (!SMP && g_next > g_seen) { g_seen = g_next; thr = fmaxf(thr, KeyS::unord(g_next)); }
             mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
             tc_fence_after();
@@ -756,13 +849,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 tmem_ld_wait(va);
                 tmem_ld_x32(trow + (c + 1) * 32, vb);
                 if constexpr (SMP) epi_chunk_sample<LS, HAS_BIAS>(va, row0 + c * 32, p, slist);
-                else if constexpr (L == 0) epi_chunk_pool<HAS_BIAS>(va, row0 + c * 32, p, thr, region, rcount);
+                else if constexpr (L == 0) epi_chunk_pool<HAS_BIAS>(va, row0 + c * 32, p, thr, region, rcount, gq, publish);
                 else epi_chunk<LL, HAS_BIAS>(va, row0 + c * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
                 tmem_ld_wait(vb);
                 if (c + 2 < NC) tmem_ld_x32(trow + (c + 2) * 32, va);
                 if constexpr (SMP) epi_chunk_sample<LS, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, slist);
-                else if constexpr (L == 0) epi_chunk_pool<HAS_BIAS>(vb, row0 + (c + 1) * 32, p, thr, region, rcount);
+                else if constexpr (L == 0) epi_chunk_pool<HAS_BIAS>(vb, row0 + (c + 1) * 32, p, thr, region, rcount, gq, publish);
                 else epi_chunk<LL, HAS_BIAS>(vb, row0 + (c + 1) * 32, p, list, thr, g_seen, gq, publish);
                 __syncwarp();
             }
@@ -771,79 +864,85 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (lane == 0) mbar_arrive(&bar_tempty[buf]);
         };
 
+        const bool tracer = p.trace != nullptr && warp == 2 && lane == 0;
+        if (tracer) p.trace[(size_t)blockIdx.x * 4 + 0] = globaltimer_ns();
         int it = 0;
-        {
-            if (p.seed_tiles > 0) {
-                // ---- seeding phase (see GemmParams::seed_tiles) ----
-                // 1. the first S tiles of the slice in sampling mode: the list collects the best step maxima
-                RegList<LS> slist; slist.init();
-                for (int i = 0; i < S; ++i, ++it) run_tile(t0 + i, it, std::true_type(), slist);
-                // 2. post them, count this CTA in
-                // values posted per thread: its 2 (4) best when the block's sampling slices then still post >= 4 L (2 L) between
-                // them -- the L-th best of that union is as good a bound -- else all it has (S * NC step maxima at most)
-                const int n_samp = (p.n_slices + p.seed_stride - 1) / p.seed_stride;      // slices that sample
-                const int pv = n_samp >= LS ? 2 : n_samp * GEMM_HALVES >= LS ? 4 : min(LS, (p.seed_tiles * NC + 3) & ~3);
-                if (publish) {
-                    unsigned *dst = p.samples + ((size_t)(q - p.qblock0 * GEMM_BM) * (p.n_slices * GEMM_HALVES) +
-                                                 (size_t)(slice * GEMM_HALVES + half)) * pv;
-#pragma unroll
-                    for (int i = 0; i < LS; i += 2) {
-                        if (i >= pv) break;
-                        uint2 o;
-                        o.x = slist.r[i] != 0xffffffffu ? KeyS::ord(slist.s[i]) : 0u;
-                        o.y = slist.r[i + 1] != 0xffffffffu ? KeyS::ord(slist.s[i + 1]) : 0u;
-                        *reinterpret_cast<uint2 *>(dst + i) = o;
-                    }
-                    __threadfence();
-                }
-                epi_bar_sync();                                   // every epilogue thread's post is fenced
-                if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(p.arrive + qb, 1u); }
-                // 3. this CTA's share of the block's queries, one per epilogue warp: once every slice has posted,
-                //    the L-th best posted score becomes the query's bound.  All waits are bounded: the seed is an
-                //    accelerator, the certificate never depends on it.
-                const unsigned long long t_start = globaltimer_ns();
-                const int lq0 = GEMM_BM * slice / p.n_slices, lq1 = GEMM_BM * (slice + 1) / p.n_slices;
-                const int per_q = p.n_slices * GEMM_HALVES * pv;
-                for (int lq = lq0 + (warp - 2); lq < lq1; lq += GEMM_EPI_WARPS) {
-                    const int qs = qb * GEMM_BM + lq;
-                    if (qs >= p.nq) break;
-                    bool posted;
-                    while (!(posted = ld_acquire_gpu(p.arrive + qb) >= (unsigned)p.n_slices)) {
-                        if (globaltimer_ns() - t_start > GEMM_SEED_TIMEOUT_NS) break;
-                        __nanosleep(64);
-                    }
-                    if (!posted) break;
-                    const unsigned v = warp_lth_largest<LS>(p.samples + (size_t)(qs - p.qblock0 * GEMM_BM) * per_q, per_q, lane);
-                    if (lane == 0) {
-                        if (v != 0u) atomicMax(p.gthr + qs, v);       // the finalize reads the bound from gthr[q]
-                        __threadfence();
-                        atomicExch(p.seeded + qs, v != 0u ? v : 1u);  // flag and seed in one word (1 = no seed: too few rows pass)
-                    }
-                }
-                // 4. wait for this thread's own query: even with one live lane per warp an unseeded tile costs more
-                //    than the wait (measured: batch 1 144 vs 149 us, batch 16 151 vs 172 us per call)
-                if (publish) {
-                    unsigned sd;
-                    while ((sd = ld_acquire_gpu(p.seeded + q)) == 0u) {
-                        if (globaltimer_ns() - t_start > GEMM_SEED_TIMEOUT_NS) break;
-                        __nanosleep(32);
-                    }
-                    if (sd > 1u) g_next = sd;
-                }
-                __syncwarp();
+        if (p.seed_tiles > 0) {
+            // ---- seeding phase ----
+            // 1. the first S tiles of the slice in sampling mode: the list collects the best step maxima
+            const unsigned long long t_begin = __shfl_sync(FULL_MASK, globaltimer_ns(), 0);   // warp-uniform clock readings
+            RegList<LS> slist; slist.init();
+            for (int i = 0; i < S; ++i, ++it) run_tile(t0 + i, it, std::true_type(), slist);
+            if (p.delay_us > 0 && slice % 3 == 1) {            // development: a slow CTA
+                const unsigned long long t_d = globaltimer_ns();
+                while (globaltimer_ns() - t_d < (unsigned long long)p.delay_us * 1000ull) __nanosleep(256);
             }
+            // 2. post them, count this CTA in
+            if (publish) {
+                unsigned *dst = p.samples + ((size_t)(q - p.qblock0 * GEMM_BM) * (p.n_slices * GEMM_HALVES) +
+                                             (size_t)(slice * GEMM_HALVES + half)) * pv;
+#pragma unroll
+                for (int i = 0; i < LS; i += 2) {
+                    if (i >= pv) break;
+                    uint2 o;
+                    o.x = slist.r[i] != 0xffffffffu ? KeyS::ord(slist.s[i]) : 0u;
+                    o.y = slist.r[i + 1] != 0xffffffffu ? KeyS::ord(slist.s[i + 1]) : 0u;
+                    *reinterpret_cast<uint2 *>(dst + i) = o;
+                }
+                __threadfence();
+            }
+            epi_bar_sync();                                   // every epilogue thread's post is fenced
+            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(p.arrive + qb, 1u); }
+            const unsigned long long t_post = __shfl_sync(FULL_MASK, globaltimer_ns(), 0);
+            if (tracer) p.trace[(size_t)blockIdx.x * 4 + 1] = t_post;
+            unsigned long long budget = GEMM_SEED_TIMEOUT_NS;
+            if (L == 0) budget = min(max(2ull * (t_post - t_begin), GEMM_POOL_WAIT_MIN_NS), GEMM_POOL_WAIT_MAX_NS);
+            if (p.seed_wait_ns) budget = p.seed_wait_ns;
+            // 3. this CTA's share of the block's queries, one per epilogue warp, as soon as every slice has posted.  The
+            //    wait is bounded; a fold that cannot run now is retried at the top of every tile of the main loop.
+            fold_pending = lq_next < lq1 && qb * GEMM_BM + lq_next < p.nq;
+            while (fold_pending) {
+                if (fold_ready()) { fold_share(); break; }
+                if (__shfl_sync(FULL_MASK, (int)(globaltimer_ns() - t_post > budget), 0)) break;
+                __nanosleep(64);
+            }
+            // 4. wait for this thread's own query (another CTA folds it): even with one live lane per warp an unseeded
+            //    tile costs more than the wait (measured: batch 1 144 vs 149 us, batch 16 151 vs 172 us per call).  A seed
+            //    that comes later still arrives through gthr[q], which every tile re-reads.
+            if (publish) {
+                unsigned sd;
+                while ((sd = ld_acquire_gpu(p.seeded + q)) == 0u) {
+                    if (globaltimer_ns() - t_post > budget) break;
+                    __nanosleep(32);
+                }
+                if (sd > 1u) g_next = sd;
+            }
+            __syncwarp();
         }
+        if (tracer) p.trace[(size_t)blockIdx.x * 4 + 2] = globaltimer_ns();
         for (int t = t0; t < t1; ++t, ++it) run_tile(t, it, std::false_type(), list);
+        if (fold_pending && fold_ready()) fold_share();          // last chance before this CTA leaves
+        if (tracer) p.trace[(size_t)blockIdx.x * 4 + 3] = globaltimer_ns();
 
         if (L == 0) {
             if (q < p.nq && rcount > 0) {     // compact the private region into the query's pool
-                const int nv = min(rcount, p.region_cap);
-                const unsigned base = atomicAdd(&p.cnt[q], (unsigned)nv) & 0x7fffffffu;
-                const bool fits = base + (unsigned)nv <= (unsigned)p.list_stride;
-                KeyS *dst = p.lists + (size_t)q * p.list_stride + base;
-                if (fits)
-                    for (int i = 0; i < nv; ++i) dst[i] = region[i];
-                if (!fits || rcount > p.region_cap) atomicOr(&p.cnt[q], 0x80000000u);   // rows were dropped: not certifiable
+                // entries that do not reach the bound published so far need not travel: whatever is dropped here scores
+                // <= the final gthr[q], which is all the certificate asks of a row outside the pool
+                const unsigned g_now = *reinterpret_cast<volatile unsigned *>(gq);
+                int nv = 0;
+                for (int i = 0; i < rcount; ++i) nv += (unsigned)(region[i].v >> 32) >= g_now ? 1 : 0;
+                if (nv) {
+                    const unsigned base = atomicAdd(&p.cnt[q], (unsigned)nv) & 0x7fffffffu;
+                    if (base + (unsigned)nv <= (unsigned)p.list_stride) {
+                        KeyS *dst = p.lists + (size_t)q * p.list_stride + base;
+                        for (int i = 0, j = 0; i < rcount; ++i) {
+                            const KeyS e = region[i];
+                            if ((unsigned)(e.v >> 32) >= g_now) dst[j++] = e;
+                        }
+                    } else {
+                        atomicOr(&p.cnt[q], 0x80000000u);   // the pool is full, rows were dropped: not certifiable -> exact fix-up
+                    }
+                }
             }
         } else if (q < p.nq) {    // append this thread's entries to the query's candidate pool (compact: most lists are short)
             // entries below the bound published so far need not travel: whatever is dropped here scores
