@@ -324,6 +324,13 @@ class B200Collection:
         f.allow_bits = bits.ctypes.data
         return f, bits
 
+    def device_filter(self, where=None):
+        """(b2r_filter struct, keep-alive object) for `where`, as `query` would hand it to the C ABI -- for callers that
+        drive b2r_query themselves with device-resident buffers (bench.py).  Keep the second value alive while the
+        struct is in use."""
+        with self._lock:
+            return self._filter(where)
+
     def filter_bits(self, where=None) -> np.ndarray:
         """The pass bitmap the device derives for `where` (bool per row: live AND matching) -- b2r_filter_eval."""
         with self._lock:

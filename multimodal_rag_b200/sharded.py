@@ -183,17 +183,22 @@ class DeviceShard:
     numbered row_base + local.  query_device keeps every tensor on the GPU and enqueues
     local scan -> all_gather -> merge on the current stream without a host sync."""
 
+    exchange_mode = "nccl all_gather_into_tensor + merge kernel, same stream"
+
     def __init__(self, dim, space="cosine", *, capacity=0, row_base=0, device=None, group=None,
-                 keep_f32_master=True):
+                 keep_f32_master=True, world=None):
         self.lib = _lib.load()
         self.device = torch.cuda.current_device() if device is None else device
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # world=1: a stand-alone shard inside a distributed job (no exchange)
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         h = ctypes.c_void_p()
         _lib.check(self.lib.b2r_create(dim, _lib.SPACE_CODE[space], capacity, self.device,
                                        0 if keep_f32_master else _lib.FLAG_NO_F32_MASTER, ctypes.byref(h)))
         self.h = h
         self.dim = dim
+        self._side = None           # stream of the pipelined exchange
+        self._inflight = None
         _lib.check(self.lib.b2r_set_row_base(h, row_base))
 
     def close(self):
@@ -233,6 +238,24 @@ class DeviceShard:
             "m_cnt": torch.empty((nq,), dtype=torch.int32, device=dev),
         }
 
+    def alloc_host(self, nq, k):
+        """Pinned host mirrors for query_host: the query batch staging and the merged results."""
+        return {"rows": torch.empty((nq, k), dtype=torch.int64).pin_memory(),
+                "dist": torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                "cnt": torch.empty((nq,), dtype=torch.int32).pin_memory(),
+                "q_dev": torch.empty((nq, self.dim), dtype=torch.float32, device=torch.device("cuda", self.device))}
+
+    def query_host(self, q_host: torch.Tensor, k: int, o: dict, h: dict):
+        """End to end with HOST buffers: pinned query batch -> device, local exact top-k, exchange + merge, merged
+        rows / distances / counts -> pinned host arrays, stream synchronised on return."""
+        h["q_dev"].copy_(q_host, non_blocking=True)
+        rows, dist_, cnt = self.query_device(h["q_dev"], k, o)
+        h["rows"].copy_(rows, non_blocking=True)
+        h["dist"].copy_(dist_, non_blocking=True)
+        h["cnt"].copy_(cnt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h["rows"], h["dist"], h["cnt"]
+
     def query_local(self, q: torch.Tensor, k: int, o: dict):
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.b2r_query_ex(self.h, q.data_ptr(), q.shape[0], k, None, o["rows"].data_ptr(),
@@ -245,11 +268,41 @@ class DeviceShard:
         self.query_local(q, k, o)
         if self.world == 1:
             return o["rows"], o["dist"], o["cnt"]
+        self._exchange(q.shape[0], k, o)
+        return o["m_rows"], o["m_dist"], o["m_cnt"]
+
+    def _exchange(self, nq, k, o):
         dist.all_gather_into_tensor(o["a_pack"], o["pack"], group=self.group)      # the only data-path collective
         st = torch.cuda.current_stream().cuda_stream
-        nq = q.shape[0]
         stride, off_rows, off_d64, off_cnt = o["layout"]
         _lib.check(self.lib.b2r_merge_shards_packed(o["a_pack"].data_ptr(), stride, off_rows, off_d64, off_cnt,
                                                     self.world, nq, k, o["m_rows"].data_ptr(), o["m_dist"].data_ptr(),
                                                     o["m_cnt"].data_ptr(), self.device, st), "b2r_merge_shards_packed")
-        return o["m_rows"], o["m_dist"], o["m_cnt"]
+
+    def query_device_pipelined(self, q: torch.Tensor, k: int, o: dict):
+        """The same with the exchange taken off the scoring stream: the local top-k of this batch is enqueued on the
+        current stream, its all_gather + merge on a side stream behind an event, so the next batch's scan starts while
+        this batch's lists travel.  `o` must not be reused before the batch after next (two output sets, alternated);
+        results are valid once o['ev_done'] has been reached -- `drain()` makes the current stream wait for every
+        exchange still in flight."""
+        cur = torch.cuda.current_stream()
+        if "ev_done" in o:
+            cur.wait_event(o["ev_done"])          # the previous user of these buffers has been merged
+        self.query_local(q, k, o)
+        if self.world == 1:
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        if "ev_local" not in o:
+            o["ev_local"], o["ev_done"] = torch.cuda.Event(), torch.cuda.Event()
+        o["ev_local"].record(cur)
+        self._side.wait_event(o["ev_local"])
+        with torch.cuda.stream(self._side):
+            self._exchange(q.shape[0], k, o)
+            o["ev_done"].record(self._side)
+        self._inflight = o
+
+    def drain(self):
+        if self._inflight is not None:
+            torch.cuda.current_stream().wait_event(self._inflight["ev_done"])
+            self._inflight = None

@@ -27,6 +27,8 @@ def lib():
     if _lib is None:
         _lib = ctypes.CDLL(build())
         _lib.b2r_oracle_threads.restype = ctypes.c_int
+        _lib.b2r_oracle_set_threads.argtypes = [ctypes.c_int]
+        _lib.b2r_oracle_set_threads.restype = None
         _lib.b2r_oracle_normalize_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
         _lib.b2r_oracle_normalize_f32.restype = None
         _lib.b2r_oracle_topk.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
@@ -49,6 +51,14 @@ def lib():
 
 def threads() -> int:
     return int(lib().b2r_oracle_threads())
+
+
+def set_threads(n: int = 0) -> int:
+    """Use n OpenMP threads (0 = every core this process may run on); returns the count now in effect."""
+    if n <= 0:
+        n = len(os.sched_getaffinity(0))
+    lib().b2r_oracle_set_threads(int(n))
+    return threads()
 
 
 def normalize_f32(x: np.ndarray) -> np.ndarray:

@@ -47,6 +47,16 @@ int b2r_oracle_threads(void) {
 #endif
 }
 
+/* n <= 0 restores the OpenMP default.  torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm of the bench
+ * runs on rank 0 alone and asks for all the cores it may use. */
+void b2r_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+#else
+    (void)n;
+#endif
+}
+
 /* hnswlib bindings.cpp normalize_vector; sum of squares in fp64, rounded once to fp32 */
 void b2r_oracle_normalize_f32(const float *x, int64_t n, int d, float *out) {
 #pragma omp parallel for schedule(static)
