@@ -213,9 +213,11 @@ int64_t b2r_launch_count(b2r_handle h);
  * accumulated device time and launch count (reset != 0 clears the accumulators).      */
 int b2r_set_kernel_timing(b2r_handle h, int enable);
 int b2r_kernel_time_ms(b2r_handle h, double *total_ms, int64_t *launches, int reset);
-/* Development: with B2R_TRACE=1 in the environment when the handle is created, the tcgen05 scoring kernel records four
- * %globaltimer readings per CTA of its last launch (epilogue start, samples posted, bound seeded, slice done).  Copies
- * min(max_ctas, CTAs of that launch) * 4 values (ns) to the host array `out` after synchronising the device; *n_ctas =
+/* Development: with B2R_TRACE=1 in the environment when the handle is created, the tcgen05 scoring kernel records eight
+ * values per CTA of its last launch: four %globaltimer readings (epilogue start, samples posted, bound seeded, slice done; ns)
+ * and four wait totals in SM cycles (MMA thread: empty accumulator, operands; first epilogue warp: full accumulator;
+ * TMA producer: free ring slot).  Copies min(max_ctas, CTAs of that launch) * 8 values to the host array `out` after
+ * synchronising the device; *n_ctas =
  * number of CTAs copied (0 when tracing is off).                                                       */
 int b2r_debug_trace(b2r_handle h, uint64_t *out, int max_ctas, int *n_ctas);
 

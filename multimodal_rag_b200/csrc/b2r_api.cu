@@ -167,6 +167,7 @@ extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device,
     if (const char *e = getenv("B2R_DELAY_US")) h->delay_us = atoi(e);
     if (const char *e = getenv("B2R_POOL_SAMPLE_DIV")) h->pool_sample_div = std::max(1, atoi(e));
     if (const char *e = getenv("B2R_TRACE")) h->trace_on = atoi(e) != 0;
+    if (const char *e = getenv("B2R_NO_PAIR")) h->no_pair = atoi(e) != 0;
     int rc = B2R_OK;
     do {
         if (cudaMalloc(&h->max_norm2, 256) != cudaSuccess || cudaMalloc(&h->counters, 256) != cudaSuccess ||
@@ -280,7 +281,7 @@ extern "C" int b2r_debug_trace(b2r_handle h, uint64_t *out, int max_ctas, int *n
     B2R_CUDA(cudaSetDevice(h->device));
     B2R_CUDA(cudaDeviceSynchronize());
     const int n = std::min(max_ctas, h->trace_ctas);
-    B2R_CUDA(cudaMemcpy(out, h->trace.p, sizeof(uint64_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    B2R_CUDA(cudaMemcpy(out, h->trace.p, sizeof(uint64_t) * 8 * (size_t)n, cudaMemcpyDeviceToHost));
     *n_ctas = n;
     return B2R_OK;
 }
@@ -827,7 +828,7 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
     if (pool_mode &&
         (rc = ensure(h->gemm_regions, sizeof(KeyS) * (size_t)GEMM_BM * h->sm_count * GEMM_HALVES * GEMM_REGION_CAP)) != B2R_OK)
         return rc;
-    if (h->trace_on && (rc = ensure(h->trace, sizeof(unsigned long long) * 4 * (size_t)h->sm_count)) != B2R_OK) return rc;
+    if (h->trace_on && (rc = ensure(h->trace, sizeof(unsigned long long) * 8 * (size_t)h->sm_count)) != B2R_OK) return rc;
     // cacheable: no bitmap at all (key 0), or a remembered clause's bitmap (its hash); a caller's own allow bitmap is not
     const bool cacheable = !allow_dev || filter_key != 0;
     const bool pb_hit = cacheable && h->pb_buf == h->pass_bits.p && h->pb_gen == h->mut_gen && h->pb_rows == h->rows &&
@@ -841,6 +842,7 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
     }
     if (h->tm_corpus_base != h->corpus || h->tm_corpus_rows != h->capacity) {
         if ((rc = gemm_encode_map(&h->tm_corpus, h->corpus, h->dp, (uint64_t)h->capacity, BN)) != B2R_OK) return rc;
+        if ((rc = gemm_encode_map(&h->tm_corpus_half, h->corpus, h->dp, (uint64_t)h->capacity, BN / 2)) != B2R_OK) return rc;
         h->tm_corpus_base = h->corpus; h->tm_corpus_rows = h->capacity;
     }
     if (h->tm_query_base != h->q_bf16.p || h->tm_query_rows != nq) {
@@ -870,6 +872,16 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         const int q0 = qb0 * GEMM_BM, nq_here = std::min(nq - q0, gp.n_qblocks * GEMM_BM);
         gp.tiles_total = tiles_total;
         gp.n_slices = std::max(1, std::min(h->sm_count / gp.n_qblocks, tiles_total));
+        // an even number of query blocks runs as CTA pairs (cta_group::2): query blocks 2j and 2j+1 of a slice share every
+        // corpus tile, each CTA stages half of it
+        bool pair = false;
+        if (!h->no_pair && gp.n_qblocks % 2 == 0) {
+            const int max_pairs = gemm_max_pairs(h->dp, L, h->bias != nullptr);
+            if (max_pairs >= gp.n_qblocks / 2) {
+                pair = true;
+                gp.n_slices = std::max(1, std::min(gp.n_slices, max_pairs / (gp.n_qblocks / 2)));
+            }
+        }
         {   // seeding tiles per CTA: >= 128 tiles (32k rows) over the block's slices, more on long slices (<= 1/64 extra work)
             const int tiles_per_cta = tiles_total / gp.n_slices;
             const int want = std::max((128 + gp.n_slices - 1) / gp.n_slices, std::min(tiles_per_cta / 64, 8));
@@ -887,8 +899,9 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
             if (gp.seed_tiles && h->seed_tiles_override > 0) gp.seed_tiles = std::min(h->seed_tiles_override, std::max(1, tiles_per_cta / 2));
         }
         un.max_entries = pool_mode ? GEMM_POOL_CAP : gp.n_slices * GEMM_HALVES * L;
+        if (h->trace_on) B2R_CUDA(cudaMemsetAsync(h->trace.p, 0, sizeof(unsigned long long) * 8 * (size_t)h->sm_count, s));
         KernelTimer kt(h, s);
-        B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, h->tm_query, h->tm_corpus, gp, s));
+        B2R_CUDA(gemm_launch(h->dp, L, h->bias != nullptr, pair, h->tm_query, pair ? h->tm_corpus_half : h->tm_corpus, gp, s));
         kt.stop();
         h->trace_ctas = gp.n_slices * gp.n_qblocks;
         h->n_launches++;

@@ -61,7 +61,8 @@ bool gemm_supported(int dp, int k);
 int gemm_list_len(int k);          // per-thread list length L for n_results = k; 0 = pool mode (32 < k <= 128); -1 = unsupported
 int gemm_tile_rows(int dp);        // corpus rows per MMA tile (BN)
 int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, int box_rows);
-cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
+int gemm_max_pairs(int dp, int L, bool bias);   // co-resident CTA pairs of the cta_group::2 form (0 = unusable)
+cudaError_t gemm_launch(int dp, int L, bool bias, bool pair, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
                         const GemmParams &p, cudaStream_t s);
 cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_mask, const uint32_t *allow_bits,
                              unsigned n, unsigned n_words, uint32_t *out, int sm_count, cudaStream_t s);
@@ -103,7 +104,7 @@ struct b2r_index {
     b2r::DevBuf q_eps;              // [nq][2] fp64: per-query error bound and |q|^2 (query preparation)
 
     // TMA tensor maps (K3), re-encoded when the buffer they describe moves or grows
-    CUtensorMap tm_corpus, tm_query;
+    CUtensorMap tm_corpus, tm_corpus_half, tm_query;     // corpus boxes of a whole tile / of half a tile (CTA pairs)
     const void *tm_corpus_base = nullptr; int64_t tm_corpus_rows = -1;
     const void *tm_query_base = nullptr; int64_t tm_query_rows = -1;
     // the pass bitmap is reused while (rows, type mask, tombstones) are unchanged and no allow bitmap is given
@@ -122,6 +123,7 @@ struct b2r_index {
     // shard (default 32), B2R_TRACE=1 records per-CTA phase timestamps of the last K3 launch (b2r_debug_trace)
     unsigned long long seed_wait_ns = 0;
     int delay_us = 0, pool_sample_div = 32;
+    bool no_pair = false;           // B2R_NO_PAIR=1: never use the cta_group::2 form of K3
     b2r::DevBuf trace;
     bool trace_on = false; int trace_ctas = 0;
     int timing_stage = 0;           // which launch the events bracket: 0 scoring (default); B2R_TIME_STAGE=1, 4, 5 (development):

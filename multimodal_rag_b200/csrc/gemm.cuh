@@ -87,7 +87,8 @@ struct GemmParams {
     // development knobs (0 in production; b2r_create reads them from the environment)
     unsigned long long seed_wait_ns;   // overrides the wait budget of the seeding phase (1 = do not wait at all)
     int delay_us;                // every third slice sleeps this long before it posts its samples (a slow CTA)
-    unsigned long long *trace;   // [grid][4] globaltimer: epilogue start, posted, seeded, done (nullptr = off)
+    unsigned long long *trace;   // [grid][8]: globaltimer at epilogue start, posted, seeded, done; then SM cycles the MMA thread waited for an
+                                 // empty accumulator / for operands, the first epilogue warp for a full accumulator, the producer for a free slot (nullptr = off)
 };
 
 // Up to 512 dims (KB <= 8) the query block stays resident in shared memory (KB * 16 KB) and a pipeline stage
@@ -95,14 +96,19 @@ struct GemmParams {
 // streamed too: a stage = query K-block (16 KB, an L2 hit every time) + corpus K-block (32 KB).
 __host__ __device__ constexpr bool gemm_a_resident(int KB) { return KB <= 8; }
 __host__ __device__ constexpr int gemm_bn(int KB) { return 256; }
-__host__ __device__ constexpr int gemm_stage_bytes(int KB) { return gemm_bn(KB) * 128 + (gemm_a_resident(KB) ? 0 : GEMM_BM * 128); }
-__host__ __device__ constexpr int gemm_stages(int KB) {
+// PAIR: two CTAs of a cluster (the two SMs of a TPC) score 256 queries against the same corpus tile with one
+// tcgen05.mma.cta_group::2 (M = 256); each CTA stages only HALF of the tile's rows, the tensor core reads both halves,
+// so a corpus tile crosses L2 -> shared memory once per pair instead of once per query block.
+__host__ __device__ constexpr int gemm_stage_bytes(int KB, bool pair = false) {
+    return (pair ? gemm_bn(KB) / 2 : gemm_bn(KB)) * 128 + (gemm_a_resident(KB) ? 0 : GEMM_BM * 128);
+}
+__host__ __device__ constexpr int gemm_stages(int KB, bool pair = false) {
     int a = gemm_a_resident(KB) ? KB * GEMM_BM * 128 : 0;
-    int s = (GEMM_SMEM_LIMIT - GEMM_SMEM_SLACK - a) / gemm_stage_bytes(KB);
+    int s = (GEMM_SMEM_LIMIT - GEMM_SMEM_SLACK - a) / gemm_stage_bytes(KB, pair);
     return s > 8 ? 8 : s;
 }
-__host__ __device__ constexpr size_t gemm_smem_bytes(int KB) {
-    return (size_t)(gemm_a_resident(KB) ? KB * GEMM_BM * 128 : 0) + (size_t)gemm_stages(KB) * gemm_stage_bytes(KB) + 1024;
+__host__ __device__ constexpr size_t gemm_smem_bytes(int KB, bool pair = false) {
+    return (size_t)(gemm_a_resident(KB) ? KB * GEMM_BM * 128 : 0) + (size_t)gemm_stages(KB, pair) * gemm_stage_bytes(KB, pair) + 1024;
 }
 
 // ---------------------------------------------------------------------------------
@@ -151,6 +157,65 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// ---- CTA pair (cta_group::2) forms ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the pair's loads complete on the LEADER's mbarrier (rank 0 of the pair: the same shared-memory offset with the peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n mbarrier.arrive.shared::cluster.b64 _, [ra];\n}\n"
+        ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t parity) {     // acquire at cluster scope
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *slot, uint32_t ncols) {   // one warp in EACH CTA of the pair, same slot offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 in each CTA's smem] * B[N rows: N/2 in each CTA's smem]^T; the leader's elected thread issues
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0u;      // disable-output-lane mask: none
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z), "r"(z), "r"(z), "r"(z), "r"(z)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs when every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -687,19 +752,24 @@ __device__ __forceinline__ unsigned warp_lth_largest(const unsigned *vals, int n
 // ---------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------
-template <int KB, int L, bool HAS_BIAS>
+// PAIR = launched as clusters of two CTAs (query blocks 2j and 2j+1 of the same slice): the even CTA (cluster rank 0) is the
+// leader -- it owns the full / accumulator-empty barriers and issues every tcgen05.mma.cta_group::2 for the pair; both CTAs
+// load (their own query block, their half of each corpus tile) and both run the epilogue on their own 128 TMEM lanes.
+template <int KB, int L, bool HAS_BIAS, bool PAIR>
 // 10 warps = 3 on some SM sub-partition, whose register file is 16K: 168 registers per thread is the hard cap
 // (measured: __maxnreg__(192) compiles without spills but cannot launch)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
     constexpr int BN = gemm_bn(KB);
-    constexpr int STAGES = gemm_stages(KB);
+    constexpr int STAGES = gemm_stages(KB, PAIR);
     constexpr bool A_RES = gemm_a_resident(KB);
+    constexpr int NCTA = PAIR ? 2 : 1;
+    constexpr int B_ROWS = BN / NCTA;                       // corpus rows of a tile this CTA stages (tm_x's box has this many rows)
     constexpr uint32_t A_KB_BYTES = GEMM_BM * 128;          // one K-block of the query block
-    constexpr uint32_t B_STAGE_BYTES = BN * 128;            // one K-block of a corpus tile
-    constexpr uint32_t STAGE_BYTES = gemm_stage_bytes(KB);  // ring slot: corpus K-block (+ query K-block when streamed)
+    constexpr uint32_t B_STAGE_BYTES = B_ROWS * 128;        // one K-block of this CTA's share of a corpus tile
+    constexpr uint32_t STAGE_BYTES = gemm_stage_bytes(KB, PAIR);  // ring slot: corpus K-block (+ query K-block when streamed)
     constexpr uint32_t TMEM_COLS = 2 * BN;
-    constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM, BN);
+    constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM * NCTA, BN);
     static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
 
@@ -713,6 +783,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     unsigned char *smB = sm + (A_RES ? (size_t)KB * A_KB_BYTES : 0);   // [STAGES][BN rows][128 B] (+ [128 rows][128 B] streamed A)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;     // blockIdx.x & 1: the grid is launched in clusters of 2 along x
+    const bool leader = crank == 0u;
     const int qb = p.qblock0 + blockIdx.x % p.n_qblocks, slice = blockIdx.x / p.n_qblocks;
     const int t0 = (int)((long long)p.tiles_total * slice / p.n_slices);
     const int t1 = (int)((long long)p.tiles_total * (slice + 1) / p.n_slices);
@@ -725,12 +797,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tma_prefetch_desc(&tm_x);
         mbar_init(&bar_a, 1);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], GEMM_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], GEMM_EPI_WARPS * NCTA); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(&tmem_slot, TMEM_COLS); else tmem_alloc(&tmem_slot, TMEM_COLS); }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();     // the peer's barriers and TMEM exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     pdl_wait();          // everything above overlapped the previous kernel; queries / bounds / bitmap are read below
@@ -739,46 +811,64 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            auto load = [&](void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
+                if (PAIR) tma_load_2d_pair(dst, tm, bar, c0, c1); else tma_load_2d(dst, tm, bar, c0, c1);
+            };
             if (A_RES) {
-                mbar_expect_tx(&bar_a, KB * A_KB_BYTES);
-                for (int kb = 0; kb < KB; ++kb) tma_load_2d(smA + (size_t)kb * A_KB_BYTES, &tm_q, &bar_a, kb * 64, qb * GEMM_BM);
+                if (leader) mbar_expect_tx(&bar_a, NCTA * KB * A_KB_BYTES);
+                for (int kb = 0; kb < KB; ++kb) load(smA + (size_t)kb * A_KB_BYTES, &tm_q, &bar_a, kb * 64, qb * GEMM_BM);
             }
             int stage = 0; uint32_t phase = 0;
+            long long w_empty = 0;
             for (int i = 0; i < n_iter; ++i) {
                 const int t = i < S ? t0 + i : t0 + i - S;      // the seeding tiles are scanned again by the main loop
                 for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&bar_empty[stage], phase ^ 1);
-                    mbar_expect_tx(&bar_full[stage], STAGE_BYTES);
-                    if (!A_RES) tma_load_2d(smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES, &tm_q, &bar_full[stage], kb * 64, qb * GEMM_BM);
-                    tma_load_2d(smB + (size_t)stage * STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * BN);
+                    if (p.trace) { const long long c0 = clock64(); mbar_wait(&bar_empty[stage], phase ^ 1); w_empty += clock64() - c0; }
+                    else mbar_wait(&bar_empty[stage], phase ^ 1);
+                    if (leader) mbar_expect_tx(&bar_full[stage], NCTA * STAGE_BYTES);     // both CTAs' bytes land on the leader's barrier
+                    if (!A_RES) load(smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES, &tm_q, &bar_full[stage], kb * 64, qb * GEMM_BM);
+                    load(smB + (size_t)stage * STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * BN + (int)crank * B_ROWS);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.trace) p.trace[(size_t)blockIdx.x * 8 + 7] = (unsigned long long)w_empty;
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (the leader's elected thread issues for the pair) =====
+        if (lane == 0 && leader) {
+            auto commit = [&](uint64_t *bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             if (A_RES) { mbar_wait(&bar_a, 0); tc_fence_after(); }
             int stage = 0; uint32_t phase = 0;
+            long long w_tempty = 0, w_full = 0;
             for (int it = 0; it < n_iter; ++it) {
                 const int buf = it & 1;
+                long long c0 = p.trace ? clock64() : 0;
+                // (PAIR: the peer's epilogue warps arrive remotely.  Default-scope arrive / try_wait, as CUTLASS's 2-SM pipelines use:
+                // the cluster-scope release/acquire forms cost ~1500 cycles per tile here; what is handed over is TMEM, ordered by
+                // the tcgen05 fences on both sides)
                 mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1);
+                if (p.trace) w_tempty += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(buf * BN);
                 for (int kb = 0; kb < KB; ++kb) {
+                    if (p.trace) c0 = clock64();
                     mbar_wait(&bar_full[stage], phase);
+                    if (p.trace) w_full += clock64() - c0;
                     tc_fence_after();
                     const uint64_t ad = umma_smem_desc(smem_u32(A_RES ? smA + (size_t)kb * A_KB_BYTES
                                                                           : smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES));
                     const uint64_t bd = umma_smem_desc(smem_u32(smB + (size_t)stage * STAGE_BYTES));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)      // UMMA_K = 16 bf16 = 32 B: +2 in the (>>4) address field
-                        umma_bf16_ss(d, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(&bar_empty[stage]);                  // smem slot free once these MMAs retire
-                    if (kb == KB - 1) umma_commit(&bar_tfull[buf]);  // accumulator complete
+                    for (int k = 0; k < 4; ++k) {    // UMMA_K = 16 bf16 = 32 B: +2 in the (>>4) address field
+                        if (PAIR) umma_bf16_ss_pair(d, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        else umma_bf16_ss(d, ad + 2 * k, bd + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    commit(&bar_empty[stage]);                  // smem slot free (in both CTAs) once these MMAs retire
+                    if (kb == KB - 1) commit(&bar_tfull[buf]);  // accumulator complete (in both CTAs)
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.trace) { p.trace[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)w_tempty; p.trace[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)w_full; }
         }
     } else {
         // ===== epilogue: thread = query, column = corpus row =====
@@ -830,13 +920,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             fold_pending = false;
         };
 
+        const bool tracer = p.trace != nullptr && warp == 2 && lane == 0;
+        long long w_tfull = 0;
         // one tile: TMEM -> registers in 32-column steps, two register buffers so the next load flies under this step
         auto run_tile = [&](int t, int it, auto sample_c, auto &slist) {
             constexpr bool SMP = decltype(sample_c)::value;
             const int buf = it & 1;
             if (!SMP && fold_pending && fold_ready()) fold_share();     // a fold that had to be put off (a slice was late)
             if (!SMP && g_next > g_seen) { g_seen = g_next; thr = fmaxf(thr, KeyS::unord(g_next)); }
-            mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
+            if (tracer) { const long long c0 = clock64(); mbar_wait(&bar_tfull[buf], (it >> 1) & 1); w_tfull += clock64() - c0; }
+            else mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             // the other slices' progress on this query: loaded now, consumed at the top of the next tile
             if (!SMP) g_next = *reinterpret_cast<volatile unsigned *>(gq);
@@ -861,17 +954,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+            if (lane == 0) { if (PAIR) mbar_arrive_remote(&bar_tempty[buf], 0u); else mbar_arrive(&bar_tempty[buf]); }
         };
 
-        const bool tracer = p.trace != nullptr && warp == 2 && lane == 0;
-        if (tracer) p.trace[(size_t)blockIdx.x * 4 + 0] = globaltimer_ns();
+        if (tracer) p.trace[(size_t)blockIdx.x * 8 + 0] = globaltimer_ns();
         int it = 0;
         if (p.seed_tiles > 0) {
             // ---- seeding phase ----
             // 1. the first S tiles of the slice in sampling mode: the list collects the best step maxima
             const unsigned long long t_begin = __shfl_sync(FULL_MASK, globaltimer_ns(), 0);   // warp-uniform clock readings
             RegList<LS> slist; slist.init();
+            {   // A sampling step consumes its word of the pass bitmap at once (the main loop only on a hit): fetch the words of
+                // the sampling tiles now, while the first tile is still on its way, or every step pays a cold DRAM round trip
+                const uint32_t *pb = p.pass_bits + (((unsigned)t0 * BN) >> 5);
+                unsigned warm = 0u;
+                for (int w = lane; w < S * (BN / 32); w += 32) warm |= __ldg(pb + w);
+                asm volatile("" ::"r"(warm));
+            }
             for (int i = 0; i < S; ++i, ++it) run_tile(t0 + i, it, std::true_type(), slist);
             if (p.delay_us > 0 && slice % 3 == 1) {            // development: a slow CTA
                 const unsigned long long t_d = globaltimer_ns();
@@ -894,7 +993,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             epi_bar_sync();                                   // every epilogue thread's post is fenced
             if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(p.arrive + qb, 1u); }
             const unsigned long long t_post = __shfl_sync(FULL_MASK, globaltimer_ns(), 0);
-            if (tracer) p.trace[(size_t)blockIdx.x * 4 + 1] = t_post;
+            if (tracer) p.trace[(size_t)blockIdx.x * 8 + 1] = t_post;
             unsigned long long budget = GEMM_SEED_TIMEOUT_NS;
             if (L == 0) budget = min(max(2ull * (t_post - t_begin), GEMM_POOL_WAIT_MIN_NS), GEMM_POOL_WAIT_MAX_NS);
             if (p.seed_wait_ns) budget = p.seed_wait_ns;
@@ -919,10 +1018,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
             __syncwarp();
         }
-        if (tracer) p.trace[(size_t)blockIdx.x * 4 + 2] = globaltimer_ns();
+        if (tracer) p.trace[(size_t)blockIdx.x * 8 + 2] = globaltimer_ns();
         for (int t = t0; t < t1; ++t, ++it) run_tile(t, it, std::false_type(), list);
         if (fold_pending && fold_ready()) fold_share();          // last chance before this CTA leaves
-        if (tracer) p.trace[(size_t)blockIdx.x * 4 + 3] = globaltimer_ns();
+        if (tracer) { p.trace[(size_t)blockIdx.x * 8 + 3] = globaltimer_ns(); p.trace[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)w_tfull; }
 
         if (L == 0) {
             if (q < p.nq && rcount > 0) {     // compact the private region into the query's pool
@@ -961,8 +1060,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+    if (PAIR) cluster_sync_all(); else __syncthreads();     // neither CTA of a pair leaves while the other may still reach its memory
+    if (warp == 1) { tc_fence_after(); if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 }  // namespace b2r

@@ -13,22 +13,24 @@ typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmParams);
 #ifdef B2R_KB
 #define B2R_CAT2(a, b) a##b
 #define B2R_CAT(a, b) B2R_CAT2(a, b)
-gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias) {
-    if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true> : gemm_topk_kernel<B2R_KB, 8, false>;
-    if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true> : gemm_topk_kernel<B2R_KB, 16, false>;
-    if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true> : gemm_topk_kernel<B2R_KB, 32, false>;
-    if (L == 0) return bias ? gemm_topk_kernel<B2R_KB, 0, true> : gemm_topk_kernel<B2R_KB, 0, false>;   // pool mode
+template <bool PAIR>
+static gemm_fn pick(int L, bool bias) {
+    if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true, PAIR> : gemm_topk_kernel<B2R_KB, 8, false, PAIR>;
+    if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true, PAIR> : gemm_topk_kernel<B2R_KB, 16, false, PAIR>;
+    if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true, PAIR> : gemm_topk_kernel<B2R_KB, 32, false, PAIR>;
+    if (L == 0) return bias ? gemm_topk_kernel<B2R_KB, 0, true, PAIR> : gemm_topk_kernel<B2R_KB, 0, false, PAIR>;   // pool mode
     return nullptr;
 }
+gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias, bool pair) { return pair ? pick<true>(L, bias) : pick<false>(L, bias); }
 }  // namespace b2r
 #else
-gemm_fn gemm_lookup_2(int, bool);
-gemm_fn gemm_lookup_4(int, bool);
-gemm_fn gemm_lookup_6(int, bool);
-gemm_fn gemm_lookup_8(int, bool);
-gemm_fn gemm_lookup_12(int, bool);
-gemm_fn gemm_lookup_16(int, bool);
-gemm_fn gemm_lookup_24(int, bool);
+gemm_fn gemm_lookup_2(int, bool, bool);
+gemm_fn gemm_lookup_4(int, bool, bool);
+gemm_fn gemm_lookup_6(int, bool, bool);
+gemm_fn gemm_lookup_8(int, bool, bool);
+gemm_fn gemm_lookup_12(int, bool, bool);
+gemm_fn gemm_lookup_16(int, bool, bool);
+gemm_fn gemm_lookup_24(int, bool, bool);
 
 // ---------------------------------------------------------------------------------
 // pass bitmap: bit r of word r>>5 = row r is live, passes the type mask and the allow bitmap.
@@ -48,27 +50,27 @@ static __global__ void pass_bits_kernel(const uint8_t *__restrict__ type_code, u
 
 
 namespace {
-gemm_fn lookup(int kb, int L, bool bias) {
+gemm_fn lookup(int kb, int L, bool bias, bool pair) {
     switch (kb) {
-        case 2:  return gemm_lookup_2(L, bias);
-        case 4:  return gemm_lookup_4(L, bias);
-        case 6:  return gemm_lookup_6(L, bias);     // all-MiniLM-L6-v2 (384)
-        case 8:  return gemm_lookup_8(L, bias);     // CLIP ViT-B/32 shape (512)
-        case 12: return gemm_lookup_12(L, bias);    // 768
-        case 16: return gemm_lookup_16(L, bias);    // 1024
-        case 24: return gemm_lookup_24(L, bias);    // 1536
+        case 2:  return gemm_lookup_2(L, bias, pair);
+        case 4:  return gemm_lookup_4(L, bias, pair);
+        case 6:  return gemm_lookup_6(L, bias, pair);     // all-MiniLM-L6-v2 (384)
+        case 8:  return gemm_lookup_8(L, bias, pair);     // CLIP ViT-B/32 shape (512)
+        case 12: return gemm_lookup_12(L, bias, pair);    // 768
+        case 16: return gemm_lookup_16(L, bias, pair);    // 1024
+        case 24: return gemm_lookup_24(L, bias, pair);    // 1536
         default: return nullptr;
     }
 }
-size_t smem_of(int kb) {
+size_t smem_of(int kb, bool pair) {
     switch (kb) {
-        case 2:  return gemm_smem_bytes(2);
-        case 4:  return gemm_smem_bytes(4);
-        case 6:  return gemm_smem_bytes(6);
-        case 8:  return gemm_smem_bytes(8);
-        case 12: return gemm_smem_bytes(12);
-        case 16: return gemm_smem_bytes(16);
-        case 24: return gemm_smem_bytes(24);
+        case 2:  return gemm_smem_bytes(2, pair);
+        case 4:  return gemm_smem_bytes(4, pair);
+        case 6:  return gemm_smem_bytes(6, pair);
+        case 8:  return gemm_smem_bytes(8, pair);
+        case 12: return gemm_smem_bytes(12, pair);
+        case 16: return gemm_smem_bytes(16, pair);
+        case 24: return gemm_smem_bytes(24, pair);
         default: return 0;
     }
 }
@@ -96,7 +98,7 @@ encode_fn get_encode() {
 // per-thread list length for n_results = k; 0 = pool mode (no lists, 32 < k <= 128); -1 = unsupported
 int gemm_list_len(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : k <= 128 ? 0 : -1; }
 int gemm_tile_rows(int dp) { return gemm_bn(dp / 64); }
-bool gemm_supported(int dp, int k) { return dp % 64 == 0 && lookup(dp / 64, 8, false) != nullptr && gemm_list_len(k) >= 0; }
+bool gemm_supported(int dp, int k) { return dp % 64 == 0 && lookup(dp / 64, 8, false, false) != nullptr && gemm_list_len(k) >= 0; }
 
 // [rows, dp] bf16 row-major -> 2-D tensor map, box = 64 elements (128 B, one swizzle row) x box_rows
 int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, int box_rows) {
@@ -113,26 +115,72 @@ int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, i
     return B2R_OK;
 }
 
-cudaError_t gemm_launch(int dp, int L, bool bias, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
-                        const GemmParams &p, cudaStream_t s) {
-    const int kb = dp / 64;
-    gemm_fn f = lookup(kb, L, bias);
-    if (!f) return cudaErrorInvalidValue;
-    const size_t smem = smem_of(kb);
+static cudaError_t gemm_prepare(gemm_fn f, size_t smem) {
     static std::mutex mu;
     static std::map<std::tuple<int, const void *>, bool> done;
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        std::lock_guard<std::mutex> g(mu);
-        auto key = std::make_tuple(dev, (const void *)f);
-        if (!done.count(key)) {
-            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            done[key] = true;
-        }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    auto key = std::make_tuple(dev, (const void *)f);
+    if (!done.count(key)) {
+        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        done[key] = true;
     }
-    return launch_pdl(f, dim3(p.n_slices * p.n_qblocks), dim3(GEMM_THREADS), smem, s, tm_q, tm_x, p);
+    return cudaSuccess;
+}
+
+// CTA pairs (clusters of 2) of the pair kernel that can be co-resident on this device: 0 = the pair form is not usable
+int gemm_max_pairs(int dp, int L, bool bias) {
+    const int kb = dp / 64;
+    gemm_fn f = lookup(kb, L, bias, true);
+    if (!f) return 0;
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void *>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(std::make_tuple(dev, (const void *)f));
+        if (it != cache.end()) return it->second;
+    }
+    const size_t smem = smem_of(kb, true);
+    int n = 0;
+    if (gemm_prepare(f, smem) == cudaSuccess) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, f, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    }
+    std::lock_guard<std::mutex> g(mu);
+    cache[std::make_tuple(dev, (const void *)f)] = n;
+    return n;
+}
+
+// pair = launch clusters of two CTAs (query blocks 2j, 2j+1 of a slice); tm_x must then describe half-tile boxes
+cudaError_t gemm_launch(int dp, int L, bool bias, bool pair, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
+                        const GemmParams &p, cudaStream_t s) {
+    const int kb = dp / 64;
+    gemm_fn f = lookup(kb, L, bias, pair);
+    if (!f) return cudaErrorInvalidValue;
+    const size_t smem = smem_of(kb, pair);
+    cudaError_t e = gemm_prepare(f, smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.n_slices * p.n_qblocks); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (pair) {
+        at[1].id = cudaLaunchAttributeClusterDimension;
+        at[1].val.clusterDim.x = 2; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
+    return cudaLaunchKernelEx(&cfg, f, tm_q, tm_x, p);
 }
 
 cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_mask, const uint32_t *allow_bits,

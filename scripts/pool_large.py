@@ -1,7 +1,7 @@
 """Pool mode (32 < k <= 128) on large shards: time, fall-backs, pool size, per-CTA phase skew, parity against the exact
 fp64 path on a sample of the batch.  Development aid (BASELINE config 4 per-GPU shapes: 12.5M / 25M / 50M rows).
 
-    python scripts/pool_large.py ROWS [NQ K ITERS CHECK]      env: B2R_TRACE=1 B2R_DELAY_US=.. B2R_SEED_WAIT_NS=.. B2R_NO_SEED=1
+    python scripts/pool_large.py ROWS [NQ K ITERS CHECK DIM]      env: B2R_TRACE=1 B2R_DELAY_US=.. B2R_SEED_WAIT_NS=.. B2R_NO_SEED=1
 """
 import ctypes, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,22 +22,26 @@ def build(rows, dim, seed=0xC4):
 
 
 def trace_summary(lib, sh):
-    buf = np.zeros((256, 4), dtype=np.uint64)
+    buf = np.zeros((256, 8), dtype=np.uint64)
     n = ctypes.c_int()
     _lib.check(lib.b2r_debug_trace(sh.h, buf.ctypes.data, 256, ctypes.byref(n)))
     if n.value == 0:
         return None
     t = buf[: n.value].astype(np.int64)
     t0 = t[:, 0].min()
-    rel = (t - t0) / 1e3
-    return {"ctas": n.value, "start_spread_us": float(rel[:, 0].max()), "posted_us": [float(rel[:, 1].min()), float(rel[:, 1].max())],
+    rel = (t[:, :4] - t0) / 1e3
+    wait = t[:, 4:]
+    waits = {"mma_wait_empty_acc_kcyc": [float(np.median(wait[:, 0][wait[:, 0] > 0]) / 1e3) if (wait[:, 0] > 0).any() else 0.0],
+             "mma_wait_operands_kcyc": [float(np.median(wait[:, 1][wait[:, 1] > 0]) / 1e3) if (wait[:, 1] > 0).any() else 0.0],
+             "epi_wait_full_acc_kcyc": float(np.median(wait[:, 2]) / 1e3), "producer_wait_slot_kcyc": float(np.median(wait[:, 3]) / 1e3)}
+    return {"waits": waits, "ctas": n.value, "start_spread_us": float(rel[:, 0].max()), "posted_us": [float(rel[:, 1].min()), float(rel[:, 1].max())],
             "seeded_us": [float(rel[:, 2].min()), float(rel[:, 2].max())], "done_us": [float(rel[:, 3].min()), float(np.median(rel[:, 3])), float(rel[:, 3].max())]}
 
 
 def main():
-    a = [int(x) for x in sys.argv[1:]] + [None] * 5
+    a = [int(x) for x in sys.argv[1:]] + [None] * 6
     rows, nq, k, iters, check = a[0] or 25_000_000, a[1] or 1024, a[2] or 100, a[3] or 3, a[4] if a[4] is not None else 8
-    dim = 384
+    dim = a[5] or 384
     lib = _lib.load()
     t0 = time.time()
     sh = build(rows, dim)
