@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 def test_config3_mixed_collection_type_filter_1m_x_512():
     """1M x 512-d mixed text+table+image rows, where={'type': ...}, top_k=10, batch 1 and batch 256.
     Properties: every returned row carries the requested type, results are sorted, planted neighbours
-    of the requested type are found, a planted neighbour of the WRONG type is never returned, and the
-    filtered answer equals an fp32 torch reference restricted to the same rows."""
+    of the requested type are found, a planted neighbour of the WRONG type is never returned.  (The bit-exact
+    comparison of this shape against the fp64 oracle is in test_gpu_fullsize.py.)"""
     import torch
     from multimodal_rag_b200 import _lib
     from multimodal_rag_b200.sharded import DeviceShard
@@ -56,11 +56,7 @@ def test_config3_mixed_collection_type_filter_1m_x_512():
         assert rows[:min(4, batch), 0].tolist() == planted[:min(4, batch)].tolist()
         if batch > 4:
             assert not torch.isin(rows[4:6], wrong).any()
-        S = Q[:batch] @ X.T
-        S[:, codes_d != 2] = -2.0
-        ref = torch.topk(S, k, dim=1).indices
-        assert (rows == ref).float().mean() > 0.999          # fp32 matmul noise may swap a near-tie
-        del S
+        # (ids bit-exact against the fp64 oracle restricted to the same rows: test_gpu_fullsize.py)
     st = _lib.B2RStats()
     _lib.check(lib.b2r_get_stats(sh.h, ctypes.byref(st)))
     assert st.n_exact_fallbacks == 0

@@ -38,6 +38,20 @@ def _worker(rank, world, port, n, d, nq, k, out):
         rows, dist_, cnt = sh.query_device(torch.from_numpy(Q).cuda(), k, o)
         torch.cuda.synchronize()
         res = {"rows": rows.cpu().numpy(), "dist": dist_.cpu().numpy(), "cnt": cnt.cpu().numpy()}
+        # the pipelined form (exchange of batch i on a side stream under the scan of batch i+1), two output sets
+        os_ = [sh.alloc_out(nq, k) for _ in range(2)]
+        Qd = torch.from_numpy(Q).cuda()
+        for i in range(5):
+            sh.query_device_pipelined(Qd, k, os_[i % 2])
+        sh.drain()
+        torch.cuda.synchronize()
+        res["pipelined_same"] = all(bool(torch.equal(o_["m_rows"], rows)) and bool(torch.equal(o_["m_dist"], dist_)) for o_ in os_)
+        # pool mode (top_k = 100) across the shards, a batch of two query blocks (CTA pairs)
+        Q2 = torch.from_numpy(make_unit(130, d, 8)).cuda()
+        o2 = sh.alloc_out(130, 100)
+        r2, d2, c2 = sh.query_device(Q2, 100, o2)
+        torch.cuda.synchronize()
+        res["rows100"], res["dist100"], res["cnt100"] = r2.cpu().numpy(), d2.cpu().numpy(), c2.cpu().numpy()
         sh.close()
         # (2) the Chroma-shaped collective collection with ids and a where clause
         sc = ShardedCollection("mm", {"hnsw:space": "cosine"}, device=rank)
@@ -68,6 +82,11 @@ def test_two_gpu_row_sharded_matches_oracle(tmp_path):
     for i in range(nq):
         np.testing.assert_array_equal(res["rows"][i, : res["cnt"][i]], er[i])
         np.testing.assert_allclose(res["dist"][i, : res["cnt"][i]], ed[i], rtol=1e-5, atol=1e-7)
+    assert res["pipelined_same"]
+    er3, ed3 = eo.topk_exact(eo.normalize_f32(make_unit(130, d, 8)), eo.normalize_f32(X), 100, "cosine")
+    for i in range(130):
+        np.testing.assert_array_equal(res["rows100"][i, : res["cnt100"][i]], er3[i])
+        np.testing.assert_allclose(res["dist100"][i, : res["cnt100"][i]], ed3[i], rtol=1e-5, atol=1e-7)
     mask = (np.arange(n) % 3 == 0)
     er2, _ = eo.topk_exact(eo.normalize_f32(Q[:4]), eo.normalize_f32(X), k, "cosine", allowed=mask)
     for i in range(4):

@@ -192,7 +192,10 @@ def test_large_corpus_properties():
     rows, dist, cnt = c.query_rows(Q, k)
     assert rows[:, 0].tolist() == planted.tolist()
     assert (np.diff(dist, axis=1) >= 0).all() and (cnt == k).all()
-    # torch fp32 reference of the same op (ids only; fp32 matmul is not the parity oracle)
-    ref = torch.topk(Q @ X.T, k, dim=1).indices.cpu().numpy()
-    np.testing.assert_array_equal(rows, ref)
+    # the fp64 C oracle over the same stored rows: ids bit-exact, distances to 1e-5 relative
+    from oracle import c_oracle
+    c_oracle.set_threads(0)
+    er, ed, _ = c_oracle.topk(c_oracle.normalize_f32(X.cpu().numpy()), c_oracle.normalize_f32(Q.cpu().numpy()), k, "cosine", acc64=True)
+    np.testing.assert_array_equal(rows, er)
+    np.testing.assert_allclose(dist, ed, rtol=1e-5, atol=1e-7)
     assert c.stats()["n_exact_fallbacks"] == 0
