@@ -887,7 +887,60 @@ def leg_config5(lib, _lib, dev, timed, summarize, hbm_roofline, pk, K):
                                    "unit": "GB/s", "frac": ing_rows * bytes_per_row / (ing_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}}}
     assert state["visible"], "an upserted row is not its own nearest neighbour in the next query"
     sh.close()
+    out["collection_api"] = leg_config5_collection(dev, rows0, dim, k, nq, up, out["ms_per_step"])
     return out
+
+
+def leg_config5_collection(dev, rows0, dim, k, nq, up, device_ms):
+    """The same streaming loop through the Chroma-shaped collection (string ids, host id tables): B200Collection.upsert
+    (~10 % of each batch overwrites existing ids) + B200Collection.query_rows, device-resident vectors in, numpy results
+    out.  Reported beside the raw-ABI number: what the host tables cost."""
+    import numpy as np
+    import torch
+    from multimodal_rag_b200 import B200Collection
+    steps = 24
+    c = B200Collection("config5", {"hnsw:space": "cosine"}, capacity=rows0 + (steps + 4) * up, device=dev.index)
+    g = torch.Generator(device=dev).manual_seed(0xC5)
+    t0 = time.perf_counter()
+    for s in range(0, rows0, 1 << 18):
+        m = min(1 << 18, rows0 - s)
+        c.add(ids=[f"r{i}" for i in range(s, s + m)],
+              embeddings=torch.nn.functional.normalize(torch.randn(m, dim, generator=g, device=dev), dim=1))
+    load_s = time.perf_counter() - t0
+    rng = np.random.default_rng(55)
+    base = torch.nn.functional.normalize(torch.randn(up, dim, generator=g, device=dev), dim=1)
+    Qb = torch.nn.functional.normalize(torch.randn(nq, dim, generator=g, device=dev), dim=1)
+    n_over = up // 10
+    batches = []
+    for j in range(steps + 2):
+        u = torch.roll(base, shifts=j + 1, dims=1).contiguous()
+        q = Qb.clone(); q[:8] = u[:8]
+        ids = [f"n{j}_{i}" for i in range(up)]
+        for t, o in enumerate(rng.integers(0, rows0, size=n_over).tolist()):
+            ids[up - 1 - t] = f"r{o}"                      # overwrite an existing id
+        ids = list(dict.fromkeys(ids))
+        batches.append((ids, u[: len(ids)], q))
+    torch.cuda.synchronize()
+    ok = True
+
+    def step(j):
+        ids, u, q = batches[j]
+        c.upsert(ids=ids, embeddings=u)
+        rows, dist, cnt = c.query_rows(q, k)
+        return rows, dist
+
+    for j in range(2):
+        rows, dist = step(j)
+    t0 = time.perf_counter()
+    for j in range(2, steps + 2):
+        rows, dist = step(j)
+        ok = ok and all(c._ids[r] == batches[j][0][i] for i, r in enumerate(rows[:8, 0].tolist())) and bool((np.abs(dist[:8, 0]) < 1e-5).all())
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    n_live = c.count()
+    c.close()
+    return {"api": "B200Collection.upsert(ids, device tensor) + B200Collection.query_rows(device tensor, k) -> numpy",
+            "qps": nq / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "visibility_check": ok, "live_rows_at_end": n_live,
+            "bulk_add_rows_per_s": rows0 / load_s, "slowdown_vs_raw_abi": ms / device_ms}
 
 
 def leg_config4(args, lib, _lib, dev, dist, rank, world, timed, summarize, sum_over_ranks, pk, K):

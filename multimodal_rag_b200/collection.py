@@ -88,7 +88,7 @@ class B200Collection:
         self._lock = threading.RLock()
         self._ids: list[str] = []
         self._docs: list = []
-        self._alive = np.zeros(0, dtype=bool)
+        self._alive_buf = np.zeros(1024, dtype=bool)     # tombstone table, grown x2 (amortised O(1) per row)
         self._row_of: dict[str, int] = {}
         self._meta = MetaTable()
         self.device_where = True      # general where clauses run on the device (False: host-evaluated bitmaps)
@@ -120,6 +120,19 @@ class B200Collection:
         return self._dim
 
     @property
+    def _alive(self) -> np.ndarray:
+        """bool per appended row: not tombstoned (a view of the growable table)"""
+        return self._alive_buf[: len(self._ids)]
+
+    def _alive_extend(self, n_new: int) -> None:
+        need = len(self._ids) + n_new
+        if need > self._alive_buf.shape[0]:
+            grown = np.zeros(max(need, 2 * self._alive_buf.shape[0]), dtype=bool)
+            grown[: len(self._ids)] = self._alive_buf[: len(self._ids)]
+            self._alive_buf = grown
+        self._alive_buf[len(self._ids): need] = True
+
+    @property
     def handle(self):
         return self._h
 
@@ -130,9 +143,9 @@ class B200Collection:
         if not isinstance(ids, (list, tuple)):
             raise ValueError("Expected ids to be a list of str")
         n = len(ids)
-        for i in ids:
-            if not isinstance(i, str) or not i:
-                raise ValueError(f"Expected ID to be a non-empty str, got {i!r}")
+        if not all(type(i) is str and i for i in ids):
+            bad = next(i for i in ids if not (isinstance(i, str) and i))
+            raise ValueError(f"Expected ID to be a non-empty str, got {bad!r}")
         if len(set(ids)) != n:
             seen, dup = set(), []
             for i in ids:
@@ -157,15 +170,21 @@ class B200Collection:
 
     # ---- mutations -------------------------------------------------------------------
     def _append_rows(self, ids, m: _Matrix, sel, metadatas, documents):
-        """Ingest rows `sel` (indices into the batch) and register them on the host."""
-        if not sel:
+        """Ingest rows `sel` (indices into the batch; None = the whole batch) and register them on the host."""
+        whole = sel is None or len(sel) == m.n
+        n = m.n if whole else len(sel)
+        if n == 0:
             return
         if self._h is None:
             self._open(m.d)
-        metas = [None if metadatas is None else metadatas[i] for i in sel]
-        # type codes must be known before the device call; MetaTable only commits below
-        codes = np.asarray([self._meta.type_code_of(md) for md in metas], dtype=np.uint8)
-        if len(sel) == m.n:
+        if metadatas is None:
+            metas, codes_ptr = None, None                  # bare vectors: type code 0 for every row, no per-row host work
+        else:
+            metas = list(metadatas) if whole else [metadatas[i] for i in sel]
+            # type codes must be known before the device call; MetaTable only commits below
+            codes = np.asarray([self._meta.type_code_of(md) for md in metas], dtype=np.uint8)
+            codes_ptr = codes.ctypes.data
+        if whole:
             ptr, keep = m.ptr, m.keep
         elif m.is_cuda:
             keep = m.keep[_torch().as_tensor(sel, device=m.keep.device)].contiguous()
@@ -174,18 +193,25 @@ class B200Collection:
             keep = np.ascontiguousarray(m.keep[sel])
             ptr = keep.ctypes.data
         first = ctypes.c_int64(-1)
-        _lib.check(self._lib.b2r_ingest_f32(self._h, ptr, len(sel), codes.ctypes.data, ctypes.byref(first),
-                                            m.stream), "b2r_ingest_f32")
+        _lib.check(self._lib.b2r_ingest_f32(self._h, ptr, n, codes_ptr, ctypes.byref(first), m.stream), "b2r_ingest_f32")
         assert first.value == len(self._ids), "host tables out of step with the device corpus"
-        for j, i in enumerate(sel):
-            self._row_of[ids[i]] = first.value + j
-            self._ids.append(ids[i])
-            self._docs.append(None if documents is None else documents[i])
-            self._meta.append(metas[j])
-        self._alive = np.concatenate([self._alive, np.ones(len(sel), dtype=bool)])
-        self._push_columns(first.value, len(sel), {k for md in metas if md for k in md})
+        new_ids = ids if whole else [ids[i] for i in sel]
+        self._alive_extend(n)
+        self._row_of.update(zip(new_ids, range(first.value, first.value + n)))
+        self._ids.extend(new_ids)
+        if documents is None:
+            self._docs.extend([None] * n)
+        else:
+            self._docs.extend(documents if whole else [documents[i] for i in sel])
+        if metas is None:
+            self._meta.append_none(n)
+        else:
+            for md in metas:
+                self._meta.append(md)
+            self._push_columns(first.value, n, {k for md in metas if md for k in md}, m.stream)
+        del keep
 
-    def _push_columns(self, first: int, n: int, keys):
+    def _push_columns(self, first: int, n: int, keys, stream=0):
         """Mirror the dictionary codes of rows [first, first + n) of the touched metadata keys to the device
         columns (b2r_column_set); keys beyond the 16 device columns stay host-only."""
         for key in keys:
@@ -195,37 +221,53 @@ class B200Collection:
             have = self._meta.cols[key].codes[first: first + n]      # the column may end before the batch does
             codes = np.full(n, -1, dtype=np.int32)
             codes[: have.shape[0]] = have
-            _lib.check(self._lib.b2r_column_set(self._h, ci, first, n, codes.ctypes.data, 0), "b2r_column_set")
+            _lib.check(self._lib.b2r_column_set(self._h, ci, first, n, codes.ctypes.data, stream), "b2r_column_set")
 
-    def _kill_rows(self, rows):
-        if not rows:
+    def _kill_rows(self, rows, stream=0):
+        if len(rows) == 0:
             return
-        arr = np.asarray(rows, dtype=np.int64)
-        _lib.check(self._lib.b2r_tombstone(self._h, arr.ctypes.data, arr.shape[0], 0), "b2r_tombstone")
-        self._alive[arr] = False
-        for r in rows:
-            self._row_of.pop(self._ids[r], None)
+        arr = np.ascontiguousarray(rows, dtype=np.int64)
+        _lib.check(self._lib.b2r_tombstone(self._h, arr.ctypes.data, arr.shape[0], stream), "b2r_tombstone")
+        self._alive_buf[arr] = False
+        ids = self._ids
+        for r in arr.tolist():
+            self._row_of.pop(ids[r], None)
 
     def add(self, ids, embeddings=None, metadatas=None, documents=None):
         """Chroma ``Collection.add``: ids already present are skipped (with a warning)."""
         with self._lock:
             ids, m = self._validate_batch(ids, embeddings, metadatas, documents)
-            sel = [i for i, id_ in enumerate(ids) if id_ not in self._row_of]
-            if len(sel) != len(ids):
+            row_of = self._row_of
+            if row_of.keys().isdisjoint(ids):
+                sel = None
+            else:
+                sel = [i for i, id_ in enumerate(ids) if id_ not in row_of]
                 logger.warning("Add of existing embedding ID(s) skipped: %d of %d", len(ids) - len(sel), len(ids))
             self._append_rows(ids, m, sel, metadatas, documents)
 
     def upsert(self, ids, embeddings=None, metadatas=None, documents=None):
-        """Chroma ``Collection.upsert``: existing ids are overwritten (tombstone + append)."""
+        """Chroma ``Collection.upsert``: existing ids are overwritten.  The new rows are appended FIRST and the old versions
+        tombstoned after that succeeded, so a failed ingest (out of memory while growing, a bad batch) leaves the old
+        versions in place; a query never sees both because both steps are enqueued on one stream before it."""
         with self._lock:
             ids, m = self._validate_batch(ids, embeddings, metadatas, documents)
-            old = [self._row_of[i] for i in ids if i in self._row_of]
+            row_of = self._row_of
+            old = [row_of[i] for i in ids if i in row_of] if not row_of.keys().isdisjoint(ids) else []
             if self._h is None and ids:
                 self._open(m.d)
-            self._kill_rows(old)
-            self._append_rows(ids, m, list(range(len(ids))), metadatas, documents)
+            self._append_rows(ids, m, None, metadatas, documents)       # re-points _row_of[id] at the new rows
+            if old:
+                arr = np.asarray(old, dtype=np.int64)
+                _lib.check(self._lib.b2r_tombstone(self._h, arr.ctypes.data, arr.shape[0], m.stream), "b2r_tombstone")
+                self._alive_buf[arr] = False
 
-    def delete(self, ids=None, where=None):
+    def delete(self, ids=None, where=None, where_document=None):
+        """Chroma ``Collection.delete``: by ids and / or a where clause.  With neither, chromadb 0.4.22 raises instead of
+        wiping the collection (the reference empties a collection through delete_collection, embedder.py:669-678)."""
+        if where_document:
+            raise NotImplementedError("where_document ($contains) is not part of the reference's hot path")
+        if (ids is None or (not isinstance(ids, str) and len(ids) == 0)) and not where:
+            raise ValueError("You must provide either ids, where, or where_document to delete.")
         with self._lock:
             rows = self._select_rows(ids, where)
             self._kill_rows(rows)
@@ -240,17 +282,24 @@ class B200Collection:
             return n
 
     # ---- reads -----------------------------------------------------------------------
+    def _where_mask(self, where) -> np.ndarray:
+        """bool per row: live AND matching `where`.  The clause runs on the device columns (b2r_filter_eval) like a
+        query's would; clauses the device cannot run fall back to the host tables inside `_filter`."""
+        if self._h is None or not self._ids:
+            return np.zeros(len(self._ids), dtype=bool)
+        return self.filter_bits(where)
+
     def _select_rows(self, ids, where):
         if ids is not None:
             if isinstance(ids, str):
                 ids = [ids]
             rows = sorted(self._row_of[i] for i in ids if i in self._row_of)
-            if where:
-                mask = self._meta.mask(where)
+            if where and rows:
+                mask = self._where_mask(where)
                 rows = [r for r in rows if mask[r]]
             return rows
         if where:
-            mask = self._meta.mask(where) & self._alive
+            mask = self._where_mask(where)
         else:
             mask = self._alive
         return np.flatnonzero(mask).tolist()
@@ -471,9 +520,9 @@ class B200Collection:
         c._meta.type_overflow = bool(t["type_overflow"])
         for md in t["metadatas"]:
             c._meta.append(md)
-        c._alive = np.ones(len(c._ids), dtype=bool)
-        c._alive[np.asarray(t["dead_rows"], dtype=np.int64)] = False
-        c._row_of = {id_: r for r, id_ in enumerate(c._ids) if c._alive[r]}
+        c._alive_buf = np.ones(max(len(c._ids), 1024), dtype=bool)
+        c._alive_buf[np.asarray(t["dead_rows"], dtype=np.int64)] = False
+        c._row_of = {id_: r for r, id_ in enumerate(c._ids) if c._alive_buf[r]}
         if c._h is not None:
             c._push_columns(0, len(c._ids), list(c._meta.cols))
             st = c.stats()

@@ -80,27 +80,46 @@ class ShardedCollection:
 
     def _ingest(self, ids, embeddings, metadatas, documents, upsert):
         n = len(ids)
+        # the WHOLE batch is validated on EVERY rank before any rank-local work: a bad batch raises everywhere, so no
+        # rank is left waiting in the next collective for one that bailed out
         if len(set(ids)) != n:
             raise ValueError("Expected IDs to be unique")
+        if not all(isinstance(i, str) and i for i in ids):
+            raise ValueError("Expected IDs to be non-empty strings")
         emb = embeddings if isinstance(embeddings, (np.ndarray, torch.Tensor)) else np.asarray(embeddings, dtype=np.float32)
-        if len(emb) != n:
+        if emb.ndim != 2 or len(emb) != n:
             raise ValueError(f"Number of embeddings {len(emb)} must match number of ids {n}")
+        dim = getattr(self.shard, "dimension", None)
+        if dim is not None and emb.shape[1] != dim:
+            raise ValueError(f"Embedding dimension {emb.shape[1]} does not match collection dimensionality {dim}")
+        for name, lst in (("metadatas", metadatas), ("documents", documents)):
+            if lst is not None and len(lst) != n:
+                raise ValueError(f"Number of {name} {len(lst)} must match number of ids {n}")
+        if metadatas is not None:
+            from .where import MetaTable
+            for md in metadatas:
+                MetaTable.validate(md)
         have_local = [i for i in ids if i in self.shard._row_of]
         have = set().union(*self._all_gather_obj(have_local))
         if upsert:
-            if have_local:
-                self.shard.delete(ids=have_local)
             new = list(range(n))
         else:
             new = [j for j, i in enumerate(ids) if i not in have]
         lo, hi = self._slice(len(new))
         mine = new[lo:hi]
+        if upsert and have_local:
+            # the old versions go only after the batch was accepted everywhere (validated above); an id keeps living on
+            # the rank that first stored it unless this rank's slice of the batch carries it again
+            stay = set(ids[j] for j in mine)
+            gone = [i for i in have_local if i not in stay]
+            if gone:
+                self.shard.delete(ids=gone)
         if mine:
             if isinstance(emb, torch.Tensor):
                 e = emb[torch.as_tensor(mine, device=emb.device)]
             else:
                 e = emb[np.asarray(mine)]
-            self.shard.add(ids=[ids[j] for j in mine], embeddings=e,
+            (self.shard.upsert if upsert else self.shard.add)(ids=[ids[j] for j in mine], embeddings=e,
                            metadatas=None if metadatas is None else [metadatas[j] for j in mine],
                            documents=None if documents is None else [documents[j] for j in mine])
             self._gseq = np.concatenate([self._gseq, self._next_seq + np.asarray(range(lo, hi), dtype=np.int64)])
@@ -114,6 +133,8 @@ class ShardedCollection:
         self._ingest(list(ids), embeddings, metadatas, documents, upsert=True)
 
     def delete(self, ids=None, where=None):
+        if (ids is None or len(ids) == 0) and not where:
+            raise ValueError("You must provide either ids, where, or where_document to delete.")
         if ids is not None:
             ids = [i for i in ids if i in self.shard._row_of]
             if not ids and where is None:

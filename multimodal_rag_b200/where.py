@@ -126,6 +126,11 @@ class MetaTable:
                 col.set(row, v)
         return self.type_code_of(meta)
 
+    def append_none(self, n: int) -> None:
+        """n rows without metadata (bulk adds of bare vectors): no per-row work"""
+        self.nrows += n
+        self.meta.extend([None] * n)
+
     def clear(self):
         self.__init__()
 

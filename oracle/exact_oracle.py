@@ -180,6 +180,10 @@ class ExactCollection:
         self._alive: list[bool] = []
         self._row_of: dict[str, int] = {}
 
+    @property
+    def dimension(self):
+        return self.dim
+
     # -- helpers -----------------------------------------------------------
     def _coerce(self, embeddings):
         e = np.asarray(embeddings, dtype=np.float32)

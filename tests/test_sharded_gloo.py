@@ -44,6 +44,13 @@ class OracleShard:
     def add(self, **kw):
         self.c.add(**kw)
 
+    def upsert(self, **kw):
+        self.c.upsert(**kw)
+
+    @property
+    def dimension(self):
+        return self.c.dim
+
     def delete(self, ids=None, where=None):
         self.c.delete(ids=ids, where=where)
 
