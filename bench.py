@@ -567,6 +567,14 @@ def run_gpu(args):
         Q2h = [q.cpu().pin_memory() for q in Q2]
         o2 = sh2.alloc_out(nq, k)
         o2b = [sh2.alloc_out(nq, k) for _ in range(2)]
+        # the un-pipelined NCCL form first (scan -> all_gather -> merge on one stream): the baseline the library's own exchange replaces
+        def step_sharded_nccl(i):
+            sh2.query_device(Q2[i % n_batches], k, o2)
+        for i in range(W):
+            step_sharded_nccl(i)
+        shd_nccl = summarize(timed(step_sharded_nccl, K, min_s=0.2), K)
+        if args.p2p_exchange:
+            sh2.enable_p2p_exchange(nq_max=max(nq, 1024), k_max=128)
 
         def step_sharded(i):
             # the exchange of batch i (all_gather + merge, side stream) overlaps the scan of batch i+1; the last step of a
@@ -623,12 +631,15 @@ def run_gpu(args):
         line.update({"value": world * nq / (shd["ms_per_step"] * 1e-3), **shd,
                      "merged_queries_per_s": nq / (shd["ms_per_step"] * 1e-3),
                      "ms_per_step_per_rank": per_rank_ms, "verified": True, "verified_how": detail if rank == 0 else None,
-                     "comm": {"backend": "nccl", "nranks": world, "collectives_per_step": 1,
-                              "collective": "all_gather of the packed [batch, top_k] x (int64 row, fp64 distance) + [batch] int32 count block",
+                     "comm": {"backend": "nccl" if not args.p2p_exchange else "nccl for setup and timing reductions; data path: peer-to-peer stores over NVLink (b2r_xchg_push / b2r_xchg_merge)",
+                              "nranks": world, "collectives_per_step": 1,
+                              "collective": "exchange of the per-rank [batch, top_k] x (int64 row, fp64 distance) + [batch] int32 count lists",
                               "bytes_sent_per_rank_per_step": bytes_per_rank, "bytes_gathered_per_rank_per_step": world * bytes_per_rank,
-                              "exchange": "all_gather + merge of batch i on a side stream, overlapping the scan of batch i+1 (DeviceShard.query_device_pipelined)",
+                              "exchange": sh2.exchange_mode + "; issued on a side stream behind an event so that it overlaps the scan of the next batch (DeviceShard.query_device_pipelined)",
                               "serial_ms_per_step": shd_serial["ms_per_step"],
-                              "serial_note": "scan -> all_gather -> merge on one stream: the latency of one batch"},
+                              "serial_note": "scan -> exchange -> merge on one stream: the latency of one batch",
+                              "nccl_all_gather_ms_per_step": shd_nccl["ms_per_step"],
+                              "nccl_note": "the same step with torch.distributed all_gather_into_tensor + b2r_merge_shards_packed on one stream"},
                      "e2e": {"value": world * nq / (shd_e2e["ms_per_step"] * 1e-3), "unit": UNIT, **shd_e2e,
                              "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * k * 12 + nq * 4,
                              "api": "DeviceShard.query_host: pinned host batch -> H2D -> b2r_query_ex -> all_gather -> merge -> D2H of the merged "
@@ -1023,6 +1034,8 @@ def main():
     ap.add_argument("--no-hnsw", action="store_true", help="skip the HNSW restatement inside the CPU legs")
     ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the 100M-row config-4 leg")
     ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the config3 / config5 legs")
+    ap.add_argument("--p2p-exchange", action="store_true", help="N > 1: the library's own exchange (b2r_xchg_push / b2r_xchg_merge: peer-to-peer stores + "
+                    "stream memory operations) instead of the NCCL all_gather; measured slower at the headline shape, see profiles/r2_exchange.md")
     ap.add_argument("--c4-rows", type=int, default=100_000_000, help="total rows of the config-4 leg")
     args = ap.parse_args()
     if args.impl == "reference":

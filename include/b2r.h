@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B2R_ABI_VERSION 2
+#define B2R_ABI_VERSION 3
 
 typedef struct b2r_index *b2r_handle;
 
@@ -200,6 +200,25 @@ int b2r_merge_shards(const int64_t *in_rows, const double *in_dist64, const int3
 int b2r_merge_shards_packed(const void *packed, int64_t shard_stride, int64_t off_rows, int64_t off_dist64,
                             int64_t off_count, int nshards, int nq, int k, int64_t *out_rows, float *out_dist,
                             int32_t *out_count, int device, void *stream);
+
+/* The same exchange + merge WITHOUT a collective library on the data path.  Every rank owns a mailbox (device memory
+ * allocated by this library, mapped into the other processes with CUDA IPC).  b2r_xchg_push (enqueue on the stream of the
+ * scan) stores this rank's lists straight into every peer's mailbox over NVLink and publishes a sequence number there;
+ * b2r_xchg_merge (same stream, or another one so that the exchange of batch i overlaps the scan of batch i+1) makes its stream
+ * wait for the peers' sequence numbers with stream memory operations -- no SM spins while a peer is late -- and merges.  Two
+ * mailbox slots alternate; a slot is rewritten only after every rank has read it.  Collective: every rank makes the same
+ * sequence of push / merge calls (same nq, k).  Setup: b2r_xchg_create on every rank, exchange the 64-byte handles by any
+ * means (torch.distributed all_gather_object), b2r_xchg_open with all of them in rank order, then a barrier.  world <= 8.
+ * No reference counterpart: the reference is single-process.                                                              */
+typedef struct b2r_xchg *b2r_xchg_handle;
+int b2r_xchg_create(int device, int rank, int world, int nq_max, int k_max, b2r_xchg_handle *out);
+int b2r_xchg_ipc_handle(b2r_xchg_handle x, void *out64);
+int b2r_xchg_open(b2r_xchg_handle x, const void *handles /* world x 64 bytes, rank order */);
+/* rows / dist64 / count: this rank's b2r_query_ex results (device) */
+int b2r_xchg_push(b2r_xchg_handle x, const int64_t *rows, const double *dist64, const int32_t *count, int nq, int k, void *stream);
+/* merges the oldest pushed batch that has not been merged yet; outputs as b2r_merge_shards */
+int b2r_xchg_merge(b2r_xchg_handle x, int nq, int k, int64_t *out_rows, float *out_dist, int32_t *out_count, void *stream);
+int b2r_xchg_destroy(b2r_xchg_handle x);
 
 /* Diagnostics used by bench.py: run only the scoring/selection kernel selected by
  * `path` on device-resident prepared inputs, so it can be timed alone.

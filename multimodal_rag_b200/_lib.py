@@ -22,6 +22,7 @@ ABI_SYMBOLS = (
     "b2r_get_stats", "b2r_set_row_base", "b2r_merge_shards", "b2r_merge_shards_packed", "b2r_set_path", "b2r_launch_count",
     "b2r_set_kernel_timing", "b2r_kernel_time_ms", "b2r_save", "b2r_load", "b2r_column_set", "b2r_filter_eval", "b2r_query_async", "b2r_wait",
     "b2r_debug_trace",
+    "b2r_xchg_create", "b2r_xchg_ipc_handle", "b2r_xchg_open", "b2r_xchg_push", "b2r_xchg_merge", "b2r_xchg_destroy",
 )
 
 
@@ -93,6 +94,12 @@ def load() -> ctypes.CDLL:
         "b2r_query_async": (i32, [vp, vp, i32, i32, ctypes.POINTER(B2RFilter), vp, vp, vp, vp, ctypes.POINTER(ctypes.c_uint64)]),
         "b2r_wait": (i32, [vp, ctypes.c_uint64]),
         "b2r_debug_trace": (i32, [vp, vp, i32, ctypes.POINTER(ctypes.c_int)]),
+        "b2r_xchg_create": (i32, [i32, i32, i32, i32, i32, ctypes.POINTER(vp)]),
+        "b2r_xchg_ipc_handle": (i32, [vp, vp]),
+        "b2r_xchg_open": (i32, [vp, vp]),
+        "b2r_xchg_push": (i32, [vp, vp, vp, vp, i32, i32, vp]),
+        "b2r_xchg_merge": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+        "b2r_xchg_destroy": (i32, [vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -220,9 +220,16 @@ class DeviceShard:
         self.dim = dim
         self._side = None           # stream of the pipelined exchange
         self._inflight = None
+        self._xchg = None           # peer-to-peer exchange (enable_p2p_exchange)
         _lib.check(self.lib.b2r_set_row_base(h, row_base))
 
     def close(self):
+        if self._xchg is not None:
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)          # no peer may still be writing into this rank's mailbox
+            self.lib.b2r_xchg_destroy(self._xchg)
+            self._xchg = None
         if self.h is not None:
             self.lib.b2r_destroy(self.h)
             self.h = None
@@ -292,13 +299,51 @@ class DeviceShard:
         self._exchange(q.shape[0], k, o)
         return o["m_rows"], o["m_dist"], o["m_cnt"]
 
+    def enable_p2p_exchange(self, nq_max=1024, k_max=128):
+        """Replace the NCCL all_gather + merge launch by the library's own exchange kernel (b2r_xchg_*): every rank's
+        lists go straight into the peers' mailboxes over NVLink and the same kernel merges.  Collective (every rank
+        calls it); needs all ranks on one node with peer access.  torch.distributed is only used here, for the one-off
+        hand-over of the IPC handles."""
+        if self.world == 1 or self._xchg is not None:
+            return
+        rank = dist.get_rank(self.group)
+        x = ctypes.c_void_p()
+        _lib.check(self.lib.b2r_xchg_create(self.device, rank, self.world, nq_max, k_max, ctypes.byref(x)), "b2r_xchg_create")
+        buf = ctypes.create_string_buffer(64)
+        _lib.check(self.lib.b2r_xchg_ipc_handle(x, buf), "b2r_xchg_ipc_handle")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(buf.raw), group=self.group)
+        _lib.check(self.lib.b2r_xchg_open(x, b"".join(handles)), "b2r_xchg_open")
+        dist.barrier(group=self.group)
+        self._xchg = x
+        self._xchg_limits = (nq_max, k_max)
+        self.exchange_mode = ("b2r_xchg_push / b2r_xchg_merge: peer-to-peer stores into the peers' mailboxes over NVLink, stream "
+                              "memory operations as the only waits, merge kernel; no NCCL on the data path")
+
+    def _uses_xchg(self, nq, k):
+        return self._xchg is not None and nq <= self._xchg_limits[0] and k <= self._xchg_limits[1]
+
+    def _xchg_push(self, nq, k, o):
+        _lib.check(self.lib.b2r_xchg_push(self._xchg, o["rows"].data_ptr(), o["d64"].data_ptr(), o["cnt"].data_ptr(), nq, k,
+                                          torch.cuda.current_stream().cuda_stream), "b2r_xchg_push")
+
+    def _xchg_merge(self, nq, k, o):
+        _lib.check(self.lib.b2r_xchg_merge(self._xchg, nq, k, o["m_rows"].data_ptr(), o["m_dist"].data_ptr(), o["m_cnt"].data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream), "b2r_xchg_merge")
+
     def _exchange(self, nq, k, o):
+        if self._uses_xchg(nq, k):
+            self._xchg_push(nq, k, o)
+            self._xchg_merge(nq, k, o)
+            return
         dist.all_gather_into_tensor(o["a_pack"], o["pack"], group=self.group)      # the only data-path collective
         st = torch.cuda.current_stream().cuda_stream
         stride, off_rows, off_d64, off_cnt = o["layout"]
         _lib.check(self.lib.b2r_merge_shards_packed(o["a_pack"].data_ptr(), stride, off_rows, off_d64, off_cnt,
                                                     self.world, nq, k, o["m_rows"].data_ptr(), o["m_dist"].data_ptr(),
                                                     o["m_cnt"].data_ptr(), self.device, st), "b2r_merge_shards_packed")
+
+    PIPELINE_MAX_BYTES = 64 << 10      # per-rank message up to which the exchange is moved to the side stream
 
     def query_device_pipelined(self, q: torch.Tensor, k: int, o: dict):
         """The same with the exchange taken off the scoring stream: the local top-k of this batch is enqueued on the
@@ -309,6 +354,16 @@ class DeviceShard:
         cur = torch.cuda.current_stream()
         if "ev_done" in o:
             cur.wait_event(o["ev_done"])          # the previous user of these buffers has been merged
+        if self.world > 1 and not self._uses_xchg(q.shape[0], k) and o["layout"][0] > self.PIPELINE_MAX_BYTES:
+            # large lists (config 4: 1.6 MB per rank): NCCL's all_gather then wants many SMs at once and fights the next
+            # batch's scan for them -- measured 10 ms per step instead of 0.9 -- so the exchange stays on the scan's stream,
+            # where it costs 40 us of a multi-millisecond step
+            self.query_device(q, k, o)
+            if "ev_local" not in o:
+                o["ev_local"], o["ev_done"] = torch.cuda.Event(), torch.cuda.Event()
+            o["ev_done"].record(cur)
+            self._inflight = o
+            return
         self.query_local(q, k, o)
         if self.world == 1:
             return
@@ -316,11 +371,18 @@ class DeviceShard:
             self._side = torch.cuda.Stream(device=self.device)
         if "ev_local" not in o:
             o["ev_local"], o["ev_done"] = torch.cuda.Event(), torch.cuda.Event()
-        o["ev_local"].record(cur)
-        self._side.wait_event(o["ev_local"])
-        with torch.cuda.stream(self._side):
-            self._exchange(q.shape[0], k, o)
-            o["ev_done"].record(self._side)
+        nq = q.shape[0]
+        if self._uses_xchg(nq, k):
+            self._xchg_push(nq, k, o)              # on the scan's stream: a few microseconds, nothing waits inside it
+            with torch.cuda.stream(self._side):    # the merge's stream waits on the mailbox words (this rank's push included)
+                self._xchg_merge(nq, k, o)
+                o["ev_done"].record(self._side)
+        else:
+            o["ev_local"].record(cur)
+            self._side.wait_event(o["ev_local"])
+            with torch.cuda.stream(self._side):
+                self._exchange(nq, k, o)
+                o["ev_done"].record(self._side)
         self._inflight = o
 
     def drain(self):

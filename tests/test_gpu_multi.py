@@ -52,6 +52,27 @@ def _worker(rank, world, port, n, d, nq, k, out):
         r2, d2, c2 = sh.query_device(Q2, 100, o2)
         torch.cuda.synchronize()
         res["rows100"], res["dist100"], res["cnt100"] = r2.cpu().numpy(), d2.cpu().numpy(), c2.cpu().numpy()
+        # the library's own exchange (peer-to-peer stores into the peers' mailboxes + flags + merge in ONE kernel, no NCCL on
+        # the data path) must give what the all_gather + merge gave -- several calls in a row (both slots, the slot
+        # hand-back), a different batch size in between, and the pipelined form
+        sh.enable_p2p_exchange(nq_max=256, k_max=128)
+        ok = True
+        for rep in range(5):
+            o3 = sh.alloc_out(nq, k)
+            r3, d3, c3 = sh.query_device(Qd, k, o3)
+            torch.cuda.synchronize()
+            ok = ok and bool(torch.equal(r3, rows)) and bool(torch.equal(d3, dist_)) and bool(torch.equal(c3, cnt))
+            if rep == 2:
+                o4 = sh.alloc_out(130, 100)
+                r4, d4, c4 = sh.query_device(Q2, 100, o4)
+                torch.cuda.synchronize()
+                ok = ok and bool(torch.equal(r4, r2)) and bool(torch.equal(d4, d2))
+        for i in range(6):
+            sh.query_device_pipelined(Qd, k, os_[i % 2])
+        sh.drain()
+        torch.cuda.synchronize()
+        ok = ok and all(bool(torch.equal(o_["m_rows"], rows)) and bool(torch.equal(o_["m_dist"], dist_)) for o_ in os_)
+        res["p2p_same"] = ok
         sh.close()
         # (2) the Chroma-shaped collective collection with ids and a where clause
         sc = ShardedCollection("mm", {"hnsw:space": "cosine"}, device=rank)
@@ -82,7 +103,7 @@ def test_two_gpu_row_sharded_matches_oracle(tmp_path):
     for i in range(nq):
         np.testing.assert_array_equal(res["rows"][i, : res["cnt"][i]], er[i])
         np.testing.assert_allclose(res["dist"][i, : res["cnt"][i]], ed[i], rtol=1e-5, atol=1e-7)
-    assert res["pipelined_same"]
+    assert res["pipelined_same"] and res["p2p_same"]
     er3, ed3 = eo.topk_exact(eo.normalize_f32(make_unit(130, d, 8)), eo.normalize_f32(X), 100, "cosine")
     for i in range(130):
         np.testing.assert_array_equal(res["rows100"][i, : res["cnt100"][i]], er3[i])
