@@ -576,23 +576,34 @@ def run_gpu(args):
         if args.p2p_exchange:
             sh2.enable_p2p_exchange(nq_max=max(nq, 1024), k_max=128)
 
-        def step_sharded(i):
+        def step_sharded_pipelined(i):
             # the exchange of batch i (all_gather + merge, side stream) overlaps the scan of batch i+1; the last step of a
             # region waits for every exchange in flight, so a region ends with all of its merged answers in place
             sh2.query_device_pipelined(Q2[i % n_batches], k, o2b[i % 2])
             if i == K - 1:
                 sh2.drain()
 
+        def step_sharded_serial(i):
+            # scan -> exchange -> merge on one stream: the latency of one batch
+            sh2.query_device(Q2[i % n_batches], k, o2)
+
+        # Both forms are timed briefly and the faster one is measured in full.  Which one wins depends on N: on a side stream
+        # NCCL's kernel competes with the next scan for SMs -- a gain at 2 GPUs (+9 us instead of +21 us per step), a loss at 8
+        # (profiles/r2_exchange.md).
         for i in range(W):
-            step_sharded(i)
+            step_sharded_pipelined(i)
         sh2.drain()
+        for i in range(W):
+            step_sharded_serial(i)
+        trial = {"pipelined": summarize(timed(step_sharded_pipelined, K, min_s=0.1), K)["ms_per_step"],
+                 "serial": summarize(timed(step_sharded_serial, K, min_s=0.1), K)["ms_per_step"]}
+        pick = torch.tensor([1 if trial["pipelined"] < trial["serial"] else 0], device=dev)
+        dist.broadcast(pick, 0)
+        use_pipelined = bool(int(pick.item()))
+        step_sharded = step_sharded_pipelined if use_pipelined else step_sharded_serial
         launches0 = lib.b2r_launch_count(sh2.h)
         shd = summarize(timed(step_sharded, K), K)
-        # the un-pipelined form (scan -> all_gather -> merge on one stream) beside it: the latency of one batch
-        def step_sharded_serial(i):
-            sh2.query_device(Q2[i % n_batches], k, o2)
-        shd_serial = summarize(timed(step_sharded_serial, K, min_s=0.2), K)
-        gpu_launches = int(round((lib.b2r_launch_count(sh2.h) - launches0) / shd["repeats"])) + K      # + one merge launch per step
+        shd_serial = {"ms_per_step": trial["serial"]}
         per_rank_ms = [None] * world
         dist.all_gather_object(per_rank_ms, shd["ms_per_step"])
         kern_ms_per_step, launches_per_step = kernel_time(sh2.h, step_sharded, max(K, 50))
@@ -635,9 +646,10 @@ def run_gpu(args):
                               "nranks": world, "collectives_per_step": 1,
                               "collective": "exchange of the per-rank [batch, top_k] x (int64 row, fp64 distance) + [batch] int32 count lists",
                               "bytes_sent_per_rank_per_step": bytes_per_rank, "bytes_gathered_per_rank_per_step": world * bytes_per_rank,
-                              "exchange": sh2.exchange_mode + "; issued on a side stream behind an event so that it overlaps the scan of the next batch (DeviceShard.query_device_pipelined)",
-                              "serial_ms_per_step": shd_serial["ms_per_step"],
-                              "serial_note": "scan -> exchange -> merge on one stream: the latency of one batch",
+                              "exchange": sh2.exchange_mode + ("; issued on a side stream behind an event so that it overlaps the scan of the next batch "
+                                                               "(DeviceShard.query_device_pipelined)" if use_pipelined else "; on the scan's stream (DeviceShard.query_device)"),
+                              "form_timed": "pipelined" if use_pipelined else "serial", "trial_ms_per_step": trial,
+                              "trial_note": "both forms are timed for 0.1 s and the faster one is measured in full",
                               "nccl_all_gather_ms_per_step": shd_nccl["ms_per_step"],
                               "nccl_note": "the same step with torch.distributed all_gather_into_tensor + b2r_merge_shards_packed on one stream"},
                      "e2e": {"value": world * nq / (shd_e2e["ms_per_step"] * 1e-3), "unit": UNIT, **shd_e2e,

@@ -166,7 +166,7 @@ extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device,
     if (const char *e = getenv("B2R_SEED_WAIT_NS")) h->seed_wait_ns = strtoull(e, nullptr, 10);
     if (const char *e = getenv("B2R_DELAY_US")) h->delay_us = atoi(e);
     if (const char *e = getenv("B2R_POOL_SAMPLE_DIV")) h->pool_sample_div = std::max(1, atoi(e));
-    if (const char *e = getenv("B2R_TRACE")) h->trace_on = atoi(e) != 0;
+    if (const char *e = getenv("B2R_TRACE")) { h->trace_on = atoi(e) != 0; h->trace_mode = atoi(e); }
     if (const char *e = getenv("B2R_NO_PAIR")) h->no_pair = atoi(e) != 0;
     int rc = B2R_OK;
     do {
@@ -865,7 +865,7 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         gp.samples = (unsigned *)h->gemm_samples.p; gp.seeded = gp.cnt + (size_t)qblocks_total * GEMM_BM; gp.arrive = gp.seeded + (size_t)qblocks_total * GEMM_BM;
         gp.seed_tiles = 0;
         gp.seed_wait_ns = h->seed_wait_ns; gp.delay_us = h->delay_us;
-        gp.trace = h->trace_on ? (unsigned long long *)h->trace.p : nullptr;
+        gp.trace = h->trace_on ? (unsigned long long *)h->trace.p : nullptr; gp.trace_mode = h->trace_mode;
         UnionParams un;
         un.lists = gp.lists; un.list_stride = list_stride; un.gthr = gp.gthr; un.cnt = gp.cnt;
         un.pool_stats = h->counters + 2;

@@ -125,7 +125,7 @@ struct b2r_index {
     int delay_us = 0, pool_sample_div = 32;
     bool no_pair = false;           // B2R_NO_PAIR=1: never use the cta_group::2 form of K3
     b2r::DevBuf trace;
-    bool trace_on = false; int trace_ctas = 0;
+    bool trace_on = false; int trace_ctas = 0, trace_mode = 1;
     int timing_stage = 0;           // which launch the events bracket: 0 scoring (default); B2R_TIME_STAGE=1, 4, 5 (development):
                                     // 1 prepare, 4 finalize, 5 exact fix-up
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;

@@ -87,6 +87,7 @@ struct GemmParams {
     // development knobs (0 in production; b2r_create reads them from the environment)
     unsigned long long seed_wait_ns;   // overrides the wait budget of the seeding phase (1 = do not wait at all)
     int delay_us;                // every third slice sleeps this long before it posts its samples (a slow CTA)
+    int trace_mode;              // 1: slots 4..7 = wait totals (below); 2: slots 4, 5 = globaltimer at the first full accumulator / when the sampling tiles are done
     unsigned long long *trace;   // [grid][8]: globaltimer at epilogue start, posted, seeded, done; then SM cycles the MMA thread waited for an
                                  // empty accumulator / for operands, the first epilogue warp for a full accumulator, the producer for a free slot (nullptr = off)
 };
@@ -805,8 +806,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     if (PAIR) cluster_sync_all(); else __syncthreads();     // the peer's barriers and TMEM exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    pdl_wait();          // everything above overlapped the previous kernel; queries / bounds / bitmap are read below
-    pdl_trigger();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -814,6 +813,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             auto load = [&](void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
                 if (PAIR) tma_load_2d_pair(dst, tm, bar, c0, c1); else tma_load_2d(dst, tm, bar, c0, c1);
             };
+            // The corpus does not depend on the kernel this one was launched behind (the query preparation, or the pass-bitmap
+            // kernel after it: every kernel of the library waits for ITS predecessor before it lets its successor start, so all
+            // ingests are complete by now).  With resident queries the first ring slots are therefore filled BEFORE the
+            // programmatic-launch wait: the first tile is in shared memory when the prepared queries arrive.
+            int early = 0;
+            if (A_RES) {
+                early = min(STAGES, n_iter * KB);
+                for (int j = 0; j < early; ++j) {
+                    const int i = j / KB, kb = j % KB;
+                    const int t = i < S ? t0 + i : t0 + i - S;
+                    if (leader) mbar_expect_tx(&bar_full[j], NCTA * STAGE_BYTES);
+                    load(smB + (size_t)j * STAGE_BYTES, &tm_x, &bar_full[j], kb * 64, t * BN + (int)crank * B_ROWS);
+                }
+            }
+            pdl_wait();          // the prepared queries are read below
+            pdl_trigger();
             if (A_RES) {
                 if (leader) mbar_expect_tx(&bar_a, NCTA * KB * A_KB_BYTES);
                 for (int kb = 0; kb < KB; ++kb) load(smA + (size_t)kb * A_KB_BYTES, &tm_q, &bar_a, kb * 64, qb * GEMM_BM);
@@ -823,6 +838,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             for (int i = 0; i < n_iter; ++i) {
                 const int t = i < S ? t0 + i : t0 + i - S;      // the seeding tiles are scanned again by the main loop
                 for (int kb = 0; kb < KB; ++kb) {
+                    if (i * KB + kb < early) {                  // issued above
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (p.trace) { const long long c0 = clock64(); mbar_wait(&bar_empty[stage], phase ^ 1); w_empty += clock64() - c0; }
                     else mbar_wait(&bar_empty[stage], phase ^ 1);
                     if (leader) mbar_expect_tx(&bar_full[stage], NCTA * STAGE_BYTES);     // both CTAs' bytes land on the leader's barrier
@@ -835,6 +854,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
     } else if (warp == 1) {
         // ===== MMA issuer (the leader's elected thread issues for the pair) =====
+        pdl_wait();
+        pdl_trigger();
         if (lane == 0 && leader) {
             auto commit = [&](uint64_t *bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             if (A_RES) { mbar_wait(&bar_a, 0); tc_fence_after(); }
@@ -868,10 +889,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
-            if (p.trace) { p.trace[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)w_tempty; p.trace[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)w_full; }
+            if (p.trace && p.trace_mode != 2) { p.trace[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)w_tempty; p.trace[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)w_full; }
         }
     } else {
         // ===== epilogue: thread = query, column = corpus row =====
+        pdl_wait();          // bounds / cursors / seed flags (cleared by the preparation) and the pass bitmap are read below
+        pdl_trigger();
         constexpr int NC = BN / 32 / GEMM_HALVES;                    // 32-column steps per tile per warp
         static_assert(NC % 2 == 0, "steps are processed in double-buffered pairs");
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
@@ -912,9 +935,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 if (qs >= p.nq) break;
                 const unsigned v = warp_lth_largest<LS>(p.samples + (size_t)(qs - p.qblock0 * GEMM_BM) * per_q, per_q, lane);
                 if (lane == 0) {
-                    if (v != 0u) atomicMax(p.gthr + qs, v);       // the finalize reads the bound from gthr[q]
-                    __threadfence();
-                    atomicExch(p.seeded + qs, v != 0u ? v : 1u);  // flag and seed in one word (1 = no seed: too few rows pass)
+                    atomicExch(p.seeded + qs, v != 0u ? v : 1u);  // flag and seed in one word (1 = no seed: too few rows pass): the waiting threads take it from here
+                    if (v != 0u) atomicMax(p.gthr + qs, v);       // the finalize (and every later tile) reads the bound from gthr[q]
                 }
             }
             fold_pending = false;
@@ -928,8 +950,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             const int buf = it & 1;
             if (!SMP && fold_pending && fold_ready()) fold_share();     // a fold that had to be put off (a slice was late)
             if (!SMP && g_next > g_seen) { g_seen = g_next; thr = fmaxf(thr, KeyS::unord(g_next)); }
-            if (tracer) { const long long c0 = clock64(); mbar_wait(&bar_tfull[buf], (it >> 1) & 1); w_tfull += clock64() - c0; }
-            else mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
+            if (tracer) {
+                const long long c0 = clock64(); mbar_wait(&bar_tfull[buf], (it >> 1) & 1); w_tfull += clock64() - c0;
+                if (it == 0 && p.trace_mode == 2) p.trace[(size_t)blockIdx.x * 8 + 4] = globaltimer_ns();
+            } else mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             // the other slices' progress on this query: loaded now, consumed at the top of the next tile
             if (!SMP) g_next = *reinterpret_cast<volatile unsigned *>(gq);
@@ -972,6 +996,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 asm volatile("" ::"r"(warm));
             }
             for (int i = 0; i < S; ++i, ++it) run_tile(t0 + i, it, std::true_type(), slist);
+            if (tracer && p.trace_mode == 2) p.trace[(size_t)blockIdx.x * 8 + 5] = globaltimer_ns();
             if (p.delay_us > 0 && slice % 3 == 1) {            // development: a slow CTA
                 const unsigned long long t_d = globaltimer_ns();
                 while (globaltimer_ns() - t_d < (unsigned long long)p.delay_us * 1000ull) __nanosleep(256);
@@ -988,10 +1013,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     o.y = slist.r[i + 1] != 0xffffffffu ? KeyS::ord(slist.s[i + 1]) : 0u;
                     *reinterpret_cast<uint2 *>(dst + i) = o;
                 }
-                __threadfence();
             }
-            epi_bar_sync();                                   // every epilogue thread's post is fenced
-            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(p.arrive + qb, 1u); }
+            epi_bar_sync();                                   // every epilogue thread's post happens before ...
+            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(p.arrive + qb, 1u); }   // ... this (cumulative) fence + arrival
             const unsigned long long t_post = __shfl_sync(FULL_MASK, globaltimer_ns(), 0);
             if (tracer) p.trace[(size_t)blockIdx.x * 8 + 1] = t_post;
             unsigned long long budget = GEMM_SEED_TIMEOUT_NS;

@@ -34,6 +34,11 @@ def trace_summary(lib, sh):
     waits = {"mma_wait_empty_acc_kcyc": [float(np.median(wait[:, 0][wait[:, 0] > 0]) / 1e3) if (wait[:, 0] > 0).any() else 0.0],
              "mma_wait_operands_kcyc": [float(np.median(wait[:, 1][wait[:, 1] > 0]) / 1e3) if (wait[:, 1] > 0).any() else 0.0],
              "epi_wait_full_acc_kcyc": float(np.median(wait[:, 2]) / 1e3), "producer_wait_slot_kcyc": float(np.median(wait[:, 3]) / 1e3)}
+    if os.environ.get("B2R_TRACE") == "2":
+        ft = (t[:, 4] - t0) / 1e3; sd = (t[:, 5] - t0) / 1e3
+        ft = ft[t[:, 4] > 0]; sd = sd[t[:, 5] > 0]
+        waits = {"first_full_acc_us": [float(ft.min()), float(np.median(ft)), float(ft.max())],
+                 "sampling_done_us": [float(sd.min()), float(np.median(sd)), float(sd.max())]}
     return {"waits": waits, "ctas": n.value, "start_spread_us": float(rel[:, 0].max()), "posted_us": [float(rel[:, 1].min()), float(rel[:, 1].max())],
             "seeded_us": [float(rel[:, 2].min()), float(rel[:, 2].max())], "done_us": [float(rel[:, 3].min()), float(np.median(rel[:, 3])), float(rel[:, 3].max())]}
 
