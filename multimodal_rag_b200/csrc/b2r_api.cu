@@ -168,6 +168,7 @@ extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device,
     if (const char *e = getenv("B2R_POOL_SAMPLE_DIV")) h->pool_sample_div = std::max(1, atoi(e));
     if (const char *e = getenv("B2R_TRACE")) { h->trace_on = atoi(e) != 0; h->trace_mode = atoi(e); }
     if (const char *e = getenv("B2R_NO_PAIR")) h->no_pair = atoi(e) != 0;
+    if (const char *e = getenv("B2R_NO_DYN")) h->no_dyn = atoi(e) != 0;
     int rc = B2R_OK;
     do {
         if (cudaMalloc(&h->max_norm2, 256) != cudaSuccess || cudaMalloc(&h->counters, 256) != cudaSuccess ||
@@ -863,6 +864,7 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         gp.gthr = (unsigned *)h->gthr.p; gp.cnt = gp.gthr + (size_t)qblocks_total * GEMM_BM; gp.lists = (KeyS *)h->gemm_lists.p;
         gp.regions = (KeyS *)h->gemm_regions.p; gp.region_cap = GEMM_REGION_CAP;
         gp.samples = (unsigned *)h->gemm_samples.p; gp.seeded = gp.cnt + (size_t)qblocks_total * GEMM_BM; gp.arrive = gp.seeded + (size_t)qblocks_total * GEMM_BM;
+        gp.tile_counter = nullptr;
         gp.seed_tiles = 0;
         gp.seed_wait_ns = h->seed_wait_ns; gp.delay_us = h->delay_us;
         gp.trace = h->trace_on ? (unsigned long long *)h->trace.p : nullptr; gp.trace_mode = h->trace_mode;
@@ -898,6 +900,9 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
             }
             if (gp.seed_tiles && h->seed_tiles_override > 0) gp.seed_tiles = std::min(h->seed_tiles_override, std::max(1, tiles_per_cta / 2));
         }
+        // one query block, list mode, plenty of tiles: the CTAs take tiles dynamically instead of owning a static slice
+        if (!pair && !pool_mode && !h->no_dyn && gp.n_qblocks == 1 && tiles_total >= 8 * gp.n_slices)
+            gp.tile_counter = gp.arrive + (size_t)qblocks_total;
         un.max_entries = pool_mode ? GEMM_POOL_CAP : gp.n_slices * GEMM_HALVES * L;
         if (h->trace_on) B2R_CUDA(cudaMemsetAsync(h->trace.p, 0, sizeof(unsigned long long) * 8 * (size_t)h->sm_count, s));
         KernelTimer kt(h, s);
@@ -1010,9 +1015,9 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
         p.zero[0] = (unsigned *)h->need_ctl; p.zero_words[0] = 2;
         p.zero[1] = nullptr; p.zero_words[1] = 0;
         p.zero[2] = nullptr; p.zero_words[2] = 0;
-        if (path == 2) {   // ... and K3's [bounds | cursors | seed flags][q-blocks * 128], [arrivals][q-blocks]
+        if (path == 2) {   // ... and K3's [bounds | cursors | seed flags][q-blocks * 128], [arrivals][q-blocks], [tile counters][q-blocks]
             const int qblocks = (nq + GEMM_BM - 1) / GEMM_BM;
-            p.zero_words[2] = qblocks * (GEMM_BM * 3 + 1);
+            p.zero_words[2] = qblocks * (GEMM_BM * 3 + 2);
             if ((rc = ensure(h->gthr, (size_t)p.zero_words[2] * 4)) != B2R_OK) return rc;
             p.zero[2] = (unsigned *)h->gthr.p;
         }

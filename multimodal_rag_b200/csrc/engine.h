@@ -123,7 +123,8 @@ struct b2r_index {
     // shard (default 32), B2R_TRACE=1 records per-CTA phase timestamps of the last K3 launch (b2r_debug_trace)
     unsigned long long seed_wait_ns = 0;
     int delay_us = 0, pool_sample_div = 32;
-    bool no_pair = false;           // B2R_NO_PAIR=1: never use the cta_group::2 form of K3
+    bool no_pair = false;
+    bool no_dyn = false;            // B2R_NO_DYN=1: static slices only (no dynamic tile hand-out)           // B2R_NO_PAIR=1: never use the cta_group::2 form of K3
     b2r::DevBuf trace;
     bool trace_on = false; int trace_ctas = 0, trace_mode = 1;
     int timing_stage = 0;           // which launch the events bracket: 0 scoring (default); B2R_TIME_STAGE=1, 4, 5 (development):

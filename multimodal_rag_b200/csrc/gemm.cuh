@@ -84,6 +84,9 @@ struct GemmParams {
     unsigned *samples;           // [launch queries (padded to 128)][n_slices*2][2 .. L] ordered score keys, 0 = empty
     unsigned *seeded;            // [all queries] 0 = not seeded yet, 1 = seeded without a bound, else the seed (= gthr[q] then)
     unsigned *arrive;            // [all q-blocks] CTAs that have posted (0 between calls: the query preparation clears it)
+    unsigned *tile_counter;      // nullptr: every CTA scans its static slice.  Else (one query block per launch, no pairs): the next
+                                 // tile of the shard nobody has taken yet (0 at launch: cleared by the preparation); CTAs take tiles
+                                 // one at a time, so a slow SM simply takes fewer and all finish within one tile of each other
     // development knobs (0 in production; b2r_create reads them from the environment)
     unsigned long long seed_wait_ns;   // overrides the wait budget of the seeding phase (1 = do not wait at all)
     int delay_us;                // every third slice sleeps this long before it posts its samples (a slow CTA)
@@ -777,6 +780,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_a, bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ int tile_ring[8];          // dynamic tiles: the tile iteration `it` works on, at [it & 7] (bit 30 = sampling pass, -1 = no tile left)
+    constexpr int TILE_SMP = 1 << 30;
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
@@ -792,6 +797,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // in-kernel threshold seeding: sampling tiles in front of the slice (every seed_stride-th slice samples, all post)
     const int S = (p.seed_tiles > 0 && slice % p.seed_stride == 0) ? min(p.seed_tiles, t1 - t0) : 0;
     const int n_iter = S + (t1 - t0);
+    const bool dyn = !PAIR && p.tile_counter != nullptr;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_q);
@@ -818,7 +824,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             // ingests are complete by now).  With resident queries the first ring slots are therefore filled BEFORE the
             // programmatic-launch wait: the first tile is in shared memory when the prepared queries arrive.
             int early = 0;
-            if (A_RES) {
+            if (A_RES && !dyn) {
                 early = min(STAGES, n_iter * KB);
                 for (int j = 0; j < early; ++j) {
                     const int i = j / KB, kb = j % KB;
@@ -835,6 +841,37 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
             int stage = 0; uint32_t phase = 0;
             long long w_empty = 0;
+            if (dyn) {
+                // ---- dynamic tiles: take the next free tile of the shard, tell the other roles which one it is ----
+                unsigned *ctr = p.tile_counter + p.qblock0;
+                int it = 0, ns = 0, samp[8];
+                auto issue = [&](int t, int tag) {
+                    *reinterpret_cast<volatile int *>(&tile_ring[it & 7]) = t | tag;     // before the first arrive of the tile (release)
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait(&bar_empty[stage], phase ^ 1);
+                        mbar_expect_tx(&bar_full[stage], STAGE_BYTES);
+                        if (!A_RES) load(smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES, &tm_q, &bar_full[stage], kb * 64, qb * GEMM_BM);
+                        load(smB + (size_t)stage * STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * BN);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    ++it;
+                };
+                for (; ns < min(p.seed_tiles, 8); ++ns) {          // the sampling pass: this CTA's first few tiles ...
+                    const int t = (int)atomicAdd(ctr, 1u);
+                    if (t >= p.tiles_total) break;
+                    samp[ns] = t;
+                    issue(t, TILE_SMP);
+                }
+                for (int i = 0; i < ns; ++i) issue(samp[i], 0);     // ... which the main pass scans again with the bound in place
+                for (;;) {
+                    const int t = (int)atomicAdd(ctr, 1u);
+                    if (t >= p.tiles_total) break;
+                    issue(t, 0);
+                }
+                *reinterpret_cast<volatile int *>(&tile_ring[it & 7]) = -1;              // nothing left: wake the MMA thread with an empty slot
+                mbar_wait(&bar_empty[stage], phase ^ 1);
+                mbar_arrive(&bar_full[stage]);
+            } else
             for (int i = 0; i < n_iter; ++i) {
                 const int t = i < S ? t0 + i : t0 + i - S;      // the seeding tiles are scanned again by the main loop
                 for (int kb = 0; kb < KB; ++kb) {
@@ -861,8 +898,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (A_RES) { mbar_wait(&bar_a, 0); tc_fence_after(); }
             int stage = 0; uint32_t phase = 0;
             long long w_tempty = 0, w_full = 0;
-            for (int it = 0; it < n_iter; ++it) {
+            for (int it = 0; dyn || it < n_iter; ++it) {
                 const int buf = it & 1;
+                bool last = false;
                 long long c0 = p.trace ? clock64() : 0;
                 // (PAIR: the peer's epilogue warps arrive remotely.  Default-scope arrive / try_wait, as CUTLASS's 2-SM pipelines use:
                 // the cluster-scope release/acquire forms cost ~1500 cycles per tile here; what is handed over is TMEM, ordered by
@@ -875,6 +913,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     if (p.trace) c0 = clock64();
                     mbar_wait(&bar_full[stage], phase);
                     if (p.trace) w_full += clock64() - c0;
+                    if (dyn && kb == 0 && *reinterpret_cast<volatile int *>(&tile_ring[it & 7]) < 0) { last = true; break; }
                     tc_fence_after();
                     const uint64_t ad = umma_smem_desc(smem_u32(A_RES ? smA + (size_t)kb * A_KB_BYTES
                                                                           : smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES));
@@ -888,6 +927,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     if (kb == KB - 1) commit(&bar_tfull[buf]);  // accumulator complete (in both CTAs)
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (last) { commit(&bar_tfull[buf]); break; }   // no tile left: pass the end marker on to the epilogue
             }
             if (p.trace && p.trace_mode != 2) { p.trace[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)w_tempty; p.trace[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)w_full; }
         }
@@ -944,6 +984,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
         const bool tracer = p.trace != nullptr && warp == 2 && lane == 0;
         long long w_tfull = 0;
+        // dynamic tiles: which tile does iteration `it` hold (bit 30 = sampling pass, -1 = none left)?  Waits for its accumulator.
+        auto peek = [&](int it) -> int {
+            mbar_wait(&bar_tfull[it & 1], (it >> 1) & 1);
+            return *reinterpret_cast<volatile int *>(&tile_ring[it & 7]);
+        };
         // one tile: TMEM -> registers in 32-column steps, two register buffers so the next load flies under this step
         auto run_tile = [&](int t, int it, auto sample_c, auto &slist) {
             constexpr bool SMP = decltype(sample_c)::value;
@@ -995,7 +1040,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 for (int w = lane; w < S * (BN / 32); w += 32) warm |= __ldg(pb + w);
                 asm volatile("" ::"r"(warm));
             }
-            for (int i = 0; i < S; ++i, ++it) run_tile(t0 + i, it, std::true_type(), slist);
+            if (dyn) {
+                for (int tv; (tv = peek(it)) >= 0 && (tv & TILE_SMP); ++it) run_tile(tv & ~TILE_SMP, it, std::true_type(), slist);
+            } else {
+                for (int i = 0; i < S; ++i, ++it) run_tile(t0 + i, it, std::true_type(), slist);
+            }
             if (tracer && p.trace_mode == 2) p.trace[(size_t)blockIdx.x * 8 + 5] = globaltimer_ns();
             if (p.delay_us > 0 && slice % 3 == 1) {            // development: a slow CTA
                 const unsigned long long t_d = globaltimer_ns();
@@ -1043,7 +1092,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             __syncwarp();
         }
         if (tracer) p.trace[(size_t)blockIdx.x * 8 + 2] = globaltimer_ns();
-        for (int t = t0; t < t1; ++t, ++it) run_tile(t, it, std::false_type(), list);
+        if (dyn) {
+            for (int tv; (tv = peek(it)) >= 0; ++it) run_tile(tv, it, std::false_type(), list);
+        } else {
+            for (int t = t0; t < t1; ++t, ++it) run_tile(t, it, std::false_type(), list);
+        }
         if (fold_pending && fold_ready()) fold_share();          // last chance before this CTA leaves
         if (tracer) { p.trace[(size_t)blockIdx.x * 8 + 3] = globaltimer_ns(); p.trace[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)w_tfull; }
 
