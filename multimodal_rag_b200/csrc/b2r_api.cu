@@ -165,7 +165,7 @@ extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device,
     if (const char *e = getenv("B2R_SEED_TILES")) h->seed_tiles_override = atoi(e);   // development: seeding tiles per CTA
     if (const char *e = getenv("B2R_SEED_WAIT_NS")) h->seed_wait_ns = strtoull(e, nullptr, 10);
     if (const char *e = getenv("B2R_DELAY_US")) h->delay_us = atoi(e);
-    if (const char *e = getenv("B2R_POOL_SAMPLE_DIV")) h->pool_sample_div = std::max(1, atoi(e));
+    if (const char *e = getenv("B2R_POOL_SAMPLE_DIV")) h->pool_sample_div = std::max(0, atoi(e));
     if (const char *e = getenv("B2R_TRACE")) { h->trace_on = atoi(e) != 0; h->trace_mode = atoi(e); }
     if (const char *e = getenv("B2R_NO_PAIR")) h->no_pair = atoi(e) != 0;
     if (const char *e = getenv("B2R_NO_DYN")) h->no_dyn = atoi(e) != 0;
@@ -892,7 +892,10 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
                                // that the 32nd best sample leaves ~1024 candidates per query -- far more than k, or the
                                // certificate (k-th exact candidate vs the bound) could not hold.  Without a seed (tiny
                                // shards, B2R_NO_SEED) every thread bounds itself from its own region.
-                const int sample_tiles = (tiles_total >= 8 && !h->no_seed) ? std::max(4, tiles_total / h->pool_sample_div) : 0;
+                // (1/32 of the shard; 1/64 from 8M rows on: the sampling tiles are scored twice, and on a long scan the half-size
+                // sample is worth more than the pools it doubles to ~2000 entries cost the finalize: -1.2 % at 12.5M and 50M rows)
+                const int div = h->pool_sample_div > 0 ? h->pool_sample_div : (h->rows >= (8ll << 20) ? 64 : 32);
+                const int sample_tiles = (tiles_total >= 8 && !h->no_seed) ? std::max(4, tiles_total / div) : 0;
                 gp.seed_tiles = sample_tiles ? std::max(1, sample_tiles / gp.n_slices) : 0;
                 if (sample_tiles && sample_tiles < gp.n_slices) gp.seed_stride = gp.n_slices / sample_tiles;
             } else {

@@ -122,7 +122,7 @@ struct b2r_index {
     // (1 = never wait), B2R_DELAY_US makes every third slice post late, B2R_POOL_SAMPLE_DIV = pool mode samples 1/div of the
     // shard (default 32), B2R_TRACE=1 records per-CTA phase timestamps of the last K3 launch (b2r_debug_trace)
     unsigned long long seed_wait_ns = 0;
-    int delay_us = 0, pool_sample_div = 32;
+    int delay_us = 0, pool_sample_div = 0;     // 0 = by shard size (1/32, 1/64 from 8M rows on)
     bool no_pair = false;
     bool no_dyn = false;            // B2R_NO_DYN=1: static slices only (no dynamic tile hand-out)           // B2R_NO_PAIR=1: never use the cta_group::2 form of K3
     b2r::DevBuf trace;
