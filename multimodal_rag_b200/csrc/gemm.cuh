@@ -887,7 +887,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
-            if (p.trace) p.trace[(size_t)blockIdx.x * 8 + 7] = (unsigned long long)w_empty;
+            if (p.trace && p.trace_mode < 3) p.trace[(size_t)blockIdx.x * 8 + 7] = (unsigned long long)w_empty;
         }
     } else if (warp == 1) {
         // ===== MMA issuer (the leader's elected thread issues for the pair) =====
@@ -895,7 +895,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         pdl_trigger();
         if (lane == 0 && leader) {
             auto commit = [&](uint64_t *bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
+            if (p.trace && p.trace_mode == 3) p.trace[(size_t)blockIdx.x * 8 + 4] = globaltimer_ns();      // MMA thread past the launch wait
             if (A_RES) { mbar_wait(&bar_a, 0); tc_fence_after(); }
+            if (p.trace && p.trace_mode == 3) p.trace[(size_t)blockIdx.x * 8 + 5] = globaltimer_ns();      // queries resident
             int stage = 0; uint32_t phase = 0;
             long long w_tempty = 0, w_full = 0;
             for (int it = 0; dyn || it < n_iter; ++it) {
@@ -913,6 +915,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     if (p.trace) c0 = clock64();
                     mbar_wait(&bar_full[stage], phase);
                     if (p.trace) w_full += clock64() - c0;
+                    if (p.trace && p.trace_mode == 3 && it == 0 && kb == 0) p.trace[(size_t)blockIdx.x * 8 + 6] = globaltimer_ns();   // first corpus K-block resident
                     if (dyn && kb == 0 && *reinterpret_cast<volatile int *>(&tile_ring[it & 7]) < 0) { last = true; break; }
                     tc_fence_after();
                     const uint64_t ad = umma_smem_desc(smem_u32(A_RES ? smA + (size_t)kb * A_KB_BYTES
@@ -929,7 +932,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 }
                 if (last) { commit(&bar_tfull[buf]); break; }   // no tile left: pass the end marker on to the epilogue
             }
-            if (p.trace && p.trace_mode != 2) { p.trace[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)w_tempty; p.trace[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)w_full; }
+            if (p.trace && p.trace_mode < 2) { p.trace[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)w_tempty; p.trace[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)w_full; }
         }
     } else {
         // ===== epilogue: thread = query, column = corpus row =====
@@ -998,6 +1001,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (tracer) {
                 const long long c0 = clock64(); mbar_wait(&bar_tfull[buf], (it >> 1) & 1); w_tfull += clock64() - c0;
                 if (it == 0 && p.trace_mode == 2) p.trace[(size_t)blockIdx.x * 8 + 4] = globaltimer_ns();
+                if (it == 0 && p.trace_mode == 3) p.trace[(size_t)blockIdx.x * 8 + 7] = globaltimer_ns();
             } else mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             // the other slices' progress on this query: loaded now, consumed at the top of the next tile
@@ -1098,7 +1102,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             for (int t = t0; t < t1; ++t, ++it) run_tile(t, it, std::false_type(), list);
         }
         if (fold_pending && fold_ready()) fold_share();          // last chance before this CTA leaves
-        if (tracer) { p.trace[(size_t)blockIdx.x * 8 + 3] = globaltimer_ns(); p.trace[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)w_tfull; }
+        if (tracer) { p.trace[(size_t)blockIdx.x * 8 + 3] = globaltimer_ns(); if (p.trace_mode < 3) p.trace[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)w_tfull; }
 
         if (L == 0) {
             if (q < p.nq && rcount > 0) {     // compact the private region into the query's pool

@@ -39,6 +39,12 @@ def trace_summary(lib, sh):
         ft = ft[t[:, 4] > 0]; sd = sd[t[:, 5] > 0]
         waits = {"first_full_acc_us": [float(ft.min()), float(np.median(ft)), float(ft.max())],
                  "sampling_done_us": [float(sd.min()), float(np.median(sd)), float(sd.max())]}
+    if os.environ.get("B2R_TRACE") == "3":
+        def rel_(c):
+            v = (t[:, c] - t0) / 1e3
+            v = v[t[:, c] > 0]
+            return [float(v.min()), float(np.median(v)), float(v.max())] if v.size else None
+        waits = {"mma_past_launch_wait_us": rel_(4), "queries_resident_us": rel_(5), "first_corpus_kblock_us": rel_(6), "first_full_acc_us": rel_(7)}
     return {"waits": waits, "ctas": n.value, "start_spread_us": float(rel[:, 0].max()), "posted_us": [float(rel[:, 1].min()), float(rel[:, 1].max())],
             "seeded_us": [float(rel[:, 2].min()), float(rel[:, 2].max())], "done_us": [float(rel[:, 3].min()), float(np.median(rel[:, 3])), float(rel[:, 3].max())]}
 
