@@ -35,7 +35,10 @@ struct ExactParams {
     FinalizeParams fin;
 };
 
-// fp64 distances of one stored row against the G prepared queries in shared memory (fp64 copies, [G][dp]); whole warp
+// fp64 distances of one stored row against the G prepared queries in shared memory; whole warp.  The fp64 query copies are
+// laid out [G][elements per chunk][chunks] -- element e of chunk c at e * chunks + c -- so that the 32 lanes of a warp, which
+// own consecutive chunks, read consecutive doubles (conflict-free); [G][dp] in natural order had every lane 32 bytes apart: an
+// 8-way bank conflict on each of the 48 loads per row, which bound a corpus pass at ~480 GB/s.
 template <int G>
 __device__ __forceinline__ void exact_distance_warp_multi(const FinalizeParams &p, const double *qd, unsigned row, int lane,
                                                           double (&out)[G]) {
@@ -45,26 +48,29 @@ __device__ __forceinline__ void exact_distance_warp_multi(const FinalizeParams &
     for (int g = 0; g < G; ++g) acc[g] = 0.0;
     if (p.master) {
         const float4 *xr = reinterpret_cast<const float4 *>(p.master + (size_t)row * dp);
+        const int nc = dp / 4;
 #pragma unroll 3
-        for (int c = lane; c < dp / 4; c += 32) {
+        for (int c = lane; c < nc; c += 32) {
             const float4 x = __ldcg(xr + c);
             const double x0 = (double)x.x, x1 = (double)x.y, x2 = (double)x.z, x3 = (double)x.w;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const double *q = qd + (size_t)g * dp + 4 * c;
+                const double *q = qd + (size_t)g * dp + c;
+                const double q0 = q[0], q1 = q[nc], q2 = q[2 * nc], q3 = q[3 * nc];
                 if (p.space == 0) {
-                    const double a = q[0] - x0, b = q[1] - x1, cc = q[2] - x2, d = q[3] - x3;
+                    const double a = q0 - x0, b = q1 - x1, cc = q2 - x2, d = q3 - x3;
                     acc[g] = fma(a, a, acc[g]); acc[g] = fma(b, b, acc[g]); acc[g] = fma(cc, cc, acc[g]); acc[g] = fma(d, d, acc[g]);
                 } else {
-                    acc[g] = fma(q[0], x0, acc[g]); acc[g] = fma(q[1], x1, acc[g]);
-                    acc[g] = fma(q[2], x2, acc[g]); acc[g] = fma(q[3], x3, acc[g]);
+                    acc[g] = fma(q0, x0, acc[g]); acc[g] = fma(q1, x1, acc[g]);
+                    acc[g] = fma(q2, x2, acc[g]); acc[g] = fma(q3, x3, acc[g]);
                 }
             }
         }
     } else {
         const uint4 *xr = p.corpus + (size_t)row * (dp / 8);
+        const int nc = dp / 8;
 #pragma unroll 2
-        for (int c = lane; c < dp / 8; c += 32) {
+        for (int c = lane; c < nc; c += 32) {
             const uint4 w = __ldcg(xr + c);
             const unsigned ww[4] = {w.x, w.y, w.z, w.w};
             double x[8];
@@ -72,11 +78,12 @@ __device__ __forceinline__ void exact_distance_warp_multi(const FinalizeParams &
             for (int i = 0; i < 4; ++i) { x[2 * i] = (double)bf16lo(ww[i]); x[2 * i + 1] = (double)bf16hi(ww[i]); }
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const double *q = qd + (size_t)g * dp + 8 * c;
+                const double *q = qd + (size_t)g * dp + c;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (p.space == 0) { const double a = q[i] - x[i]; acc[g] = fma(a, a, acc[g]); }
-                    else acc[g] = fma(q[i], x[i], acc[g]);
+                    const double qi = q[i * nc];
+                    if (p.space == 0) { const double a = qi - x[i]; acc[g] = fma(a, a, acc[g]); }
+                    else acc[g] = fma(qi, x[i], acc[g]);
                 }
             }
         }
@@ -113,17 +120,22 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
         __syncthreads();
         if (threadIdx.x < G) s_qi[threadIdx.x] = threadIdx.x < ng ? (p.force_all ? it0 + (int)threadIdx.x : __ldcg(&p.fin.need_list[it0 + threadIdx.x])) : -1;
         __syncthreads();
+        const int epc = p.fin.master ? 4 : 8, nch = dp / epc;        // elements per chunk (one 16-byte load of a stored row), chunks
         for (int g = 0; g < G; ++g) {
             const int qi = s_qi[g];
-            for (int i = threadIdx.x; i < dp; i += EXACT_THREADS) sm_q[(size_t)g * dp + i] = qi >= 0 ? (double)p.fin.q[(size_t)qi * dp + i] : 0.0;
+            for (int i = threadIdx.x; i < dp; i += EXACT_THREADS)
+                sm_q[(size_t)g * dp + (size_t)(i % epc) * nch + i / epc] = qi >= 0 ? (double)p.fin.q[(size_t)qi * dp + i] : 0.0;
         }
         __syncthreads();
 
         WarpList<KeyD, EPL> wl[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) wl[g].init();
-        const unsigned gw = blockIdx.x * EXACT_WARPS + warp, nw = gridDim.x * EXACT_WARPS;
-        for (unsigned row = gw; row < p.n; row += nw) {
+        // every CTA streams one contiguous block of rows (a grid-wide stride made every warp touch a new 2 MB page on each
+        // row: TLB-bound at 25M+ rows)
+        const unsigned per_cta = (p.n + gridDim.x - 1) / gridDim.x;
+        const unsigned r_begin = blockIdx.x * per_cta, r_end = min(p.n, r_begin + per_cta);
+        for (unsigned row = r_begin + warp; row < r_end; row += EXACT_WARPS) {
             if (!row_passes(row, p.type_code, p.type_mask, p.allow_bits)) continue;   // warp-uniform
             double d[G];
             exact_distance_warp_multi<G>(p.fin, sm_q, row, lane, d);

@@ -1,6 +1,3 @@
-for st in 0 1 2 3; do
-echo "== B2R_SEED_TILES=$st  (0 = default)"
-B2R_SEED_TILES=$st timeout 200 python scripts/pool_large.py 1000000 1024 5 100 0 384 2>&1 | grep "^rows"
-B2R_SEED_TILES=$st timeout 200 python scripts/pool_large.py 1000000 512 5 150 0 384 2>&1 | grep "^rows"
-B2R_SEED_TILES=$st timeout 200 python scripts/pool_large.py 1000000 1024 20 100 0 384 2>&1 | grep "^rows"
-done
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_property.py tests/test_gpu_pool_large.py -x -q 2>&1 | tail -3
+timeout 300 python scripts/pool_large.py 25000000 1024 100 2 8 2>&1 | grep "exact\|parity"
+timeout 300 python scripts/pool_large.py 4000000 256 5 2 8 2>&1 | grep "exact\|parity"
