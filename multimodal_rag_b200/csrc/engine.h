@@ -62,7 +62,7 @@ int gemm_list_len(int k);          // per-thread list length L for n_results = k
 int gemm_tile_rows(int dp);        // corpus rows per MMA tile (BN)
 int gemm_encode_map(CUtensorMap *out, const void *base, int dp, uint64_t rows, int box_rows);
 int gemm_max_pairs(int dp, int L, bool bias);   // co-resident CTA pairs of the cta_group::2 form (0 = unusable)
-cudaError_t gemm_launch(int dp, int L, bool bias, bool pair, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
+cudaError_t gemm_launch(int dp, int L, bool bias, bool pair, int bm, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
                         const GemmParams &p, cudaStream_t s);
 cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_mask, const uint32_t *allow_bits,
                              unsigned n, unsigned n_words, uint32_t *out, int sm_count, cudaStream_t s);
@@ -106,7 +106,7 @@ struct b2r_index {
     // TMA tensor maps (K3), re-encoded when the buffer they describe moves or grows
     CUtensorMap tm_corpus, tm_corpus_half, tm_query;     // corpus boxes of a whole tile / of half a tile (CTA pairs)
     const void *tm_corpus_base = nullptr; int64_t tm_corpus_rows = -1;
-    const void *tm_query_base = nullptr; int64_t tm_query_rows = -1;
+    const void *tm_query_base = nullptr; int64_t tm_query_rows = -1; int tm_query_box = 0;
     // the pass bitmap is reused while (rows, type mask, tombstones) are unchanged and no allow bitmap is given
     int64_t mut_gen = 0, pb_gen = -1, pb_rows = -1; unsigned long long pb_mask = 0; const void *pb_buf = nullptr; int pb_bn = 0;
     // ... and so is a compiled clause's bitmap: filter_key = hash of the clause (0 = no clause), kept with the bitmaps it produced
@@ -124,7 +124,8 @@ struct b2r_index {
     unsigned long long seed_wait_ns = 0;
     int delay_us = 0, pool_sample_div = 0;     // 0 = by shard size (1/32, 1/64 from 8M rows on)
     bool no_pair = false;
-    bool no_dyn = false;            // B2R_NO_DYN=1: static slices only (no dynamic tile hand-out)           // B2R_NO_PAIR=1: never use the cta_group::2 form of K3
+    bool no_dyn = false;
+    bool no_bm64 = false;           // B2R_NO_BM64=1: 128-query blocks even for batches of at most 64            // B2R_NO_DYN=1: static slices only (no dynamic tile hand-out)           // B2R_NO_PAIR=1: never use the cta_group::2 form of K3
     b2r::DevBuf trace;
     bool trace_on = false; int trace_ctas = 0, trace_mode = 1;
     int timing_stage = 0;           // which launch the events bracket: 0 scoring (default); B2R_TIME_STAGE=1, 4, 5 (development):

@@ -98,21 +98,22 @@ struct GemmParams {
 // Up to 512 dims (KB <= 8) the query block stays resident in shared memory (KB * 16 KB) and a pipeline stage
 // is one corpus K-block.  Beyond that it would crowd out the ring (768 dims: 192 KB), so the query K-block is
 // streamed too: a stage = query K-block (16 KB, an L2 hit every time) + corpus K-block (32 KB).
-__host__ __device__ constexpr bool gemm_a_resident(int KB) { return KB <= 8; }
+// Up to 128 KB of resident queries: 512 dims at 128 queries per block, 1024 dims at 64 (the BM = 64 form of small batches).
+__host__ __device__ constexpr bool gemm_a_resident(int KB, int bm = 128) { return KB * bm * 128 <= 128 * 1024; }
 __host__ __device__ constexpr int gemm_bn(int KB) { return 256; }
 // PAIR: two CTAs of a cluster (the two SMs of a TPC) score 256 queries against the same corpus tile with one
 // tcgen05.mma.cta_group::2 (M = 256); each CTA stages only HALF of the tile's rows, the tensor core reads both halves,
 // so a corpus tile crosses L2 -> shared memory once per pair instead of once per query block.
-__host__ __device__ constexpr int gemm_stage_bytes(int KB, bool pair = false) {
-    return (pair ? gemm_bn(KB) / 2 : gemm_bn(KB)) * 128 + (gemm_a_resident(KB) ? 0 : GEMM_BM * 128);
+__host__ __device__ constexpr int gemm_stage_bytes(int KB, bool pair = false, int bm = 128) {
+    return (pair ? gemm_bn(KB) / 2 : gemm_bn(KB)) * 128 + (gemm_a_resident(KB, bm) ? 0 : bm * 128);
 }
-__host__ __device__ constexpr int gemm_stages(int KB, bool pair = false) {
-    int a = gemm_a_resident(KB) ? KB * GEMM_BM * 128 : 0;
-    int s = (GEMM_SMEM_LIMIT - GEMM_SMEM_SLACK - a) / gemm_stage_bytes(KB, pair);
+__host__ __device__ constexpr int gemm_stages(int KB, bool pair = false, int bm = 128) {
+    int a = gemm_a_resident(KB, bm) ? KB * bm * 128 : 0;
+    int s = (GEMM_SMEM_LIMIT - GEMM_SMEM_SLACK - a) / gemm_stage_bytes(KB, pair, bm);
     return s > 8 ? 8 : s;
 }
-__host__ __device__ constexpr size_t gemm_smem_bytes(int KB, bool pair = false) {
-    return (size_t)(gemm_a_resident(KB) ? KB * GEMM_BM * 128 : 0) + (size_t)gemm_stages(KB, pair) * gemm_stage_bytes(KB, pair) + 1024;
+__host__ __device__ constexpr size_t gemm_smem_bytes(int KB, bool pair = false, int bm = 128) {
+    return (size_t)(gemm_a_resident(KB, bm) ? KB * bm * 128 : 0) + (size_t)gemm_stages(KB, pair, bm) * gemm_stage_bytes(KB, pair, bm) + 1024;
 }
 
 // ---------------------------------------------------------------------------------
@@ -759,21 +760,28 @@ __device__ __forceinline__ unsigned warp_lth_largest(const unsigned *vals, int n
 // PAIR = launched as clusters of two CTAs (query blocks 2j and 2j+1 of the same slice): the even CTA (cluster rank 0) is the
 // leader -- it owns the full / accumulator-empty barriers and issues every tcgen05.mma.cta_group::2 for the pair; both CTAs
 // load (their own query block, their half of each corpus tile) and both run the epilogue on their own 128 TMEM lanes.
-template <int KB, int L, bool HAS_BIAS, bool PAIR>
+// BM = queries per CTA: 128, or 64 for batches of at most 64 queries (tcgen05.mma M = 64: rows 16i .. 16i+15 of the block sit on
+// TMEM lanes 32i .. 32i+15, so lanes 0..15 of every epilogue warp own a query and the other 16 idle).  Half the tensor work for
+// the same corpus stream -- on a power-capped GPU that is bandwidth (10M x 768, batch 64, sustained: 3.03 ms with M = 128 against
+// 2.50 ms for a batch of one) -- and twice the dims fit as resident queries (768 and 1024 dims stop re-fetching the query block
+// with every corpus K-block).
+template <int KB, int L, bool HAS_BIAS, bool PAIR, int BM = 128>
 // 10 warps = 3 on some SM sub-partition, whose register file is 16K: 168 registers per thread is the hard cap
 // (measured: __maxnreg__(192) compiles without spills but cannot launch)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
     constexpr int BN = gemm_bn(KB);
-    constexpr int STAGES = gemm_stages(KB, PAIR);
-    constexpr bool A_RES = gemm_a_resident(KB);
+    static_assert(BM == 128 || (BM == 64 && !PAIR), "64-query blocks exist only in the single-CTA form");
+    constexpr int STAGES = gemm_stages(KB, PAIR, BM);
+    constexpr bool A_RES = gemm_a_resident(KB, BM);
+    constexpr int QL = BM == 128 ? 32 : 16;                 // epilogue lanes per warp that own a query
     constexpr int NCTA = PAIR ? 2 : 1;
     constexpr int B_ROWS = BN / NCTA;                       // corpus rows of a tile this CTA stages (tm_x's box has this many rows)
-    constexpr uint32_t A_KB_BYTES = GEMM_BM * 128;          // one K-block of the query block
+    constexpr uint32_t A_KB_BYTES = BM * 128;               // one K-block of the query block
     constexpr uint32_t B_STAGE_BYTES = B_ROWS * 128;        // one K-block of this CTA's share of a corpus tile
-    constexpr uint32_t STAGE_BYTES = gemm_stage_bytes(KB, PAIR);  // ring slot: corpus K-block (+ query K-block when streamed)
+    constexpr uint32_t STAGE_BYTES = gemm_stage_bytes(KB, PAIR, BM);  // ring slot: corpus K-block (+ query K-block when streamed)
     constexpr uint32_t TMEM_COLS = 2 * BN;
-    constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM * NCTA, BN);
+    constexpr uint32_t IDESC = umma_idesc_bf16(BM * NCTA, BN);
     static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
 
@@ -837,7 +845,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             pdl_trigger();
             if (A_RES) {
                 if (leader) mbar_expect_tx(&bar_a, NCTA * KB * A_KB_BYTES);
-                for (int kb = 0; kb < KB; ++kb) load(smA + (size_t)kb * A_KB_BYTES, &tm_q, &bar_a, kb * 64, qb * GEMM_BM);
+                for (int kb = 0; kb < KB; ++kb) load(smA + (size_t)kb * A_KB_BYTES, &tm_q, &bar_a, kb * 64, qb * BM);
             }
             int stage = 0; uint32_t phase = 0;
             long long w_empty = 0;
@@ -850,7 +858,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&bar_empty[stage], phase ^ 1);
                         mbar_expect_tx(&bar_full[stage], STAGE_BYTES);
-                        if (!A_RES) load(smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES, &tm_q, &bar_full[stage], kb * 64, qb * GEMM_BM);
+                        if (!A_RES) load(smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES, &tm_q, &bar_full[stage], kb * 64, qb * BM);
                         load(smB + (size_t)stage * STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * BN);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -882,7 +890,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     if (p.trace) { const long long c0 = clock64(); mbar_wait(&bar_empty[stage], phase ^ 1); w_empty += clock64() - c0; }
                     else mbar_wait(&bar_empty[stage], phase ^ 1);
                     if (leader) mbar_expect_tx(&bar_full[stage], NCTA * STAGE_BYTES);     // both CTAs' bytes land on the leader's barrier
-                    if (!A_RES) load(smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES, &tm_q, &bar_full[stage], kb * 64, qb * GEMM_BM);
+                    if (!A_RES) load(smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES, &tm_q, &bar_full[stage], kb * 64, qb * BM);
                     load(smB + (size_t)stage * STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * BN + (int)crank * B_ROWS);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -942,16 +950,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         static_assert(NC % 2 == 0, "steps are processed in double-buffered pairs");
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
         const int half = (warp - 2) >> 2;                            // which half of a tile's columns
-        const int q = qb * GEMM_BM + quad * 32 + lane;
-        const bool publish = q < p.nq;
+        const bool owner = lane < QL;                                // BM = 64: lanes 16..31 of a TMEM quadrant hold no row
+        const int q = qb * BM + quad * QL + (lane & (QL - 1));       // (an idle lane aliases a real query's words, read-only)
+        const bool publish = owner && q < p.nq;
         constexpr int LL = L > 0 ? L : 1;                          // pool mode (L = 0) keeps no list during the scan ...
         constexpr int LS = L > 0 ? L : GEMM_POOL_SAMPLE_RANK;      // ... but seeds its bound from the 32nd best sample
         RegList<LL> list; list.init();
-        float thr = q >= p.nq ? INFINITY : -INFINITY;                // padding lanes admit nothing
+        float thr = publish ? -INFINITY : INFINITY;                  // padding / idle lanes admit nothing
         KeyS *region = nullptr;
         int rcount = 0;
         if (L == 0)
-            region = p.regions + ((size_t)(q - p.qblock0 * GEMM_BM) * (p.n_slices * GEMM_HALVES) + (size_t)(slice * GEMM_HALVES + half)) * p.region_cap;
+            region = p.regions + ((size_t)(q - p.qblock0 * BM) * (p.n_slices * GEMM_HALVES) + (size_t)(slice * GEMM_HALVES + half)) * p.region_cap;
         unsigned g_seen = 0;
         unsigned *gq = p.gthr + q;
         unsigned g_next = *reinterpret_cast<volatile unsigned *>(gq);
@@ -964,8 +973,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const int n_samp = (p.n_slices + p.seed_stride - 1) / p.seed_stride;      // slices that sample
         const int pv = n_samp >= LS ? 2 : n_samp * GEMM_HALVES >= LS ? 4 : min(LS, (p.seed_tiles * NC + 3) & ~3);
         const int per_q = p.n_slices * GEMM_HALVES * pv;
-        const int lq1 = GEMM_BM * (slice + 1) / p.n_slices;
-        int lq_next = GEMM_BM * slice / p.n_slices + (warp - 2);
+        const int lq1 = BM * (slice + 1) / p.n_slices;
+        int lq_next = BM * slice / p.n_slices + (warp - 2);
         bool fold_pending = false;
         auto fold_ready = [&]() -> bool {                  // have all slices of this block posted?
             unsigned a = 0u;
@@ -974,9 +983,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         };
         auto fold_share = [&]() {                          // the L-th best posted score becomes the query's bound
             for (; lq_next < lq1; lq_next += GEMM_EPI_WARPS) {
-                const int qs = qb * GEMM_BM + lq_next;
+                const int qs = qb * BM + lq_next;
                 if (qs >= p.nq) break;
-                const unsigned v = warp_lth_largest<LS>(p.samples + (size_t)(qs - p.qblock0 * GEMM_BM) * per_q, per_q, lane);
+                const unsigned v = warp_lth_largest<LS>(p.samples + (size_t)(qs - p.qblock0 * BM) * per_q, per_q, lane);
                 if (lane == 0) {
                     atomicExch(p.seeded + qs, v != 0u ? v : 1u);  // flag and seed in one word (1 = no seed: too few rows pass): the waiting threads take it from here
                     if (v != 0u) atomicMax(p.gthr + qs, v);       // the finalize (and every later tile) reads the bound from gthr[q]
@@ -1056,7 +1065,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
             // 2. post them, count this CTA in
             if (publish) {
-                unsigned *dst = p.samples + ((size_t)(q - p.qblock0 * GEMM_BM) * (p.n_slices * GEMM_HALVES) +
+                unsigned *dst = p.samples + ((size_t)(q - p.qblock0 * BM) * (p.n_slices * GEMM_HALVES) +
                                              (size_t)(slice * GEMM_HALVES + half)) * pv;
 #pragma unroll
                 for (int i = 0; i < LS; i += 2) {
@@ -1076,7 +1085,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (p.seed_wait_ns) budget = p.seed_wait_ns;
             // 3. this CTA's share of the block's queries, one per epilogue warp, as soon as every slice has posted.  The
             //    wait is bounded; a fold that cannot run now is retried at the top of every tile of the main loop.
-            fold_pending = lq_next < lq1 && qb * GEMM_BM + lq_next < p.nq;
+            fold_pending = lq_next < lq1 && qb * BM + lq_next < p.nq;
             while (fold_pending) {
                 if (fold_ready()) { fold_share(); break; }
                 if (__shfl_sync(FULL_MASK, (int)(globaltimer_ns() - t_post > budget), 0)) break;
@@ -1105,7 +1114,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (tracer) { p.trace[(size_t)blockIdx.x * 8 + 3] = globaltimer_ns(); if (p.trace_mode < 3) p.trace[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)w_tfull; }
 
         if (L == 0) {
-            if (q < p.nq && rcount > 0) {     // compact the private region into the query's pool
+            if (publish && rcount > 0) {      // compact the private region into the query's pool
                 // entries that do not reach the bound published so far need not travel: whatever is dropped here scores
                 // <= the final gthr[q], which is all the certificate asks of a row outside the pool
                 const unsigned g_now = *reinterpret_cast<volatile unsigned *>(gq);
@@ -1124,7 +1133,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     }
                 }
             }
-        } else if (q < p.nq) {    // append this thread's entries to the query's candidate pool (compact: most lists are short)
+        } else if (publish) {     // append this thread's entries to the query's candidate pool (compact: most lists are short)
             // entries below the bound published so far need not travel: whatever is dropped here scores
             // <= the final gthr[q], which is all the certificate asks of a row outside the pool
             int nv = 0;

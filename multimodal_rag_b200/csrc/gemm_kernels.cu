@@ -13,24 +13,26 @@ typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmParams);
 #ifdef B2R_KB
 #define B2R_CAT2(a, b) a##b
 #define B2R_CAT(a, b) B2R_CAT2(a, b)
-template <bool PAIR>
+template <bool PAIR, int BM>
 static gemm_fn pick(int L, bool bias) {
-    if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true, PAIR> : gemm_topk_kernel<B2R_KB, 8, false, PAIR>;
-    if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true, PAIR> : gemm_topk_kernel<B2R_KB, 16, false, PAIR>;
-    if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true, PAIR> : gemm_topk_kernel<B2R_KB, 32, false, PAIR>;
-    if (L == 0) return bias ? gemm_topk_kernel<B2R_KB, 0, true, PAIR> : gemm_topk_kernel<B2R_KB, 0, false, PAIR>;   // pool mode
+    if (L == 8) return bias ? gemm_topk_kernel<B2R_KB, 8, true, PAIR, BM> : gemm_topk_kernel<B2R_KB, 8, false, PAIR, BM>;
+    if (L == 16) return bias ? gemm_topk_kernel<B2R_KB, 16, true, PAIR, BM> : gemm_topk_kernel<B2R_KB, 16, false, PAIR, BM>;
+    if (L == 32) return bias ? gemm_topk_kernel<B2R_KB, 32, true, PAIR, BM> : gemm_topk_kernel<B2R_KB, 32, false, PAIR, BM>;
+    if (L == 0) return bias ? gemm_topk_kernel<B2R_KB, 0, true, PAIR, BM> : gemm_topk_kernel<B2R_KB, 0, false, PAIR, BM>;   // pool mode
     return nullptr;
 }
-gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias, bool pair) { return pair ? pick<true>(L, bias) : pick<false>(L, bias); }
+gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias, bool pair, int bm) {
+    return pair ? pick<true, 128>(L, bias) : bm == 64 ? pick<false, 64>(L, bias) : pick<false, 128>(L, bias);
+}
 }  // namespace b2r
 #else
-gemm_fn gemm_lookup_2(int, bool, bool);
-gemm_fn gemm_lookup_4(int, bool, bool);
-gemm_fn gemm_lookup_6(int, bool, bool);
-gemm_fn gemm_lookup_8(int, bool, bool);
-gemm_fn gemm_lookup_12(int, bool, bool);
-gemm_fn gemm_lookup_16(int, bool, bool);
-gemm_fn gemm_lookup_24(int, bool, bool);
+gemm_fn gemm_lookup_2(int, bool, bool, int);
+gemm_fn gemm_lookup_4(int, bool, bool, int);
+gemm_fn gemm_lookup_6(int, bool, bool, int);
+gemm_fn gemm_lookup_8(int, bool, bool, int);
+gemm_fn gemm_lookup_12(int, bool, bool, int);
+gemm_fn gemm_lookup_16(int, bool, bool, int);
+gemm_fn gemm_lookup_24(int, bool, bool, int);
 
 // ---------------------------------------------------------------------------------
 // pass bitmap: bit r of word r>>5 = row r is live, passes the type mask and the allow bitmap.
@@ -50,27 +52,27 @@ static __global__ void pass_bits_kernel(const uint8_t *__restrict__ type_code, u
 
 
 namespace {
-gemm_fn lookup(int kb, int L, bool bias, bool pair) {
+gemm_fn lookup(int kb, int L, bool bias, bool pair, int bm = 128) {
     switch (kb) {
-        case 2:  return gemm_lookup_2(L, bias, pair);
-        case 4:  return gemm_lookup_4(L, bias, pair);
-        case 6:  return gemm_lookup_6(L, bias, pair);     // all-MiniLM-L6-v2 (384)
-        case 8:  return gemm_lookup_8(L, bias, pair);     // CLIP ViT-B/32 shape (512)
-        case 12: return gemm_lookup_12(L, bias, pair);    // 768
-        case 16: return gemm_lookup_16(L, bias, pair);    // 1024
-        case 24: return gemm_lookup_24(L, bias, pair);    // 1536
+        case 2:  return gemm_lookup_2(L, bias, pair, bm);
+        case 4:  return gemm_lookup_4(L, bias, pair, bm);
+        case 6:  return gemm_lookup_6(L, bias, pair, bm);     // all-MiniLM-L6-v2 (384)
+        case 8:  return gemm_lookup_8(L, bias, pair, bm);     // CLIP ViT-B/32 shape (512)
+        case 12: return gemm_lookup_12(L, bias, pair, bm);    // 768
+        case 16: return gemm_lookup_16(L, bias, pair, bm);    // 1024
+        case 24: return gemm_lookup_24(L, bias, pair, bm);    // 1536
         default: return nullptr;
     }
 }
-size_t smem_of(int kb, bool pair) {
+size_t smem_of(int kb, bool pair, int bm = 128) {
     switch (kb) {
-        case 2:  return gemm_smem_bytes(2, pair);
-        case 4:  return gemm_smem_bytes(4, pair);
-        case 6:  return gemm_smem_bytes(6, pair);
-        case 8:  return gemm_smem_bytes(8, pair);
-        case 12: return gemm_smem_bytes(12, pair);
-        case 16: return gemm_smem_bytes(16, pair);
-        case 24: return gemm_smem_bytes(24, pair);
+        case 2:  return gemm_smem_bytes(2, pair, bm);
+        case 4:  return gemm_smem_bytes(4, pair, bm);
+        case 6:  return gemm_smem_bytes(6, pair, bm);
+        case 8:  return gemm_smem_bytes(8, pair, bm);
+        case 12: return gemm_smem_bytes(12, pair, bm);
+        case 16: return gemm_smem_bytes(16, pair, bm);
+        case 24: return gemm_smem_bytes(24, pair, bm);
         default: return 0;
     }
 }
@@ -160,13 +162,14 @@ int gemm_max_pairs(int dp, int L, bool bias) {
     return n;
 }
 
-// pair = launch clusters of two CTAs (query blocks 2j, 2j+1 of a slice); tm_x must then describe half-tile boxes
-cudaError_t gemm_launch(int dp, int L, bool bias, bool pair, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
+// pair = launch clusters of two CTAs (query blocks 2j, 2j+1 of a slice); tm_x must then describe half-tile boxes.
+// bm = queries per CTA (128, or 64 for one block of at most 64 queries, never with pair); tm_q's box must have bm rows
+cudaError_t gemm_launch(int dp, int L, bool bias, bool pair, int bm, const CUtensorMap &tm_q, const CUtensorMap &tm_x,
                         const GemmParams &p, cudaStream_t s) {
     const int kb = dp / 64;
-    gemm_fn f = lookup(kb, L, bias, pair);
+    gemm_fn f = lookup(kb, L, bias, pair, bm);
     if (!f) return cudaErrorInvalidValue;
-    const size_t smem = smem_of(kb, pair);
+    const size_t smem = smem_of(kb, pair, bm);
     cudaError_t e = gemm_prepare(f, smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
