@@ -22,7 +22,11 @@ static gemm_fn pick(int L, bool bias) {
     return nullptr;
 }
 gemm_fn B2R_CAT(gemm_lookup_, B2R_KB)(int L, bool bias, bool pair, int bm) {
-    return pair ? pick<true, 128>(L, bias) : bm == 64 ? pick<false, 64>(L, bias) : pick<false, 128>(L, bias);
+#if B2R_KB > 8          // 64-query blocks are only used beyond 512 dims
+    if (!pair && bm == 64) return pick<false, 64>(L, bias);
+#endif
+    if (bm != 128) return nullptr;
+    return pair ? pick<true, 128>(L, bias) : pick<false, 128>(L, bias);
 }
 }  // namespace b2r
 #else
