@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2r.so")
+LIB_PATH = os.environ.get("B2R_LIB") or os.path.join(_HERE, "libb2r.so")     # B2R_LIB: development (A/B of two builds on one box)
 
 B2R_OK, B2R_EINVAL, B2R_ECUDA, B2R_ENOMEM, B2R_EUNSUPPORTED = 0, 1, 2, 3, 4
 SPACE_CODE = {"l2": 0, "cosine": 1, "ip": 2}

@@ -90,9 +90,12 @@ struct GemmParams {
     // development knobs (0 in production; b2r_create reads them from the environment)
     unsigned long long seed_wait_ns;   // overrides the wait budget of the seeding phase (1 = do not wait at all)
     int delay_us;                // every third slice sleeps this long before it posts its samples (a slow CTA)
-    int trace_mode;              // 1: slots 4..7 = wait totals (below); 2: slots 4, 5 = globaltimer at the first full accumulator / when the sampling tiles are done
-    unsigned long long *trace;   // [grid][8]: globaltimer at epilogue start, posted, seeded, done; then SM cycles the MMA thread waited for an
-                                 // empty accumulator / for operands, the first epilogue warp for a full accumulator, the producer for a free slot (nullptr = off)
+    int trace_mode;              // 1: slot 6 = SM cycles the first epilogue warp waited for full accumulators; 2: slots 4, 5 = globaltimer at the first full accumulator / when the sampling tiles are done;
+                                 // 3: slots 4, 5, 7 = MMA thread past the launch wait / queries resident / first full accumulator.  (Nothing of
+                                 // this may sit inside the MMA thread's K-block loop: one extra predicated store there cost 14 % at batch 256.)
+    unsigned long long *trace;   // [grid][8]: globaltimer at epilogue start, posted, seeded, done; slots 4..7 by trace_mode (nullptr = off).  The
+                                 // MMA thread's and the producer's loops carry NO instrumentation: the wait totals they once kept (30 k / 37 k
+                                 // cycles per launch for an empty accumulator / for operands, profiles/r2_tensor_pipe.md) were worth knowing once
 };
 
 // Up to 512 dims (KB <= 8) the query block stays resident in shared memory (KB * 16 KB) and a pipeline stage
@@ -848,7 +851,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 for (int kb = 0; kb < KB; ++kb) load(smA + (size_t)kb * A_KB_BYTES, &tm_q, &bar_a, kb * 64, qb * BM);
             }
             int stage = 0; uint32_t phase = 0;
-            long long w_empty = 0;
             if (dyn) {
                 // ---- dynamic tiles: take the next free tile of the shard, tell the other roles which one it is ----
                 unsigned *ctr = p.tile_counter + p.qblock0;
@@ -887,15 +889,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
-                    if (p.trace) { const long long c0 = clock64(); mbar_wait(&bar_empty[stage], phase ^ 1); w_empty += clock64() - c0; }
-                    else mbar_wait(&bar_empty[stage], phase ^ 1);
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
                     if (leader) mbar_expect_tx(&bar_full[stage], NCTA * STAGE_BYTES);     // both CTAs' bytes land on the leader's barrier
                     if (!A_RES) load(smB + (size_t)stage * STAGE_BYTES + B_STAGE_BYTES, &tm_q, &bar_full[stage], kb * 64, qb * BM);
                     load(smB + (size_t)stage * STAGE_BYTES, &tm_x, &bar_full[stage], kb * 64, t * BN + (int)crank * B_ROWS);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
-            if (p.trace && p.trace_mode < 3) p.trace[(size_t)blockIdx.x * 8 + 7] = (unsigned long long)w_empty;
         }
     } else if (warp == 1) {
         // ===== MMA issuer (the leader's elected thread issues for the pair) =====
@@ -907,23 +907,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (A_RES) { mbar_wait(&bar_a, 0); tc_fence_after(); }
             if (p.trace && p.trace_mode == 3) p.trace[(size_t)blockIdx.x * 8 + 5] = globaltimer_ns();      // queries resident
             int stage = 0; uint32_t phase = 0;
-            long long w_tempty = 0, w_full = 0;
             for (int it = 0; dyn || it < n_iter; ++it) {
                 const int buf = it & 1;
                 bool last = false;
-                long long c0 = p.trace ? clock64() : 0;
                 // (PAIR: the peer's epilogue warps arrive remotely.  Default-scope arrive / try_wait, as CUTLASS's 2-SM pipelines use:
                 // the cluster-scope release/acquire forms cost ~1500 cycles per tile here; what is handed over is TMEM, ordered by
                 // the tcgen05 fences on both sides)
                 mbar_wait(&bar_tempty[buf], ((it >> 1) & 1) ^ 1);
-                if (p.trace) w_tempty += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(buf * BN);
                 for (int kb = 0; kb < KB; ++kb) {
-                    if (p.trace) c0 = clock64();
                     mbar_wait(&bar_full[stage], phase);
-                    if (p.trace) w_full += clock64() - c0;
-                    if (p.trace && p.trace_mode == 3 && it == 0 && kb == 0) p.trace[(size_t)blockIdx.x * 8 + 6] = globaltimer_ns();   // first corpus K-block resident
                     if (dyn && kb == 0 && *reinterpret_cast<volatile int *>(&tile_ring[it & 7]) < 0) { last = true; break; }
                     tc_fence_after();
                     const uint64_t ad = umma_smem_desc(smem_u32(A_RES ? smA + (size_t)kb * A_KB_BYTES
@@ -940,7 +934,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 }
                 if (last) { commit(&bar_tfull[buf]); break; }   // no tile left: pass the end marker on to the epilogue
             }
-            if (p.trace && p.trace_mode < 2) { p.trace[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)w_tempty; p.trace[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)w_full; }
         }
     } else {
         // ===== epilogue: thread = query, column = corpus row =====
@@ -1009,8 +1002,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (!SMP && g_next > g_seen) { g_seen = g_next; thr = fmaxf(thr, KeyS::unord(g_next)); }
             if (tracer) {
                 const long long c0 = clock64(); mbar_wait(&bar_tfull[buf], (it >> 1) & 1); w_tfull += clock64() - c0;
-                if (it == 0 && p.trace_mode == 2) p.trace[(size_t)blockIdx.x * 8 + 4] = globaltimer_ns();
-                if (it == 0 && p.trace_mode == 3) p.trace[(size_t)blockIdx.x * 8 + 7] = globaltimer_ns();
+                if (it == 0 && p.trace_mode >= 2) p.trace[(size_t)blockIdx.x * 8 + (p.trace_mode == 2 ? 4 : 7)] = globaltimer_ns();
             } else mbar_wait(&bar_tfull[buf], (it >> 1) & 1);
             tc_fence_after();
             // the other slices' progress on this query: loaded now, consumed at the top of the next tile

@@ -1,6 +1,8 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r2k_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2k_pytest.log
-for nb in 0 1; do
-for cfg in "10000000 64 20 200 0 768" "1000000 64 5 300 0 384" "1000000 1 5 300 0 384" "1000000 1 10 300 0 512" "1000000 16 5 300 0 384"; do
-echo "== NO_BM64=$nb $cfg"
-B2R_NO_BM64=$nb timeout 300 python scripts/pool_large.py $cfg 2>&1 | grep "^rows"
+for rep in 1 2; do
+for lib in scripts/_ab/libb2r_head_with_trace.so multimodal_rag_b200/libb2r.so; do
+echo "== $lib"
+B2R_LIB=$PWD/$lib timeout 200 python scripts/pool_large.py 1000000 256 5 400 0 384 2>&1 | grep "^rows"
+B2R_LIB=$PWD/$lib timeout 200 python scripts/pool_large.py 1000000 1024 5 150 0 384 2>&1 | grep "^rows"
+B2R_LIB=$PWD/$lib timeout 200 python scripts/pool_large.py 1000000 1 5 400 0 384 2>&1 | grep "^rows"
 done; done
+B2R_TRACE=1 python scripts/pool_large.py 1000000 256 5 50 0 384 2>&1 | grep "^trace"

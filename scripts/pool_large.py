@@ -31,9 +31,7 @@ def trace_summary(lib, sh):
     t0 = t[:, 0].min()
     rel = (t[:, :4] - t0) / 1e3
     wait = t[:, 4:]
-    waits = {"mma_wait_empty_acc_kcyc": [float(np.median(wait[:, 0][wait[:, 0] > 0]) / 1e3) if (wait[:, 0] > 0).any() else 0.0],
-             "mma_wait_operands_kcyc": [float(np.median(wait[:, 1][wait[:, 1] > 0]) / 1e3) if (wait[:, 1] > 0).any() else 0.0],
-             "epi_wait_full_acc_kcyc": float(np.median(wait[:, 2]) / 1e3), "producer_wait_slot_kcyc": float(np.median(wait[:, 3]) / 1e3)}
+    waits = {"epi_wait_full_acc_kcyc": float(np.median(wait[:, 2]) / 1e3)}
     if os.environ.get("B2R_TRACE") == "2":
         ft = (t[:, 4] - t0) / 1e3; sd = (t[:, 5] - t0) / 1e3
         ft = ft[t[:, 4] > 0]; sd = sd[t[:, 5] > 0]
@@ -44,7 +42,7 @@ def trace_summary(lib, sh):
             v = (t[:, c] - t0) / 1e3
             v = v[t[:, c] > 0]
             return [float(v.min()), float(np.median(v)), float(v.max())] if v.size else None
-        waits = {"mma_past_launch_wait_us": rel_(4), "queries_resident_us": rel_(5), "first_corpus_kblock_us": rel_(6), "first_full_acc_us": rel_(7)}
+        waits = {"mma_past_launch_wait_us": rel_(4), "queries_resident_us": rel_(5), "first_full_acc_us": rel_(7)}
     return {"waits": waits, "ctas": n.value, "start_spread_us": float(rel[:, 0].max()), "posted_us": [float(rel[:, 1].min()), float(rel[:, 1].max())],
             "seeded_us": [float(rel[:, 2].min()), float(rel[:, 2].max())], "done_us": [float(rel[:, 3].min()), float(np.median(rel[:, 3])), float(rel[:, 3].max())]}
 
