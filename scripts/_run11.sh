@@ -1,8 +1,8 @@
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2l_bench1.json 2> gpurun_out/r2l_bench1.err; echo "bench rc=$?"; tail -c 600 gpurun_out/r2l_bench1.err
-python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2l_ref1.json 2> gpurun_out/r2l_ref1.err; echo "ref rc=$?"
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2n_bench1.json 2> gpurun_out/r2n_bench1.err; echo "bench rc=$?"; tail -c 600 gpurun_out/r2n_bench1.err
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2n_ref1.json 2> gpurun_out/r2n_ref1.err; echo "ref rc=$?"
 python - <<'PY'
 import json
-j=json.load(open('gpurun_out/r2l_bench1.json')); r=json.load(open('gpurun_out/r2l_ref1.json'))
+j=json.load(open('gpurun_out/r2n_bench1.json')); r=json.load(open('gpurun_out/r2n_ref1.json'))
 print('value',j['value'],'ms',j['ms_per_step'],'min',j['ms_per_step_min'],'p99',j['ms_per_step_p99'],'e2e',j['e2e']['value'],'blocking',j['e2e']['blocking_call']['value'],j['e2e']['blocking_call']['latency_us_per_call'])
 print('ref',r['value'],r['cpu_baseline']['cores'], 'ratio', j['value']/r['value'], j['e2e']['value']/r['value'])
 rf=j['roofline']; print('roofline',rf['bound'],rf['frac'],rf['kernel_ms_per_step'],'hbm',rf['hbm']['frac'],'tensor_burst',rf['tensor']['frac_of_burst'])

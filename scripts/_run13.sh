@@ -1,8 +1,8 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r2j_bench4.json 2> gpurun_out/r2j_bench4.err; echo rc=$?
-tail -c 800 gpurun_out/r2j_bench4.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r2o_bench4.json 2> gpurun_out/r2o_bench4.err; echo rc=$?
+tail -c 800 gpurun_out/r2o_bench4.err
 python - <<'PY'
 import json
-j=json.load(open('gpurun_out/r2j_bench4.json'))
+j=json.load(open('gpurun_out/r2o_bench4.json'))
 for k in ('value','merged_queries_per_s','ms_per_step','ms_per_step_min','repeats','gpu_launches','clocks','verified'):
     print(k, j.get(k))
 print('comm', j['comm']['form_timed'], j['comm']['trial_ms_per_step'], j['comm']['nccl_all_gather_ms_per_step'])
