@@ -279,6 +279,17 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
         :: "memory");
 }
 
+// three-input maximum (one instruction on sm_100: PTX ISA 8.6 max.f32 d, a, b, c)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// maximum of 8 / of 4 values in 4 / 2 instructions
+__device__ __forceinline__ float fmax8(const float *v) {
+    return fmax3(fmax3(v[0], v[1], v[2]), fmax3(v[3], v[4], v[5]), fmaxf(v[6], v[7]));
+}
+
 // ---------------------------------------------------------------------------------
 // per-thread sorted list (descending score; equal scores keep the earlier = lower row first)
 // ---------------------------------------------------------------------------------
@@ -326,14 +337,7 @@ __device__ __forceinline__ void epi_chunk_sample(const uint32_t (&raw)[32], unsi
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((pm >> j) & 1u) ? v[j] : -INFINITY;
     }
-    float m[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) m[i] = fmaxf(v[2 * i], v[2 * i + 1]);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[2 * i], m[2 * i + 1]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) m[i] = fmaxf(m[2 * i], m[2 * i + 1]);
-    const float x = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+    const float x = fmaxf(fmax3(fmax8(v), fmax8(v + 8), fmax8(v + 16)), fmax8(v + 24));
     if (x > list.s[L - 1]) list.insert(x, r0);
 }
 
@@ -359,12 +363,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&raw)[32], unsigned r0
     }
     float m8[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const float a = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
-        const float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
-        m8[g] = fmaxf(a, b);
-    }
-    const float m32 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+    for (int g = 0; g < 4; ++g) m8[g] = fmax8(v + 8 * g);
+    const float m32 = fmaxf(fmax3(m8[0], m8[1], m8[2]), m8[3]);
     if (!__any_sync(FULL_MASK, m32 > thr)) return;
     // ---- slow path ----
     unsigned hm = 0;
@@ -475,12 +475,8 @@ __device__ __forceinline__ void epi_chunk_pool(const uint32_t (&raw)[32], unsign
     }
     float m8[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const float a = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), fmaxf(v[8 * g + 2], v[8 * g + 3]));
-        const float b = fmaxf(fmaxf(v[8 * g + 4], v[8 * g + 5]), fmaxf(v[8 * g + 6], v[8 * g + 7]));
-        m8[g] = fmaxf(a, b);
-    }
-    const float m32 = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+    for (int g = 0; g < 4; ++g) m8[g] = fmax8(v + 8 * g);
+    const float m32 = fmaxf(fmax3(m8[0], m8[1], m8[2]), m8[3]);
     if (!__any_sync(FULL_MASK, m32 > thr)) return;
     unsigned hm = 0;
 #pragma unroll
