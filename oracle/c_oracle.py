@@ -8,11 +8,13 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libb2r_oracle.so")
+_SO = os.environ.get("B2R_ORACLE_SO") or os.path.join(_HERE, "libb2r_oracle.so")    # B2R_ORACLE_SO: a sanitizer build (make -C oracle asan)
 SPACE_CODE = {"l2": 0, "cosine": 1, "ip": 2}
 
 
 def build(force: bool = False) -> str:
+    if os.environ.get("B2R_ORACLE_SO"):
+        return _SO
     srcs = [os.path.join(_HERE, f) for f in ("exact_topk.c", "hnsw_port.c", "Makefile")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "libb2r_oracle.so"])
