@@ -129,6 +129,31 @@ def _worker(rank, world, port, q):
         assert sc.count() == ref.count()
         a = sc.query(query_embeddings=Q, n_results=5); b = ref.query(query_embeddings=Q, n_results=5)
         assert a["ids"] == b["ids"]
+        # a bad batch is rejected on EVERY rank before any rank-local work (so nobody is left waiting in a collective), and
+        # changes nothing; delete() without ids or a clause raises instead of wiping the collection
+        before = sc.count()
+        for bad in (dict(ids=["x1", "x2"], embeddings=X[:2, :16]),                       # wrong dimension
+                    dict(ids=["x1", "x1"], embeddings=X[:2]),                            # duplicate ids
+                    dict(ids=["x1", "x2"], embeddings=X[:3]),                            # length mismatch
+                    dict(ids=["x1", "x2"], embeddings=X[:2], metadatas=[{"a": [1]}, {}])):   # bad metadata value
+            try:
+                sc.upsert(**bad)
+                raise AssertionError(f"accepted {list(bad)}")
+            except ValueError:
+                pass
+        for kw in ({}, {"ids": []}, {"where": {}}):
+            try:
+                sc.delete(**kw)
+                raise AssertionError("delete() without arguments must raise")
+            except ValueError:
+                pass
+        assert sc.count() == before
+        # an upsert that moves an id to another rank leaves exactly one live copy
+        sc.upsert(ids=[ids[5], ids[290], "new_2", "new_3"], embeddings=X[[1, 2, 3, 4]])
+        ref.upsert(ids=[ids[5], ids[290], "new_2", "new_3"], embeddings=X[[1, 2, 3, 4]])
+        assert sc.count() == ref.count()
+        a = sc.query(query_embeddings=X[[1, 2]], n_results=3); b = ref.query(query_embeddings=X[[1, 2]], n_results=3)
+        assert a["ids"] == b["ids"]
         q.put((rank, "ok"))
     except Exception as e:                                    # noqa: BLE001
         import traceback
