@@ -973,7 +973,7 @@ def leg_config5_collection(dev, rows0, dim, k, nq, up, device_ms):
     t0 = time.perf_counter()
     for j in range(2, steps + 2):
         rows, dist = step(j)
-        ok = ok and all(c._ids[r] == batches[j][0][i] for i, r in enumerate(rows[:8, 0].tolist())) and bool((np.abs(dist[:8, 0]) < 1e-5).all())
+        ok = ok and c.ids_of(rows[:8, 0]) == batches[j][0][:8] and bool((np.abs(dist[:8, 0]) < 1e-5).all())
     ms = (time.perf_counter() - t0) / steps * 1e3
     n_live = c.count()
     c.close()

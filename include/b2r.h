@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B2R_ABI_VERSION 3
+#define B2R_ABI_VERSION 4
 
 typedef struct b2r_index *b2r_handle;
 
@@ -219,6 +219,34 @@ int b2r_xchg_push(b2r_xchg_handle x, const int64_t *rows, const double *dist64, 
 /* merges the oldest pushed batch that has not been merged yet; outputs as b2r_merge_shards */
 int b2r_xchg_merge(b2r_xchg_handle x, int nq, int k, int64_t *out_rows, float *out_dist, int32_t *out_count, void *stream);
 int b2r_xchg_destroy(b2r_xchg_handle x);
+
+/* Host-side id table of a collection: string id <-> dense row number.  It stands where Chroma keeps its id index in sqlite
+ * (`embeddings.embedding_id`, consulted by collection.add / upsert / get(ids) / delete(ids): app/utils/embedder.py:518, 632,
+ * 640, 888): at 10M ids an interpreter-side dict costs a cache miss per id (~0.6 us, 4.7 ms per 8192-row upsert -- more than
+ * the device's share of the step); here a batch is hashed while its home slots are prefetched, then probed.  No device work,
+ * usable without a GPU.  A batch of ids = `bytes` + `offsets[n + 1]`: id i is bytes[offsets[i] .. offsets[i + 1] - gap), i.e.
+ * `gap` separator bytes follow every id (0 = packed, 1 = what "\0".join(ids) gives a binding in one call).  Rows are the
+ * dense insertion indices of b2r_ingest_f32; a row keeps its id bytes after it is erased (b2r_idtab_ids_of still answers).  */
+typedef struct b2r_idtab *b2r_idtab_handle;
+int b2r_idtab_create(int64_t reserve_ids, b2r_idtab_handle *out);
+int b2r_idtab_destroy(b2r_idtab_handle t);
+int b2r_idtab_clear(b2r_idtab_handle t);
+int64_t b2r_idtab_live(b2r_idtab_handle t);                 /* ids currently mapped                          */
+int64_t b2r_idtab_rows(b2r_idtab_handle t);                 /* rows appended so far (live or not)            */
+/* rows_out[i] = the row id i maps to, or -1.  first_dup (may be NULL) = index of the first id of the batch that repeats an
+ * earlier id of the same batch, or -1 (Chroma rejects such a batch: "Expected IDs to be unique").                          */
+int b2r_idtab_lookup(b2r_idtab_handle t, const char *bytes, const int64_t *offsets, int64_t n, int64_t gap,
+                     int64_t *rows_out, int64_t *first_dup);
+/* The batch becomes rows first_row .. first_row + n - 1 (first_row must equal b2r_idtab_rows: the value b2r_ingest_f32
+ * reported) and every id is (re-)pointed at its new row; prev_out[i] (may be NULL) = the row it pointed at before, or -1. */
+int b2r_idtab_append(b2r_idtab_handle t, const char *bytes, const int64_t *offsets, int64_t n, int64_t gap,
+                     int64_t first_row, int64_t *prev_out);
+/* Unmaps the ids of these rows (delete); an id that points at a newer row by now stays mapped.                            */
+int b2r_idtab_erase_rows(b2r_idtab_handle t, const int64_t *rows, int64_t n);
+/* The ids of `rows`, NUL-terminated, back to back: id i = out[offsets_out[i] .. offsets_out[i + 1] - 1).  *need = bytes
+ * required; nothing is written when out_cap < *need (call again with a larger buffer).                                    */
+int b2r_idtab_ids_of(b2r_idtab_handle t, const int64_t *rows, int64_t n, char *out, int64_t out_cap, int64_t *offsets_out,
+                     int64_t *need);
 
 /* Diagnostics used by bench.py: run only the scoring/selection kernel selected by
  * `path` on device-resident prepared inputs, so it can be timed alone.

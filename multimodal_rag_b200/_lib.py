@@ -22,6 +22,8 @@ ABI_SYMBOLS = (
     "b2r_get_stats", "b2r_set_row_base", "b2r_merge_shards", "b2r_merge_shards_packed", "b2r_set_path", "b2r_launch_count",
     "b2r_set_kernel_timing", "b2r_kernel_time_ms", "b2r_save", "b2r_load", "b2r_column_set", "b2r_filter_eval", "b2r_query_async", "b2r_wait",
     "b2r_debug_trace",
+    "b2r_idtab_create", "b2r_idtab_destroy", "b2r_idtab_clear", "b2r_idtab_live", "b2r_idtab_rows", "b2r_idtab_lookup",
+    "b2r_idtab_append", "b2r_idtab_erase_rows", "b2r_idtab_ids_of",
     "b2r_xchg_create", "b2r_xchg_ipc_handle", "b2r_xchg_open", "b2r_xchg_push", "b2r_xchg_merge", "b2r_xchg_destroy",
 )
 
@@ -100,6 +102,15 @@ def load() -> ctypes.CDLL:
         "b2r_xchg_push": (i32, [vp, vp, vp, vp, i32, i32, vp]),
         "b2r_xchg_merge": (i32, [vp, i32, i32, vp, vp, vp, vp]),
         "b2r_xchg_destroy": (i32, [vp]),
+        "b2r_idtab_create": (i32, [i64, ctypes.POINTER(vp)]),
+        "b2r_idtab_destroy": (i32, [vp]),
+        "b2r_idtab_clear": (i32, [vp]),
+        "b2r_idtab_live": (i64, [vp]),
+        "b2r_idtab_rows": (i64, [vp]),
+        "b2r_idtab_lookup": (i32, [vp, vp, vp, i64, i64, vp, ctypes.POINTER(i64)]),
+        "b2r_idtab_append": (i32, [vp, vp, vp, i64, i64, i64, vp]),
+        "b2r_idtab_erase_rows": (i32, [vp, vp, i64]),
+        "b2r_idtab_ids_of": (i32, [vp, vp, i64, vp, i64, vp, ctypes.POINTER(i64)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -27,7 +27,7 @@ GEMM_KBS = [2, 4, 6, 8, 12, 16, 24]  # padded dim / 64: 128, 256, 384, 512, 768,
 
 
 def _units():
-    units = [("b2r_api", "b2r_api.cu", []), ("exact_kernels", "exact_kernels.cu", []), ("xchg", "xchg.cu", []),
+    units = [("b2r_api", "b2r_api.cu", []), ("exact_kernels", "exact_kernels.cu", []), ("xchg", "xchg.cu", []), ("idtable", "idtable.cu", []),
              ("scan_dispatch", "scan_kernels.cu", [])]
     units += [(f"scan_dp{dp}", "scan_kernels.cu", [f"-DB2R_DP={dp}"]) for dp in SCAN_DPS]
     units.append(("gemm_dispatch", "gemm_kernels.cu", []))

@@ -8,9 +8,9 @@ Reference seam: ``chromadb.Client(...)`` + ``get_collection`` /
 per query for ``query``, flat lists for ``get``), Chroma's error behaviour for bad input.
 
 Vectors, scoring, selection and the exact re-rank live on the GPU behind the C ABI
-(include/b2r.h); ids, documents and metadata dicts stay in host tables keyed by the dense row
-number the device reports.  No CPU fallback exists: constructing a collection without the CUDA
-library or without a B200 raises.
+(include/b2r.h); documents and metadata dicts stay in host tables keyed by the dense row number
+the device reports, the id <-> row index is the library's native id table (b2r_idtab_*, idtable.py).
+No CPU fallback exists: constructing a collection without the CUDA library or without a B200 raises.
 """
 from __future__ import annotations
 
@@ -23,6 +23,7 @@ import threading
 import numpy as np
 
 from . import _lib
+from .idtable import IdTable, IdsByRow, RowOfId, encode_ids
 from .where import MetaTable, pack_bits
 
 logger = logging.getLogger(__name__)
@@ -86,10 +87,12 @@ class B200Collection:
         self._h = None
         self._dim = None
         self._lock = threading.RLock()
-        self._ids: list[str] = []
+        self._idtab = IdTable(reserve=self._capacity)    # id -> live row, row -> id bytes (native, b2r_idtab_*)
+        self._ids = IdsByRow(self._idtab)                # list-like / dict-like read-only views of it
+        self._row_of = RowOfId(self._idtab)
+        self._nrows = 0                                  # rows appended so far (live or tombstoned)
         self._docs: list = []
         self._alive_buf = np.zeros(1024, dtype=bool)     # tombstone table, grown x2 (amortised O(1) per row)
-        self._row_of: dict[str, int] = {}
         self._meta = MetaTable()
         self.device_where = True      # general where clauses run on the device (False: host-evaluated bitmaps)
         self._where_cache: dict = {}  # (clause as JSON, table rows) -> compiled clause
@@ -122,15 +125,15 @@ class B200Collection:
     @property
     def _alive(self) -> np.ndarray:
         """bool per appended row: not tombstoned (a view of the growable table)"""
-        return self._alive_buf[: len(self._ids)]
+        return self._alive_buf[: self._nrows]
 
     def _alive_extend(self, n_new: int) -> None:
-        need = len(self._ids) + n_new
+        have, need = self._nrows, self._nrows + n_new
         if need > self._alive_buf.shape[0]:
             grown = np.zeros(max(need, 2 * self._alive_buf.shape[0]), dtype=bool)
-            grown[: len(self._ids)] = self._alive_buf[: len(self._ids)]
+            grown[:have] = self._alive_buf[:have]
             self._alive_buf = grown
-        self._alive_buf[len(self._ids): need] = True
+        self._alive_buf[have:need] = True
 
     @property
     def handle(self):
@@ -138,18 +141,23 @@ class B200Collection:
 
     # ---- validation ------------------------------------------------------------------
     def _validate_batch(self, ids, embeddings, metadatas, documents):
-        """-> (ids as a list, the embedding matrix).  Everything per-row runs at C speed (set / map / dict of the whole
-        batch): an 8192-row upsert spends ~1 ms here, not ~3."""
+        """-> (ids as a list, the batch encoded for the id table, the row each id maps to now (-1 = new), the embedding
+        matrix).  Nothing runs per id in the interpreter: one join + encode, and the table's lookup reports repeats."""
         if ids is None or isinstance(ids, str):
             ids = [ids] if isinstance(ids, str) else ids
         if not isinstance(ids, (list, tuple)):
             raise ValueError("Expected ids to be a list of str")
         n = len(ids)
-        uniq = set(ids) if n else set()
-        if n and (set(map(type, ids)) != {str} or "" in uniq):
+        try:
+            enc = encode_ids(ids)
+            bad = enc.has_empty()
+        except TypeError:
+            bad = True
+        if bad:
             bad = next(i for i in ids if not (isinstance(i, str) and i))
             raise ValueError(f"Expected ID to be a non-empty str, got {bad!r}")
-        if len(uniq) != n:
+        found, first_dup = self._idtab.lookup(enc, want_dup=True)
+        if first_dup >= 0:
             seen, dup = set(), []
             for i in ids:
                 if i in seen:
@@ -169,10 +177,10 @@ class B200Collection:
                 MetaTable.validate(md)
         if n and self._dim is not None and m.d != self._dim:
             raise ValueError(f"Embedding dimension {m.d} does not match collection dimensionality {self._dim}")
-        return list(ids), m
+        return ids, enc, found, m
 
     # ---- mutations -------------------------------------------------------------------
-    def _append_rows(self, ids, m: _Matrix, sel, metadatas, documents):
+    def _append_rows(self, ids, enc, m: _Matrix, sel, metadatas, documents):
         """Ingest rows `sel` (indices into the batch; None = the whole batch) and register them on the host."""
         whole = sel is None or len(sel) == m.n
         n = m.n if whole else len(sel)
@@ -197,11 +205,10 @@ class B200Collection:
             ptr = keep.ctypes.data
         first = ctypes.c_int64(-1)
         _lib.check(self._lib.b2r_ingest_f32(self._h, ptr, n, codes_ptr, ctypes.byref(first), m.stream), "b2r_ingest_f32")
-        assert first.value == len(self._ids), "host tables out of step with the device corpus"
-        new_ids = ids if whole else [ids[i] for i in sel]
+        assert first.value == self._nrows, "host tables out of step with the device corpus"
         self._alive_extend(n)
-        self._row_of.update(zip(new_ids, range(first.value, first.value + n)))
-        self._ids.extend(new_ids)
+        self._idtab.append(enc if whole else encode_ids([ids[i] for i in sel]), first.value)   # (re-)points the ids at the new rows
+        self._nrows += n
         if documents is None:
             self._docs.extend([None] * n)
         else:
@@ -232,37 +239,30 @@ class B200Collection:
         arr = np.ascontiguousarray(rows, dtype=np.int64)
         _lib.check(self._lib.b2r_tombstone(self._h, arr.ctypes.data, arr.shape[0], stream), "b2r_tombstone")
         self._alive_buf[arr] = False
-        ids = self._ids
-        for r in arr.tolist():
-            self._row_of.pop(ids[r], None)
+        self._idtab.erase_rows(arr)
 
     def add(self, ids, embeddings=None, metadatas=None, documents=None):
         """Chroma ``Collection.add``: ids already present are skipped (with a warning)."""
         with self._lock:
-            ids, m = self._validate_batch(ids, embeddings, metadatas, documents)
-            row_of = self._row_of
-            if row_of.keys().isdisjoint(ids):
-                sel = None
-            else:
-                sel = [i for i, id_ in enumerate(ids) if id_ not in row_of]
+            ids, enc, found, m = self._validate_batch(ids, embeddings, metadatas, documents)
+            sel = None
+            if found.size and found.max() >= 0:
+                sel = np.flatnonzero(found < 0).tolist()
                 logger.warning("Add of existing embedding ID(s) skipped: %d of %d", len(ids) - len(sel), len(ids))
-            self._append_rows(ids, m, sel, metadatas, documents)
+            self._append_rows(ids, enc, m, sel, metadatas, documents)
 
     def upsert(self, ids, embeddings=None, metadatas=None, documents=None):
         """Chroma ``Collection.upsert``: existing ids are overwritten.  The new rows are appended FIRST and the old versions
         tombstoned after that succeeded, so a failed ingest (out of memory while growing, a bad batch) leaves the old
         versions in place; a query never sees both because both steps are enqueued on one stream before it."""
         with self._lock:
-            ids, m = self._validate_batch(ids, embeddings, metadatas, documents)
-            row_of = self._row_of
-            old = [r for r in map(row_of.get, ids) if r is not None] if row_of else []   # one probe per id; on a 10M-id table each
-                                                                                         # probe is a cache miss (~0.5 us): the host
-                                                                                         # tables, not the device, bound a big upsert
+            ids, enc, found, m = self._validate_batch(ids, embeddings, metadatas, documents)
+            old = found[found >= 0]
             if self._h is None and ids:
                 self._open(m.d)
-            self._append_rows(ids, m, None, metadatas, documents)       # re-points _row_of[id] at the new rows
-            if old:
-                arr = np.asarray(old, dtype=np.int64)
+            self._append_rows(ids, enc, m, None, metadatas, documents)  # re-points the ids at the new rows
+            if old.size:
+                arr = np.ascontiguousarray(old)
                 _lib.check(self._lib.b2r_tombstone(self._h, arr.ctypes.data, arr.shape[0], m.stream), "b2r_tombstone")
                 self._alive_buf[arr] = False
 
@@ -276,29 +276,43 @@ class B200Collection:
         with self._lock:
             rows = self._select_rows(ids, where)
             self._kill_rows(rows)
-            return [self._ids[r] for r in rows]
+            return self._idtab.ids_of(rows)
+
+    def rows_of(self, ids) -> np.ndarray:
+        """int64 per id: the live row it maps to, or -1 (one native lookup for the batch)"""
+        with self._lock:
+            return self._idtab.lookup(encode_ids(list(ids))) if len(ids) else np.empty(0, dtype=np.int64)
+
+    def ids_of(self, rows) -> list:
+        """the ids of device rows (live or tombstoned), one native call for the batch"""
+        with self._lock:
+            return self._idtab.ids_of(rows)
 
     def count(self) -> int:
         with self._lock:
             if self._h is None:
                 return 0
             n = int(self._lib.b2r_count(self._h))
-            assert n == len(self._row_of), "host tables out of step with the device corpus"
+            assert n == self._idtab.live, "host tables out of step with the device corpus"
             return n
 
     # ---- reads -----------------------------------------------------------------------
     def _where_mask(self, where) -> np.ndarray:
         """bool per row: live AND matching `where`.  The clause runs on the device columns (b2r_filter_eval) like a
         query's would; clauses the device cannot run fall back to the host tables inside `_filter`."""
-        if self._h is None or not self._ids:
-            return np.zeros(len(self._ids), dtype=bool)
+        if self._h is None or not self._nrows:
+            return np.zeros(self._nrows, dtype=bool)
         return self.filter_bits(where)
 
     def _select_rows(self, ids, where):
         if ids is not None:
             if isinstance(ids, str):
                 ids = [ids]
-            rows = sorted(self._row_of[i] for i in ids if i in self._row_of)
+            try:
+                found = self._idtab.lookup(encode_ids(ids)) if len(ids) else np.empty(0, dtype=np.int64)
+            except TypeError:
+                raise ValueError("Expected ids to be a list of str") from None
+            rows = np.unique(found[found >= 0]).tolist()
             if where and rows:
                 mask = self._where_mask(where)
                 rows = [r for r in rows if mask[r]]
@@ -333,7 +347,7 @@ class B200Collection:
                 rows = rows[offset:]
             if limit is not None:
                 rows = rows[:limit]
-            out = {"ids": [self._ids[r] for r in rows], "embeddings": None, "metadatas": None, "documents": None}
+            out = {"ids": self._idtab.ids_of(rows), "embeddings": None, "metadatas": None, "documents": None}
             if "embeddings" in include:
                 out["embeddings"] = self._fetch_rows(rows).tolist() if rows else []
             if "metadatas" in include:
@@ -388,7 +402,7 @@ class B200Collection:
     def filter_bits(self, where=None) -> np.ndarray:
         """The pass bitmap the device derives for `where` (bool per row: live AND matching) -- b2r_filter_eval."""
         with self._lock:
-            n = len(self._ids)
+            n = self._nrows
             words = np.zeros((n + 31) // 32, dtype=np.uint32)
             if self._h is not None and n:
                 f, keep = self._filter(where)
@@ -412,7 +426,7 @@ class B200Collection:
             dist = np.full((m.n, k), np.inf, dtype=np.float32)
             cnt = np.zeros((m.n,), dtype=np.int32)
             d64 = np.full((m.n, k), np.inf, dtype=np.float64) if want_dist64 else None
-            if self._h is None or not self._row_of:
+            if self._h is None or not self._idtab.live:
                 return (rows, dist, cnt, d64) if want_dist64 else (rows, dist, cnt)
             f, keep = self._filter(where)
             _lib.check(self._lib.b2r_query_ex(self._h, m.ptr, m.n, k, ctypes.byref(f), rows.ctypes.data,
@@ -430,7 +444,7 @@ class B200Collection:
             if not isinstance(n_results, int) or isinstance(n_results, bool) or n_results <= 0:
                 raise ValueError(f"Expected n_results to be a positive integer, got {n_results}")
             f, keep = self._filter(where)
-            if self._h is None or not self._row_of or f.allow_bits or f.where:
+            if self._h is None or not self._idtab.live or f.allow_bits or f.where:
                 return [self.query_rows(b, n_results, where) for b in batches]
             k, out, pending = n_results, [], []
             for b in batches:
@@ -465,16 +479,19 @@ class B200Collection:
         with self._lock:
             rows, dist, cnt = self.query_rows(query_embeddings, n_results, where)
             nq = rows.shape[0]
-            live = len(self._row_of)
+            live = self._idtab.live
             if n_results > live:
                 logger.warning("Number of requested results %d is greater than number of elements in index %d, "
                                "updating n_results = %d", n_results, live, live)
             res = {"ids": [], "distances": None, "metadatas": None, "documents": None, "embeddings": None}
             for key in include:
                 res[key] = []
+            flat = self._idtab.ids_of(np.concatenate([rows[i, : cnt[i]] for i in range(nq)])) if nq else []
+            at = 0
             for i in range(nq):
                 rr = rows[i, : cnt[i]].tolist()
-                res["ids"].append([self._ids[r] for r in rr])
+                res["ids"].append(flat[at: at + len(rr)])
+                at += len(rr)
                 if res["distances"] is not None:
                     res["distances"].append(dist[i, : cnt[i]].tolist())
                 if res["metadatas"] is not None:
@@ -498,7 +515,7 @@ class B200Collection:
                 _lib.check(self._lib.b2r_save(self._h, (base + ".b2r").encode(), 0), "b2r_save")
             tables = {"format": self._FORMAT, "name": self.name, "metadata": self.metadata, "space": self.space,
                       "dimension": self._dim, "keep_f32_master": not (self._flags & _lib.FLAG_NO_F32_MASTER),
-                      "ids": self._ids, "documents": self._docs, "metadatas": self._meta.meta,
+                      "ids": self._ids[:], "documents": self._docs, "metadatas": self._meta.meta,
                       "dead_rows": np.flatnonzero(~self._alive).tolist(),
                       "type_codes": self._meta.type_codes, "type_overflow": self._meta.type_overflow}
             tmp = base + ".tables.json.tmp"
@@ -520,21 +537,24 @@ class B200Collection:
             h = ctypes.c_void_p()
             _lib.check(c._lib.b2r_load((base + ".b2r").encode(), int(device), int(capacity), ctypes.byref(h)), "b2r_load")
             c._h, c._dim = h, int(t["dimension"])
-        c._ids, c._docs = list(t["ids"]), list(t["documents"])
+        c._docs = list(t["documents"])
+        c._nrows = len(t["ids"])
+        c._idtab.append(encode_ids(t["ids"]), 0)         # an id stored more than once ends at its last row ...
         c._meta.type_codes = {k: int(v) for k, v in t["type_codes"].items()}
         c._meta.type_overflow = bool(t["type_overflow"])
         for md in t["metadatas"]:
             c._meta.append(md)
-        c._alive_buf = np.ones(max(len(c._ids), 1024), dtype=bool)
-        c._alive_buf[np.asarray(t["dead_rows"], dtype=np.int64)] = False
-        c._row_of = {id_: r for r, id_ in enumerate(c._ids) if c._alive_buf[r]}
+        c._alive_buf = np.ones(max(c._nrows, 1024), dtype=bool)
+        dead = np.asarray(t["dead_rows"], dtype=np.int64)
+        c._alive_buf[dead] = False
+        c._idtab.erase_rows(dead)                        # ... and a deleted id whose last row is dead is unmapped
         if c._h is not None:
-            c._push_columns(0, len(c._ids), list(c._meta.cols))
+            c._push_columns(0, c._nrows, list(c._meta.cols))
             st = c.stats()
-            if st["rows"] != len(c._ids) or st["live"] != len(c._row_of) or st["dim"] != c._dim:
+            if st["rows"] != c._nrows or st["live"] != c._idtab.live or st["dim"] != c._dim:
                 c.close()
                 raise ValueError(f"{base}: shard file and host tables disagree "
-                                 f"(rows {st['rows']} vs {len(c._ids)}, live {st['live']} vs {len(c._row_of)})")
+                                 f"(rows {st['rows']} vs {c._nrows}, live {st['live']} vs {c._idtab.live})")
         return c
 
     def stats(self) -> dict:

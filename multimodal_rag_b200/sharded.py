@@ -99,7 +99,7 @@ class ShardedCollection:
             from .where import MetaTable
             for md in metadatas:
                 MetaTable.validate(md)
-        have_local = [i for i in ids if i in self.shard._row_of]
+        have_local = self._held(ids)
         have = set().union(*self._all_gather_obj(have_local))
         if upsert:
             new = list(range(n))
@@ -126,6 +126,13 @@ class ShardedCollection:
             self._gseq_dev = None
         self._next_seq += len(new)
 
+    def _held(self, ids) -> list:
+        """the ids of the batch this rank's shard holds (live)"""
+        if not len(ids):
+            return []
+        found = self.shard.rows_of(ids)
+        return [i for i, r in zip(ids, found.tolist()) if r >= 0]
+
     def add(self, ids, embeddings=None, metadatas=None, documents=None):
         self._ingest(list(ids), embeddings, metadatas, documents, upsert=False)
 
@@ -136,7 +143,7 @@ class ShardedCollection:
         if (ids is None or len(ids) == 0) and not where:
             raise ValueError("You must provide either ids, where, or where_document to delete.")
         if ids is not None:
-            ids = [i for i in ids if i in self.shard._row_of]
+            ids = self._held(ids)
             if not ids and where is None:
                 return
         self.shard.delete(ids=ids, where=where)
@@ -176,11 +183,13 @@ class ShardedCollection:
         # winners owned by this rank -> payload; one object all_gather assembles the rest
         mine = {}
         if len(self._gseq):
-            for i in range(nq):
-                for s in g[i, : cnt[i]].tolist():
-                    pos = int(np.searchsorted(self._gseq, s))
-                    if pos < len(self._gseq) and self._gseq[pos] == s:
-                        mine[s] = (self.shard._ids[pos], self.shard._meta.meta[pos], self.shard._docs[pos])
+            seqs = np.unique(np.concatenate([g[i, : cnt[i]] for i in range(nq)])) if nq else np.empty(0, dtype=np.int64)
+            pos = np.minimum(np.searchsorted(self._gseq, seqs), len(self._gseq) - 1)
+            own = self._gseq[pos] == seqs
+            seqs, pos = seqs[own].tolist(), pos[own]
+            meta, docs = self.shard._meta.meta, self.shard._docs
+            for s, p, id_ in zip(seqs, pos.tolist(), self.shard.ids_of(pos)):      # one id-table call for all winners
+                mine[s] = (id_, meta[p], docs[p])
         table = {}
         for part in self._all_gather_obj(mine):
             table.update(part)

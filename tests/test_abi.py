@@ -31,7 +31,7 @@ def test_header_symbols_exported(lib):
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert set(decl) <= exported
     assert {s for s in exported if s.startswith("b2r_")} == set(decl)       # nothing undocumented
-    assert lib.b2r_abi_version() == 3
+    assert lib.b2r_abi_version() == 4
 
 
 def test_library_is_sm100a_native(lib):

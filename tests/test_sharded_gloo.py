@@ -21,13 +21,11 @@ class OracleShard:
         self.eo = eo
         self.c = eo.ExactCollection("shard", {"hnsw:space": space})
 
-    @property
-    def _row_of(self):
-        return self.c._row_of
+    def rows_of(self, ids):
+        return np.asarray([self.c._row_of.get(i, -1) for i in ids], dtype=np.int64)
 
-    @property
-    def _ids(self):
-        return self.c._ids
+    def ids_of(self, rows):
+        return [self.c._ids[int(r)] for r in rows]
 
     @property
     def _docs(self):
