@@ -577,6 +577,23 @@ def run_gpu(args):
         shd_nccl = summarize(timed(step_sharded_nccl, K, min_s=0.2), K)
         if args.p2p_exchange:
             sh2.enable_p2p_exchange(nq_max=max(nq, 1024), k_max=128)
+        # the fused exchange (b2r_query_push): mailboxes mapped with CUDA IPC; NCCL stays what query_device / _pipelined use
+        fused_ok = True
+        try:
+            sh2.enable_p2p_exchange(nq_max=max(nq, 1024), k_max=128, default=False)
+        except Exception as e:                        # no peer access between these GPUs: the NCCL forms remain
+            sys.stderr.write(f"[bench] fused exchange unavailable: {e}\n")
+            fused_ok = False
+        t_ok = torch.tensor([1 if fused_ok else 0], device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        fused_ok = bool(int(t_ok.item()))
+
+        def step_sharded_fused(i):
+            # the finalize of batch i stores its lists into every rank's mailbox; the merge of batch i rides behind the kernels
+            # of batch i+1; the last step of a region merges what is still pending
+            sh2.query_device_fused(Q2[i % n_batches], k, o2b[i % 2])
+            if i == K - 1:
+                sh2.drain()
 
         def step_sharded_pipelined(i):
             # the exchange of batch i (all_gather + merge, side stream) overlaps the scan of batch i+1; the last step of a
@@ -599,10 +616,17 @@ def run_gpu(args):
             step_sharded_serial(i)
         trial = {"pipelined": summarize(timed(step_sharded_pipelined, K, min_s=0.1), K)["ms_per_step"],
                  "serial": summarize(timed(step_sharded_serial, K, min_s=0.1), K)["ms_per_step"]}
-        pick = torch.tensor([1 if trial["pipelined"] < trial["serial"] else 0], device=dev)
+        if fused_ok:
+            for i in range(W):
+                step_sharded_fused(i)
+            sh2.drain()
+            trial["fused"] = summarize(timed(step_sharded_fused, K, min_s=0.1), K)["ms_per_step"]
+        forms = sorted(trial)
+        pick = torch.tensor([forms.index(min(trial, key=trial.get))], device=dev)
         dist.broadcast(pick, 0)
-        use_pipelined = bool(int(pick.item()))
-        step_sharded = step_sharded_pipelined if use_pipelined else step_sharded_serial
+        form = forms[int(pick.item())]
+        use_pipelined = form == "pipelined"
+        step_sharded = {"pipelined": step_sharded_pipelined, "serial": step_sharded_serial, "fused": step_sharded_fused if fused_ok else None}[form]
         launches0 = lib.b2r_launch_count(sh2.h)
         shd = summarize(timed(step_sharded, K), K)
         shd_serial = {"ms_per_step": trial["serial"]}
@@ -620,8 +644,13 @@ def run_gpu(args):
         run_sharded_host(W)
         shd_e2e = summarize(timed_wall(run_sharded_host, K), K)
 
-        # self-check: the merged rows of batch 0 == a single-GPU answer over the union of the shards (rank 0 builds it)
-        sh2.query_device(Q2[0], k, o2)
+        # self-check: the merged rows of batch 0 == a single-GPU answer over the union of the shards (rank 0 builds it),
+        # through the form that was timed
+        if form == "fused":
+            sh2.query_device_fused(Q2[0], k, o2)
+            sh2.drain()
+        else:
+            sh2.query_device(Q2[0], k, o2)
         torch.cuda.synchronize()
         verified, detail = None, None
         if rank == 0:
@@ -641,17 +670,28 @@ def run_gpu(args):
         if int(vflag.item()) != 1:
             raise SystemExit("bench: row-sharded result differs from the single-GPU answer over the union")
         bytes_per_rank = o2["layout"][0]
+        if form == "fused":
+            comm_backend = "nccl for setup and timing reductions only; data path: peer-to-peer stores over NVLink from the query's own kernels"
+        elif args.p2p_exchange:
+            comm_backend = "nccl for setup and timing reductions; data path: peer-to-peer stores over NVLink (b2r_xchg_push / b2r_xchg_merge)"
+        else:
+            comm_backend = "nccl"
         line.update({"value": world * nq / (shd["ms_per_step"] * 1e-3), **shd,
                      "merged_queries_per_s": nq / (shd["ms_per_step"] * 1e-3),
                      "ms_per_step_per_rank": per_rank_ms, "verified": True, "verified_how": detail if rank == 0 else None,
-                     "comm": {"backend": "nccl" if not args.p2p_exchange else "nccl for setup and timing reductions; data path: peer-to-peer stores over NVLink (b2r_xchg_push / b2r_xchg_merge)",
+                     "comm": {"backend": comm_backend,
                               "nranks": world, "collectives_per_step": 1,
                               "collective": "exchange of the per-rank [batch, top_k] x (int64 row, fp64 distance) + [batch] int32 count lists",
                               "bytes_sent_per_rank_per_step": bytes_per_rank, "bytes_gathered_per_rank_per_step": world * bytes_per_rank,
-                              "exchange": sh2.exchange_mode + ("; issued on a side stream behind an event so that it overlaps the scan of the next batch "
+                              "nvlink_bytes_stored_per_rank_per_step": (world - 1) * nq * (k * 16 + 4) if form == "fused" else None,
+                              "exchange": ("fused into the query's kernels (b2r_query_push): the finalize / fix-up kernels store every final list into the "
+                                           "peers' mailboxes over NVLink (CUDA IPC), the call's last kernel publishes the arrival, the merge of batch i is "
+                                           "one small launch behind the kernels of batch i+1; no collective and no exchange kernel between two scans "
+                                           "(DeviceShard.query_device_fused)") if form == "fused" else
+                                          sh2.exchange_mode + ("; issued on a side stream behind an event so that it overlaps the scan of the next batch "
                                                                "(DeviceShard.query_device_pipelined)" if use_pipelined else "; on the scan's stream (DeviceShard.query_device)"),
-                              "form_timed": "pipelined" if use_pipelined else "serial", "trial_ms_per_step": trial,
-                              "trial_note": "both forms are timed for 0.1 s and the faster one is measured in full",
+                              "form_timed": form, "trial_ms_per_step": trial,
+                              "trial_note": "every form is timed for 0.1 s and the fastest one is measured in full",
                               "nccl_all_gather_ms_per_step": shd_nccl["ms_per_step"],
                               "nccl_note": "the same step with torch.distributed all_gather_into_tensor + b2r_merge_shards_packed on one stream"},
                      "e2e": {"value": world * nq / (shd_e2e["ms_per_step"] * 1e-3), "unit": UNIT, **shd_e2e,

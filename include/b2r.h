@@ -219,6 +219,15 @@ int b2r_xchg_push(b2r_xchg_handle x, const int64_t *rows, const double *dist64, 
 /* merges the oldest pushed batch that has not been merged yet; outputs as b2r_merge_shards */
 int b2r_xchg_merge(b2r_xchg_handle x, int nq, int k, int64_t *out_rows, float *out_dist, int32_t *out_count, void *stream);
 int b2r_xchg_destroy(b2r_xchg_handle x);
+/* The fused form of push: b2r_query (device-resident outputs only) whose kernels ALSO store every final list into the mailboxes of
+ * `x` as they emit it -- the finalize of the scoring kernels, the exact fix-up -- and whose last kernel publishes the arrival on
+ * its way out.  No exchange kernel, no collective, no stream memory operation is enqueued; the call's first kernel holds the stream
+ * until the mailbox slot's previous contents (four slots, round-robin) have been merged by every rank.  The batch is merged by
+ * b2r_xchg_merge like a pushed one, except that the merge kernel itself checks the arrival words: enqueue the merge of batch i
+ * AFTER b2r_query_push of batch i+1 and the exchange costs one small launch per batch (at most four batches may be pushed and
+ * not yet merged).  Collective like push / merge: same sequence of calls, same nq and k on every rank.                          */
+int b2r_query_push(b2r_handle h, b2r_xchg_handle x, const float *q, int nq, int k, const b2r_filter *filter,
+                   int64_t *out_rows, float *out_dist, int32_t *out_count, void *stream);
 
 /* Host-side id table of a collection: string id <-> dense row number.  It stands where Chroma keeps its id index in sqlite
  * (`embeddings.embedding_id`, consulted by collection.add / upsert / get(ids) / delete(ids): app/utils/embedder.py:518, 632,

@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "b2r_debug_trace",
     "b2r_idtab_create", "b2r_idtab_destroy", "b2r_idtab_clear", "b2r_idtab_live", "b2r_idtab_rows", "b2r_idtab_lookup",
     "b2r_idtab_append", "b2r_idtab_erase_rows", "b2r_idtab_ids_of",
-    "b2r_xchg_create", "b2r_xchg_ipc_handle", "b2r_xchg_open", "b2r_xchg_push", "b2r_xchg_merge", "b2r_xchg_destroy",
+    "b2r_xchg_create", "b2r_xchg_ipc_handle", "b2r_xchg_open", "b2r_xchg_push", "b2r_xchg_merge", "b2r_xchg_destroy", "b2r_query_push",
 )
 
 
@@ -102,6 +102,7 @@ def load() -> ctypes.CDLL:
         "b2r_xchg_push": (i32, [vp, vp, vp, vp, i32, i32, vp]),
         "b2r_xchg_merge": (i32, [vp, i32, i32, vp, vp, vp, vp]),
         "b2r_xchg_destroy": (i32, [vp]),
+        "b2r_query_push": (i32, [vp, vp, vp, i32, i32, ctypes.POINTER(B2RFilter), vp, vp, vp, vp]),
         "b2r_idtab_create": (i32, [i64, ctypes.POINTER(vp)]),
         "b2r_idtab_destroy": (i32, [vp]),
         "b2r_idtab_clear": (i32, [vp]),

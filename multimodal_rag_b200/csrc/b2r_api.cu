@@ -347,6 +347,7 @@ extern "C" int b2r_ingest_f32(b2r_handle h, const float *x, int64_t n, const uin
     p.type_in = td;
     p.max_norm2 = h->max_norm2; p.qerr = nullptr; p.q_eps = nullptr; p.norms = nullptr; p.eps_rel = 0.f;
     for (int z = 0; z < 3; ++z) { p.zero[z] = nullptr; p.zero_words[z] = 0; }
+    p.wait_words = nullptr; p.wait_n = 0; p.wait_val = 0;
     const int wpb = INGEST_THREADS / 32;
     const ingest_fn fn = ingest_lookup(h->dim, h->dp, xd);
     // one full wave of resident CTAs, every warp walks its share of the rows (no tail wave)
@@ -793,6 +794,7 @@ int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const Finaliz
     p.fin = fin;
     for (int first = 0; first < nq; first += items) {
         p.first_item = first;
+        p.publish = (fin.push.world && first + items >= nq) ? 1 : 0;     // the call's very last launch
         KernelTimer kt(h, s, force_all ? 0 : 5);   // the certificate fix-up is not the scoring kernel
         B2R_CUDA(exact_launch(epl, p, grid, s));
         kt.stop();
@@ -931,7 +933,7 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
 // the query itself; the caller holds h->mu
 static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
                         int64_t *out_rows, float *out_dist, double *out_dist64, int32_t *out_count,
-                        void *stream) {
+                        void *stream, b2r_xchg *push_to = nullptr) {
     B2R_REQUIRE(nq >= 1 && q, "b2r_query: need at least one query");
     B2R_REQUIRE(k >= 1, "b2r_query: n_results must be a positive integer");
     B2R_REQUIRE(out_rows && out_dist && out_count, "b2r_query: NULL output");
@@ -939,6 +941,7 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
     B2R_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     const bool dev_out = is_device_ptr(out_rows);
+    B2R_REQUIRE(!push_to || dev_out, "b2r_query_push: outputs must be device pointers");
     B2R_REQUIRE(dev_out == is_device_ptr(out_dist) && dev_out == is_device_ptr(out_count) &&
                     (!out_dist64 || dev_out == is_device_ptr(out_dist64)),
                 "b2r_query: outputs must all be host or all be device pointers");
@@ -1006,6 +1009,7 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
     if (h->rows == 0) path = 3;   // empty collection: Chroma returns empty lists; only the padding is written
 
     // ---- prepare queries (cosine: hnswlib normalisation; zero-pad to dp; bf16 copy for K3) ----
+    PushParams push;
     if (path == 2 && (rc = ensure(h->q_bf16, (size_t)nq * h->dp * 2)) != B2R_OK) return rc;
     if (path == 2 && (rc = ensure(h->q_err, (size_t)nq * 4)) != B2R_OK) return rc;
     {
@@ -1020,6 +1024,11 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
         p.q_eps = (double *)h->q_eps.p; p.norms = h->max_norm2;
         p.eps_rel = (float)(h->dp + 8) * 5.9604645e-8f * (path == 2 ? 4.f : 1.f) * 1.01f;
         // per-call shared state, cleared by the preparation: the fix-up work list control, ...
+        p.wait_words = nullptr; p.wait_n = 0; p.wait_val = 0;
+        std::memset(&push, 0, sizeof push);
+        // fused exchange: take the next mailbox slot now (nothing after this point fails before the kernels are enqueued
+        // short of a CUDA error, which breaks the collective anyway)
+        if (push_to && (rc = xchg_begin_push(push_to, h->device, nq, k, &push, &p.wait_words, &p.wait_n, &p.wait_val)) != B2R_OK) return rc;
         p.zero[0] = (unsigned *)h->need_ctl; p.zero_words[0] = 2;
         p.zero[1] = nullptr; p.zero_words[1] = 0;
         p.zero[2] = nullptr; p.zero_words[2] = 0;
@@ -1043,6 +1052,7 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
     fin.row_base = h->row_base; fin.out_rows = o_rows; fin.out_dist = o_dist; fin.out_dist64 = o_dist64;
     fin.out_count = o_count; fin.need_ctl = h->need_ctl; fin.need_list = (int *)h->need_list.p;
     fin.q_eps = (const double *)h->q_eps.p;
+    fin.push = push;
 
     if (path == 1) {
         ScanParams sp;
@@ -1080,6 +1090,13 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
     B2R_REQUIRE(h, "b2r_query: NULL handle");
     std::lock_guard<std::mutex> g(h->mu);
     return query_locked(h, q, nq, k, filter, out_rows, out_dist, out_dist64, out_count, stream);
+}
+
+extern "C" int b2r_query_push(b2r_handle h, b2r_xchg_handle x, const float *q, int nq, int k, const b2r_filter *filter,
+                              int64_t *out_rows, float *out_dist, int32_t *out_count, void *stream) {
+    B2R_REQUIRE(h && x, "b2r_query_push: NULL handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    return query_locked(h, q, nq, k, filter, out_rows, out_dist, nullptr, out_count, stream, x);
 }
 
 extern "C" int b2r_query(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,

@@ -200,6 +200,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // row filter: tombstones carry type code 63, which no mask ever has set
 #define B2R_TYPE_DEAD 63
 __device__ __forceinline__ bool row_passes(unsigned row, const uint8_t *__restrict__ type_code,

@@ -68,6 +68,10 @@ cudaError_t pass_bits_launch(const uint8_t *type_code, unsigned long long type_m
                              unsigned n, unsigned n_words, uint32_t *out, int sm_count, cudaStream_t s);
 cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const UnionParams &u, int q0, int nq, cudaStream_t s);
 
+// xchg.cu: reserves the next mailbox slot of `x` for a fused push of nq x k lists and fills what the kernels need; the acks the
+// first kernel must see before anything is stored are returned as (words, count, value)
+int xchg_begin_push(b2r_xchg *x, int device, int nq, int k, PushParams *out, const unsigned **wait_words, int *wait_n, unsigned *wait_val);
+
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;

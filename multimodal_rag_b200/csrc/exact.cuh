@@ -32,6 +32,7 @@ struct ExactParams {
     KeyD *cta_lists;              // [slots][G][gridDim.x][KP]
     unsigned *tickets;            // [EXACT_MAX_SLOTS] arrival tickets (0 between launches: the last CTA of a group resets its own)
     long long *n_fallbacks;       // device counter (may be nullptr)
+    int publish;                  // b2r_query_push, last launch of the call: the last CTA to leave publishes the arrival words
     FinalizeParams fin;
 };
 
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
             }
         }
     }
+    if (p.publish) push_publish(p.fin.push);
 }
 
 inline size_t exact_smem_bytes(int EPL, int G, int dp) {

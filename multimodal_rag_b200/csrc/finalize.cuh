@@ -23,6 +23,19 @@ struct FinCta {
     }
 };
 
+// Row-sharded corpus, fused exchange (b2r_query_push): whoever emits a query's final list also stores it -- global row,
+// fp64 distance, count -- straight into every rank's mailbox over NVLink (xchg.cu describes the mailboxes), so the lists
+// travel while the rest of the batch is still being finalized and no separate exchange kernel or collective runs.
+struct PushParams {
+    char *box[8];                       // every rank's mailbox as mapped here (box[rank] = the local one)
+    unsigned long long lists_off;       // this call's slot, this rank's block of lists: slot * slot_bytes + rank * nq_max * entry_bytes
+    unsigned long long arrive_off;      // the word (slot, this rank) of the arrival block -- written in EVERY mailbox once the call is complete
+    unsigned long long ticket_off;      // local exit ticket of the call's last kernel
+    unsigned entry_bytes, k_max;        // one query's entry: rows[k_max] i64 | dist[k_max] f64 | count i32 (+pad)
+    unsigned seq;                       // this call's sequence number
+    int world, rank;                    // world = 0: no push
+};
+
 struct FinalizeParams {
     const float *master;        // [rows, dp] fp32 stored rows, or nullptr (bf16-only corpus)
     const uint4 *corpus;        // [rows, dp] bf16 stored rows
@@ -37,7 +50,12 @@ struct FinalizeParams {
     int *out_count;             // [nq]
     int *need_ctl;              // [0] = number of queries whose certificate failed (this call; the query preparation clears it)
     int *need_list;             // [nq]: those queries, in arrival order; the exact scan (K5) redoes them
+    PushParams push;            // world = 0 unless the call is b2r_query_push
 };
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // exact distance between prepared query and stored row, fp64 accumulation, whole warp
 __device__ __forceinline__ double exact_distance_warp(const FinalizeParams &p, const float *qv,
@@ -148,6 +166,14 @@ __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, con
             p.out_rows[(size_t)qi * k + rank] = p.row_base + (long long)me.row;
             p.out_dist[(size_t)qi * k + rank] = (float)me.d;
             if (p.out_dist64) p.out_dist64[(size_t)qi * k + rank] = me.d;
+            if (p.push.world) {                          // the same entry into every rank's mailbox (a redone query overwrites its entry)
+                const size_t e_off = p.push.lists_off + (size_t)qi * p.push.entry_bytes;
+                for (int w = 0; w < p.push.world; ++w) {
+                    char *e = p.push.box[w] + e_off;
+                    reinterpret_cast<long long *>(e)[rank] = p.row_base + (long long)me.row;
+                    reinterpret_cast<double *>(e + (size_t)p.push.k_max * 8)[rank] = me.d;
+                }
+            }
         }
         if (rank == k - 1) *kth_out = me;
     }
@@ -157,6 +183,28 @@ __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, con
         if (p.out_dist64) p.out_dist64[(size_t)qi * k + t] = __longlong_as_double(0x7ff0000000000000ll);
     }
     if (tid == 0) p.out_count[qi] = cnt;
+    if (p.push.world && tid < p.push.world)
+        *reinterpret_cast<int *>(p.push.box[tid] + p.push.lists_off + (size_t)qi * p.push.entry_bytes + (size_t)p.push.k_max * 16) = cnt;
+}
+
+// Last kernel of a b2r_query_push call, every CTA on its way out: the last one to leave tells every rank that this rank's
+// lists of call `seq` are in place.  The lists were stored by CTAs of this grid (each fences at system scope before it
+// takes its ticket) or by grids that completed before this one started.
+__device__ __forceinline__ void push_publish(const PushParams &push) {
+    if (!push.world) return;
+    __shared__ unsigned s_exit;
+    __threadfence_system();
+    __syncthreads();
+    unsigned *ticket = reinterpret_cast<unsigned *>(push.box[push.rank] + push.ticket_off);
+    if (threadIdx.x == 0) s_exit = atomicAdd(ticket, 1u);
+    __syncthreads();
+    if (s_exit == gridDim.x - 1) {
+        if (threadIdx.x == 0) *ticket = 0u;              // ready for the next call on this stream
+        if ((int)threadIdx.x < push.world) {
+            __threadfence_system();
+            st_release_sys_u32(reinterpret_cast<unsigned *>(push.box[threadIdx.x] + push.arrive_off), push.seq);
+        }
+    }
 }
 
 // Stages shared by every scoring path once the candidate set is known (sm_keys: nvalid candidates,

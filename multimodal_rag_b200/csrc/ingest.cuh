@@ -26,6 +26,9 @@ struct IngestParams {
     unsigned *zero[3];         // query preparation: per-call shared state (K3's bounds, cursors, flags, counters; the
     int zero_words[3];         // fix-up work list control; K5's slot generations) is cleared here, after the previous
                                // query's kernels have finished with it
+    const unsigned *wait_words;    // b2r_query_push: the first kernel of the call holds the stream until every rank has read what
+    int wait_n;                    // the mailbox slot held before (wait_words[0 .. wait_n) >= wait_val, written by the peers);
+    unsigned wait_val;             // wait_n = 0 otherwise.  Normally true long before: the slot was used four calls ago.
 };
 
 // 1/(sqrt(s)+1e-30) exactly as hnswlib's normalize_vector does it in fp32
@@ -119,6 +122,16 @@ __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(const IngestPara
     const int d = p.d, dp = p.dp, chunks = dp / 8;
     pdl_wait();          // query preparation overwrites buffers the previous query's kernels may still read
     pdl_trigger();
+    if (p.wait_n && blockIdx.x == 0 && (int)threadIdx.x < p.wait_n) {
+        unsigned v;
+        const unsigned long long t0 = globaltimer_ns();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_words + threadIdx.x) : "memory");
+            if ((int)(v - p.wait_val) >= 0) break;
+            if (globaltimer_ns() - t0 > 4000000000ull) __trap();      // a peer that stopped merging: fail, do not hang
+            __nanosleep(200);
+        }
+    }
 #pragma unroll
     for (int z = 0; z < 3; ++z)
         for (int i = blockIdx.x * INGEST_THREADS + threadIdx.x; i < p.zero_words[z]; i += gridDim.x * INGEST_THREADS) p.zero[z][i] = 0u;

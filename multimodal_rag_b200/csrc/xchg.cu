@@ -17,6 +17,13 @@
 // cannot start itself (measured: a fused spin-wait version cost +31 us per batch on one stream and up to +50 us with outliers on a
 // side stream, NCCL's all_gather + a merge launch +26 us / +8 us).  Calls are collective: every rank makes the same sequence of
 // push / merge calls with the same nq and k.
+//
+// Fused form (b2r_query_push): no push kernel at all.  The kernels of the query store every final list into the mailboxes
+// as they emit it (finalize.cuh, emit_sorted), the call's last kernel publishes the arrival words on its way out, and the first
+// kernel of the call holds the stream until the slot's previous contents have been read everywhere (acks; four slots, so that is
+// normally true long before).  b2r_xchg_merge for such a batch checks the arrival words INSIDE the merge kernel (a bounded spin
+// on local memory): the caller enqueues the merge of batch i after the kernels of batch i+1, by which time the lists have
+// arrived, so neither a stream memory operation nor a collective kernel ever stands between two scans.
 #include <algorithm>
 #include <cstring>
 #include <new>
@@ -34,14 +41,16 @@ namespace {
 
 constexpr int XCHG_MAX_WORLD = 8;
 constexpr int XCHG_THREADS = 256;
+constexpr int XCHG_SLOTS = 4;          // mailbox slots, used round-robin by sequence number
 
 struct XchgDev {
     int rank, world, nq, k, slot;
+    int spin;                      // merge: wait for the arrival words inside the kernel (fused pushes) instead of on the stream
     unsigned seq;
     int nq_max, k_max;
     size_t entry_bytes;            // one query's list in a mailbox: rows[k_max] i64 | dist[k_max] f64 | count i32 (+pad)
     size_t slot_bytes;             // world * nq_max * entry_bytes
-    size_t flags_off;              // arrival words [2][world] u32, ack words [2][world] u32, two exit tickets
+    size_t flags_off;              // arrival words [SLOTS][world] u32, ack words [SLOTS][world] u32, three exit tickets
     char *box[XCHG_MAX_WORLD];     // every rank's mailbox as mapped in this process (box[rank] = the local allocation)
     const long long *rows; const double *d64; const int *cnt;      // push: this rank's local results
     long long *out_rows; float *out_dist; int *out_cnt;            // merge: outputs
@@ -77,7 +86,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_push_kernel(const XchgDev p
     }
     // the last CTA publishes: every store of this grid is ordered before its release (threadfence + ticket), and the release is
     // at system scope because the peers' streams read the word
-    unsigned *ticket = flag_words(p, p.rank) + 4 * p.world;
+    unsigned *ticket = flag_words(p, p.rank) + 2 * XCHG_SLOTS * p.world;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
@@ -101,6 +110,19 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_merge_kernel(const XchgDev 
     __shared__ unsigned s_ticket;
     const int tid = threadIdx.x, q = blockIdx.x;
     if (tid == 0) s_valid = 0;
+    pdl_wait();
+    pdl_trigger();
+    if (p.spin && tid < p.world) {      // fused pushes: the lists of every rank (this one included) must have arrived
+        const unsigned *w = flag_words(p, p.rank) + p.slot * p.world + tid;
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
+            if ((int)(v - p.seq) >= 0) break;
+            if (globaltimer_ns() - t0 > 4000000000ull) __trap();      // a peer that never pushed: fail, do not hang
+            __nanosleep(100);
+        }
+    }
     __syncthreads();
     const char *mine = p.box[p.rank] + (size_t)p.slot * p.slot_bytes;
     int my_valid = 0;
@@ -136,7 +158,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_merge_kernel(const XchgDev 
     }
     if (tid == 0) p.out_cnt[q] = n_out;
     // ---- the last CTA tells every peer that this rank has read the slot ----
-    unsigned *ticket = flag_words(p, p.rank) + 4 * p.world + 1;
+    unsigned *ticket = flag_words(p, p.rank) + 2 * XCHG_SLOTS * p.world + 1;
     __syncthreads();
     if (tid == 0) { __threadfence(); s_ticket = atomicAdd(ticket, 1u); }
     __syncthreads();
@@ -144,7 +166,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_merge_kernel(const XchgDev 
         if (tid == 0) *ticket = 0u;
         if (tid < p.world) {
             __threadfence_system();
-            st_release_sys(flag_words(p, tid) + 2 * p.world + p.slot * p.world + p.rank, p.seq);
+            st_release_sys(flag_words(p, tid) + XCHG_SLOTS * p.world + p.slot * p.world + p.rank, p.seq);
         }
     }
 }
@@ -175,13 +197,14 @@ struct b2r_xchg {
     char *box[XCHG_MAX_WORLD] = {};
     bool opened = false;
     unsigned seq_push = 0, seq_merge = 0;
+    bool fused[XCHG_SLOTS] = {};        // how the batch sitting in each slot was pushed
     int sm_count = 0;
     std::mutex mu;
 };
 
 static void fill(const b2r_xchg *x, XchgDev &p, int nq, int k, unsigned seq) {
     p.rank = x->rank; p.world = x->world; p.nq = nq; p.k = k;
-    p.seq = seq; p.slot = (int)(seq & 1u);
+    p.seq = seq; p.slot = (int)(seq % XCHG_SLOTS); p.spin = 0;
     p.nq_max = x->nq_max; p.k_max = x->k_max;
     p.entry_bytes = x->entry_bytes; p.slot_bytes = x->slot_bytes; p.flags_off = x->flags_off;
     for (int r = 0; r < XCHG_MAX_WORLD; ++r) p.box[r] = x->box[r];
@@ -209,8 +232,8 @@ extern "C" int b2r_xchg_create(int device, int rank, int world, int nq_max, int 
     x->device = device; x->rank = rank; x->world = world; x->nq_max = nq_max; x->k_max = k_max;
     x->entry_bytes = ((size_t)k_max * 16 + 4 + 15) / 16 * 16;
     x->slot_bytes = (size_t)world * nq_max * x->entry_bytes;
-    x->flags_off = 2 * x->slot_bytes;
-    x->total_bytes = x->flags_off + sizeof(unsigned) * ((size_t)4 * world + 4);
+    x->flags_off = XCHG_SLOTS * x->slot_bytes;
+    x->total_bytes = x->flags_off + sizeof(unsigned) * ((size_t)2 * XCHG_SLOTS * world + 4);
     cudaError_t e = cudaMalloc(&x->local, x->total_bytes);
     if (e != cudaSuccess) { delete x; B2R_CUDA(e); }
     e = cudaMemset(x->local, 0, x->total_bytes);
@@ -261,12 +284,13 @@ extern "C" int b2r_xchg_push(b2r_xchg_handle x, const int64_t *rows, const doubl
     cudaStream_t s = (cudaStream_t)stream;
     XchgDev p;
     fill(x, p, nq, k, ++x->seq_push);
+    x->fused[p.slot] = false;
     p.rows = (const long long *)rows; p.d64 = dist64; p.cnt = count;
     int rc;
-    if (p.seq > 2)      // the slot is free once every rank -- this one included: its merge may run on another stream -- has read
-                        // what the slot held two calls ago
+    if (p.seq > XCHG_SLOTS)   // the slot is free once every rank -- this one included: its merge may run on another stream -- has
+                              // read what the slot held XCHG_SLOTS calls ago
         for (int r = 0; r < x->world; ++r)
-            if ((rc = stream_wait(x, (size_t)2 * x->world + (size_t)p.slot * x->world + r, p.seq - 2, s)) != B2R_OK) return rc;
+            if ((rc = stream_wait(x, (size_t)XCHG_SLOTS * x->world + (size_t)p.slot * x->world + r, p.seq - XCHG_SLOTS, s)) != B2R_OK) return rc;
     const long long items = (long long)nq * (k + 1);
     const int grid = (int)std::max<long long>(1, std::min<long long>((items + XCHG_THREADS - 1) / XCHG_THREADS, 32));
     B2R_CUDA(launch_pdl(xchg_push_kernel, dim3(grid), dim3(XCHG_THREADS), 0, s, p));
@@ -279,18 +303,44 @@ extern "C" int b2r_xchg_merge(b2r_xchg_handle x, int nq, int k, int64_t *out_row
     XCHG_REQUIRE(nq >= 1 && nq <= x->nq_max && k >= 1 && k <= x->k_max, "b2r_xchg_merge: nq / k exceed what the exchange was created for");
     std::lock_guard<std::mutex> g(x->mu);
     XCHG_REQUIRE(x->seq_merge < x->seq_push, "b2r_xchg_merge: no pushed batch is waiting to be merged");
+    XCHG_REQUIRE(x->seq_push - x->seq_merge <= XCHG_SLOTS, "b2r_xchg_merge: more batches pushed than the mailbox has slots");
     B2R_CUDA(cudaSetDevice(x->device));
     cudaStream_t s = (cudaStream_t)stream;
     XchgDev p;
     fill(x, p, nq, k, ++x->seq_merge);
     p.out_rows = (long long *)out_rows; p.out_dist = out_dist; p.out_cnt = out_count;
     int rc;
-    for (int r = 0; r < x->world; ++r)      // own arrival word too: orders this merge after this rank's push when the streams differ
-        if ((rc = stream_wait(x, (size_t)p.slot * x->world + r, p.seq, s)) != B2R_OK) return rc;
+    p.spin = x->fused[p.slot] ? 1 : 0;
+    if (!p.spin)
+        for (int r = 0; r < x->world; ++r)      // own arrival word too: orders this merge after this rank's push when the streams differ
+            if ((rc = stream_wait(x, (size_t)p.slot * x->world + r, p.seq, s)) != B2R_OK) return rc;
     const size_t smem = (size_t)x->world * k * 16;
     if (smem > 48 * 1024) B2R_CUDA(cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    xchg_merge_kernel<<<nq, XCHG_THREADS, smem, s>>>(p);
-    B2R_CUDA(cudaGetLastError());
+    // (programmatic launch: the merge's CTAs are placed while the kernel before it on the stream drains)
+    B2R_CUDA(launch_pdl(xchg_merge_kernel, dim3(nq), dim3(XCHG_THREADS), smem, s, p));
+    return B2R_OK;
+}
+
+int b2r::xchg_begin_push(b2r_xchg *x, int device, int nq, int k, PushParams *out, const unsigned **wait_words, int *wait_n,
+                         unsigned *wait_val) {
+    XCHG_REQUIRE(x->opened, "b2r_query_push: the peers' mailboxes have not been opened (b2r_xchg_open)");
+    XCHG_REQUIRE(x->device == device, "b2r_query_push: the exchange lives on another device than the shard");
+    XCHG_REQUIRE(nq >= 1 && nq <= x->nq_max && k >= 1 && k <= x->k_max, "b2r_query_push: nq / k exceed what the exchange was created for");
+    std::lock_guard<std::mutex> g(x->mu);
+    XCHG_REQUIRE(x->seq_push - x->seq_merge < XCHG_SLOTS, "b2r_query_push: every mailbox slot holds a batch that has not been merged (b2r_xchg_merge)");
+    const unsigned seq = ++x->seq_push;
+    const int slot = (int)(seq % XCHG_SLOTS);
+    x->fused[slot] = true;
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) out->box[r] = x->box[r];
+    out->lists_off = (size_t)slot * x->slot_bytes + (size_t)x->rank * x->nq_max * x->entry_bytes;
+    out->arrive_off = x->flags_off + sizeof(unsigned) * ((size_t)slot * x->world + x->rank);
+    out->ticket_off = x->flags_off + sizeof(unsigned) * ((size_t)2 * XCHG_SLOTS * x->world + 2);
+    out->entry_bytes = (unsigned)x->entry_bytes; out->k_max = (unsigned)x->k_max;
+    out->seq = seq; out->world = x->world; out->rank = x->rank;
+    // before the slot is written again every rank must have merged what it held XCHG_SLOTS calls ago (ack words, local memory)
+    *wait_words = reinterpret_cast<const unsigned *>(x->local + x->flags_off) + (size_t)XCHG_SLOTS * x->world + (size_t)slot * x->world;
+    *wait_n = seq > (unsigned)XCHG_SLOTS ? x->world : 0;
+    *wait_val = seq - XCHG_SLOTS;
     return B2R_OK;
 }
 

@@ -214,6 +214,8 @@ class DeviceShard:
     local scan -> all_gather -> merge on the current stream without a host sync."""
 
     exchange_mode = "nccl all_gather_into_tensor + merge kernel, same stream"
+    _P2P_MODE = ("b2r_xchg_push / b2r_xchg_merge: peer-to-peer stores into the peers' mailboxes over NVLink, stream "
+                 "memory operations as the only waits, merge kernel; no NCCL on the data path")
 
     def __init__(self, dim, space="cosine", *, capacity=0, row_base=0, device=None, group=None,
                  keep_f32_master=True, world=None):
@@ -230,6 +232,7 @@ class DeviceShard:
         self._side = None           # stream of the pipelined exchange
         self._inflight = None
         self._xchg = None           # peer-to-peer exchange (enable_p2p_exchange)
+        self._fused_prev = None     # (nq, k, outputs) of the fused batch whose merge has not been enqueued yet
         _lib.check(self.lib.b2r_set_row_base(h, row_base))
 
     def close(self):
@@ -308,12 +311,17 @@ class DeviceShard:
         self._exchange(q.shape[0], k, o)
         return o["m_rows"], o["m_dist"], o["m_cnt"]
 
-    def enable_p2p_exchange(self, nq_max=1024, k_max=128):
+    def enable_p2p_exchange(self, nq_max=1024, k_max=128, default=True):
         """Replace the NCCL all_gather + merge launch by the library's own exchange kernel (b2r_xchg_*): every rank's
         lists go straight into the peers' mailboxes over NVLink and the same kernel merges.  Collective (every rank
         calls it); needs all ranks on one node with peer access.  torch.distributed is only used here, for the one-off
         hand-over of the IPC handles."""
-        if self.world == 1 or self._xchg is not None:
+        if self.world == 1:
+            return
+        if self._xchg is not None:
+            if default and not self._xchg_default:
+                self._xchg_default = True
+                self.exchange_mode = self._P2P_MODE
             return
         rank = dist.get_rank(self.group)
         x = ctypes.c_void_p()
@@ -326,11 +334,32 @@ class DeviceShard:
         dist.barrier(group=self.group)
         self._xchg = x
         self._xchg_limits = (nq_max, k_max)
-        self.exchange_mode = ("b2r_xchg_push / b2r_xchg_merge: peer-to-peer stores into the peers' mailboxes over NVLink, stream "
-                              "memory operations as the only waits, merge kernel; no NCCL on the data path")
+        self._xchg_default = default        # False: the mailboxes serve query_device_fused only, query_device keeps NCCL
+        if not default:
+            return
+        self.exchange_mode = self._P2P_MODE
 
-    def _uses_xchg(self, nq, k):
-        return self._xchg is not None and nq <= self._xchg_limits[0] and k <= self._xchg_limits[1]
+    def query_device_fused(self, q: torch.Tensor, k: int, o: dict):
+        """Replicated queries, the exchange fused into the query's own kernels (b2r_query_push): the finalize stores each
+        list into every rank's mailbox over NVLink as it emits it, and the merge of the PREVIOUS batch is enqueued behind this
+        batch's kernels -- by then its lists have arrived, so nothing waits and no collective or exchange kernel stands
+        between two scans.  Needs enable_p2p_exchange().  Results of this batch (o['m_rows'|'m_dist'|'m_cnt']) are in place
+        after the next call or after drain(); `o` must not be reused before then (alternate two output sets)."""
+        nq = q.shape[0]
+        if self.world == 1:
+            self.query_local(q, k, o)
+            return
+        if not self._uses_xchg(nq, k, fused=True):
+            raise ValueError("query_device_fused: enable_p2p_exchange(nq_max, k_max) must cover this batch")
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.b2r_query_push(self.h, self._xchg, q.data_ptr(), nq, k, None, o["rows"].data_ptr(),
+                                           o["dist"].data_ptr(), o["cnt"].data_ptr(), st), "b2r_query_push")
+        prev, self._fused_prev = self._fused_prev, (nq, k, o)
+        if prev is not None:
+            self._xchg_merge(*prev)
+
+    def _uses_xchg(self, nq, k, fused=False):
+        return self._xchg is not None and (fused or self._xchg_default) and nq <= self._xchg_limits[0] and k <= self._xchg_limits[1]
 
     def _xchg_push(self, nq, k, o):
         _lib.check(self.lib.b2r_xchg_push(self._xchg, o["rows"].data_ptr(), o["d64"].data_ptr(), o["cnt"].data_ptr(), nq, k,
@@ -395,6 +424,9 @@ class DeviceShard:
         self._inflight = o
 
     def drain(self):
+        if self._fused_prev is not None:           # the last fused batch has no successor to ride behind
+            prev, self._fused_prev = self._fused_prev, None
+            self._xchg_merge(*prev)
         if self._inflight is not None:
             torch.cuda.current_stream().wait_event(self._inflight["ev_done"])
             self._inflight = None

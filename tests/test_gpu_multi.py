@@ -73,6 +73,32 @@ def _worker(rank, world, port, n, d, nq, k, out):
         torch.cuda.synchronize()
         ok = ok and all(bool(torch.equal(o_["m_rows"], rows)) and bool(torch.equal(o_["m_dist"], dist_)) for o_ in os_)
         res["p2p_same"] = ok
+        # the fused form (b2r_query_push): the query's own kernels store the lists into the peers' mailboxes, the merge of a batch
+        # rides behind the next batch -- 9 batches in a row (every slot twice, the ack wait), k = 100 with forced exact fix-ups in
+        # between (the fix-up kernel pushes the redone queries), then the old push / merge form again on the same mailboxes
+        of = [sh.alloc_out(nq, k) for _ in range(2)]
+        ok = True
+        for i in range(9):
+            sh.query_device_fused(Qd, k, of[i % 2])
+            if i >= 1:
+                torch.cuda.synchronize()
+                o_ = of[(i - 1) % 2]
+                ok = ok and bool(torch.equal(o_["m_rows"], rows)) and bool(torch.equal(o_["m_dist"], dist_)) and bool(torch.equal(o_["m_cnt"], cnt))
+        sh.drain()
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(of[0]["m_rows"], rows)) and bool(torch.equal(of[0]["m_dist"], dist_))
+        o5 = sh.alloc_out(130, 100)
+        sh.lib.b2r_set_path(sh.h, 3)                       # exact scan for everything: K5 emits (and pushes) every list
+        sh.query_device_fused(Q2, 100, o5)
+        sh.lib.b2r_set_path(sh.h, 0)
+        sh.query_device_fused(Qd, k, of[1])
+        sh.drain()
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(o5["m_rows"], r2)) and bool(torch.equal(o5["m_dist"], d2)) and bool(torch.equal(of[1]["m_rows"], rows))
+        o6 = sh.alloc_out(nq, k)
+        r6, d6, c6 = sh.query_device(Qd, k, o6)           # push / merge kernels after fused batches
+        torch.cuda.synchronize()
+        res["fused_same"] = ok and bool(torch.equal(r6, rows)) and bool(torch.equal(d6, dist_))
         sh.close()
         # (2) the Chroma-shaped collective collection with ids and a where clause
         sc = ShardedCollection("mm", {"hnsw:space": "cosine"}, device=rank)
@@ -103,7 +129,7 @@ def test_two_gpu_row_sharded_matches_oracle(tmp_path):
     for i in range(nq):
         np.testing.assert_array_equal(res["rows"][i, : res["cnt"][i]], er[i])
         np.testing.assert_allclose(res["dist"][i, : res["cnt"][i]], ed[i], rtol=1e-5, atol=1e-7)
-    assert res["pipelined_same"] and res["p2p_same"]
+    assert res["pipelined_same"] and res["p2p_same"] and res["fused_same"]
     er3, ed3 = eo.topk_exact(eo.normalize_f32(make_unit(130, d, 8)), eo.normalize_f32(X), 100, "cosine")
     for i in range(130):
         np.testing.assert_array_equal(res["rows100"][i, : res["cnt100"][i]], er3[i])
@@ -113,3 +139,53 @@ def test_two_gpu_row_sharded_matches_oracle(tmp_path):
     for i in range(4):
         assert res["ids"][i] == [f"doc_{r:06d}_text_{r}" for r in er2[i]]
     assert res["count"] == n
+
+
+def test_fused_exchange_with_a_world_of_one():
+    """b2r_query_push on one GPU (a world of one rank: the mailbox is local): the pushed lists, merged, are the query's own
+    answer -- through K3's finalize, through the batch-1 path, through forced exact fix-ups, 10 batches (every slot, the acks)."""
+    import ctypes
+    import torch
+    from multimodal_rag_b200 import _lib
+    from multimodal_rag_b200.sharded import DeviceShard
+    lib = _lib.load()
+    n, d = 50_000, 128
+    sh = DeviceShard(d, "cosine", capacity=n, row_base=1000, device=0, world=1)
+    sh.ingest(torch.from_numpy(make_unit(n, d, 21)).cuda())
+    x = ctypes.c_void_p()
+    _lib.check(lib.b2r_xchg_create(0, 0, 1, 64, 32, ctypes.byref(x)))
+    st = torch.cuda.current_stream().cuda_stream
+    pending = []
+    for i in range(10):
+        nq, k = (1, 5) if i % 3 == 0 else (40, 10) if i % 3 == 1 else (64, 32)
+        Q = torch.from_numpy(make_unit(nq, d, 30 + i)).cuda()
+        o = sh.alloc_out(nq, k)
+        sh.query_local(Q, k, o)                                   # the plain answer
+        want = (o["rows"].clone(), o["dist"].clone(), o["cnt"].clone())
+        o2 = sh.alloc_out(nq, k)
+        if i == 4:
+            lib.b2r_set_path(sh.h, 3)
+        _lib.check(lib.b2r_query_push(sh.h, x, Q.data_ptr(), nq, k, None, o2["rows"].data_ptr(), o2["dist"].data_ptr(),
+                                      o2["cnt"].data_ptr(), st), "b2r_query_push")
+        lib.b2r_set_path(sh.h, 0)
+        pending.append((nq, k, o2, want))
+        if len(pending) == 3:                                     # up to three batches pushed and not merged
+            for nq_, k_, o_, want_ in pending[:2]:
+                _lib.check(lib.b2r_xchg_merge(x, nq_, k_, o_["m_rows"].data_ptr(), o_["m_dist"].data_ptr(), o_["m_cnt"].data_ptr(), st))
+                torch.cuda.synchronize()
+                assert torch.equal(o_["m_rows"], want_[0]) and torch.equal(o_["m_dist"], want_[1]) and torch.equal(o_["m_cnt"], want_[2])
+                assert torch.equal(o_["rows"], want_[0])           # the local outputs are written as before
+            pending = pending[2:]
+    for nq_, k_, o_, want_ in pending:
+        _lib.check(lib.b2r_xchg_merge(x, nq_, k_, o_["m_rows"].data_ptr(), o_["m_dist"].data_ptr(), o_["m_cnt"].data_ptr(), st))
+        torch.cuda.synchronize()
+        assert torch.equal(o_["m_rows"], want_[0]) and torch.equal(o_["m_dist"], want_[1])
+    # a fourth unmerged batch is refused, not deadlocked
+    Q = torch.from_numpy(make_unit(8, d, 99)).cuda()
+    outs = [sh.alloc_out(8, 5) for _ in range(5)]
+    rcs = [lib.b2r_query_push(sh.h, x, Q.data_ptr(), 8, 5, None, o_["rows"].data_ptr(), o_["dist"].data_ptr(), o_["cnt"].data_ptr(), st)
+           for o_ in outs]
+    assert rcs == [0, 0, 0, 0, _lib.B2R_EINVAL] or rcs[:3] == [0, 0, 0] and rcs[3] == _lib.B2R_EINVAL
+    torch.cuda.synchronize()
+    lib.b2r_xchg_destroy(x)
+    sh.close()
