@@ -589,7 +589,7 @@ def run_gpu(args):
         fused_ok = bool(int(t_ok.item()))
 
         def step_sharded_fused(i):
-            # the finalize of batch i stores its lists into every rank's mailbox; the merge of batch i rides behind the kernels
+            # the finalize of batch i stores its lists into every rank's mailbox; the merge of batch i rides in the last kernel
             # of batch i+1; the last step of a region merges what is still pending
             sh2.query_device_fused(Q2[i % n_batches], k, o2b[i % 2])
             if i == K - 1:
@@ -685,8 +685,8 @@ def run_gpu(args):
                               "bytes_sent_per_rank_per_step": bytes_per_rank, "bytes_gathered_per_rank_per_step": world * bytes_per_rank,
                               "nvlink_bytes_stored_per_rank_per_step": (world - 1) * nq * (k * 16 + 4) if form == "fused" else None,
                               "exchange": ("fused into the query's kernels (b2r_query_push): the finalize / fix-up kernels store every final list into the "
-                                           "peers' mailboxes over NVLink (CUDA IPC), the call's last kernel publishes the arrival, the merge of batch i is "
-                                           "one small launch behind the kernels of batch i+1; no collective and no exchange kernel between two scans "
+                                           "peers' mailboxes over NVLink (CUDA IPC), the merge of batch i rides in the last kernel of batch i+1 and the flag words are "
+                                           "written by the next call's first kernel; no collective, no exchange kernel and no extra launch between two scans "
                                            "(DeviceShard.query_device_fused)") if form == "fused" else
                                           sh2.exchange_mode + ("; issued on a side stream behind an event so that it overlaps the scan of the next batch "
                                                                "(DeviceShard.query_device_pipelined)" if use_pipelined else "; on the scan's stream (DeviceShard.query_device)"),

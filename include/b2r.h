@@ -223,11 +223,15 @@ int b2r_xchg_destroy(b2r_xchg_handle x);
  * `x` as they emit it -- the finalize of the scoring kernels, the exact fix-up -- and whose last kernel publishes the arrival on
  * its way out.  No exchange kernel, no collective, no stream memory operation is enqueued; the call's first kernel holds the stream
  * until the mailbox slot's previous contents (four slots, round-robin) have been merged by every rank.  The batch is merged by
- * b2r_xchg_merge like a pushed one, except that the merge kernel itself checks the arrival words: enqueue the merge of batch i
- * AFTER b2r_query_push of batch i+1 and the exchange costs one small launch per batch (at most four batches may be pushed and
- * not yet merged).  Collective like push / merge: same sequence of calls, same nq and k on every rank.                          */
+ * b2r_xchg_merge like a pushed one, except that the merge kernel itself checks the arrival words.  Better: hand the NEXT
+ * b2r_query_push the merge outputs (merge_rows / merge_dist / merge_count, device; NULL = none) -- the oldest batch pushed before
+ * this call and not merged yet is then merged INSIDE this call's last kernel (its lists arrived a whole scan ago), so a step of
+ * a query stream carries its exchange without a single extra launch; b2r_xchg_merge is only needed for the last batch of the
+ * stream.  At most four batches may be pushed and not yet merged.  Collective like push / merge: the same sequence of calls,
+ * the same nq and k on every rank.                                                                                            */
 int b2r_query_push(b2r_handle h, b2r_xchg_handle x, const float *q, int nq, int k, const b2r_filter *filter,
-                   int64_t *out_rows, float *out_dist, int32_t *out_count, void *stream);
+                   int64_t *out_rows, float *out_dist, int32_t *out_count, int64_t *merge_rows, float *merge_dist,
+                   int32_t *merge_count, void *stream);
 
 /* Host-side id table of a collection: string id <-> dense row number.  It stands where Chroma keeps its id index in sqlite
  * (`embeddings.embedding_id`, consulted by collection.add / upsert / get(ids) / delete(ids): app/utils/embedder.py:518, 632,

@@ -102,7 +102,7 @@ def load() -> ctypes.CDLL:
         "b2r_xchg_push": (i32, [vp, vp, vp, vp, i32, i32, vp]),
         "b2r_xchg_merge": (i32, [vp, i32, i32, vp, vp, vp, vp]),
         "b2r_xchg_destroy": (i32, [vp]),
-        "b2r_query_push": (i32, [vp, vp, vp, i32, i32, ctypes.POINTER(B2RFilter), vp, vp, vp, vp]),
+        "b2r_query_push": (i32, [vp, vp, vp, i32, i32, ctypes.POINTER(B2RFilter), vp, vp, vp, vp, vp, vp, vp]),
         "b2r_idtab_create": (i32, [i64, ctypes.POINTER(vp)]),
         "b2r_idtab_destroy": (i32, [vp]),
         "b2r_idtab_clear": (i32, [vp]),

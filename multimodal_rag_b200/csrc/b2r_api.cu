@@ -348,6 +348,7 @@ extern "C" int b2r_ingest_f32(b2r_handle h, const float *x, int64_t n, const uin
     p.max_norm2 = h->max_norm2; p.qerr = nullptr; p.q_eps = nullptr; p.norms = nullptr; p.eps_rel = 0.f;
     for (int z = 0; z < 3; ++z) { p.zero[z] = nullptr; p.zero_words[z] = 0; }
     p.wait_words = nullptr; p.wait_n = 0; p.wait_val = 0;
+    std::memset(&p.flags, 0, sizeof p.flags);
     const int wpb = INGEST_THREADS / 32;
     const ingest_fn fn = ingest_lookup(h->dim, h->dp, xd);
     // one full wave of resident CTAs, every warp walks its share of the rows (no tail wave)
@@ -771,7 +772,8 @@ int launch_scan_batch(b2r_index *h, int nq, int epl, const ScanParams &base, cud
 constexpr size_t EXACT_LISTS_BUDGET = 64u << 20;      // per-CTA list scratch per handle
 
 int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const FinalizeParams &fin,
-                       const b2r_filter &f, const uint32_t *allow_dev, cudaStream_t s) {
+                       const b2r_filter &f, const uint32_t *allow_dev, cudaStream_t s, const XchgDev *rider = nullptr,
+                       size_t rider_smem = 0) {
     const int epl = epl_exact(k);
     const int G = exact_group(epl, h->dp);
     int max_grid = exact_max_grid(epl, h->dp, h->sm_count);
@@ -794,9 +796,11 @@ int launch_exact_batch(b2r_index *h, int nq, int k, int force_all, const Finaliz
     p.fin = fin;
     for (int first = 0; first < nq; first += items) {
         p.first_item = first;
-        p.publish = (fin.push.world && first + items >= nq) ? 1 : 0;     // the call's very last launch
+        const bool last = first + items >= nq;                            // the call's very last launch
+        p.rider.nq = 0;
+        if (rider && last) p.rider = *rider;
         KernelTimer kt(h, s, force_all ? 0 : 5);   // the certificate fix-up is not the scoring kernel
-        B2R_CUDA(exact_launch(epl, p, grid, s));
+        B2R_CUDA(exact_launch(epl, p, grid, s, (rider && last) ? rider_smem : 0));
         kt.stop();
         h->n_launches++;
     }
@@ -933,7 +937,8 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
 // the query itself; the caller holds h->mu
 static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,
                         int64_t *out_rows, float *out_dist, double *out_dist64, int32_t *out_count,
-                        void *stream, b2r_xchg *push_to = nullptr) {
+                        void *stream, b2r_xchg *push_to = nullptr, int64_t *merge_rows = nullptr, float *merge_dist = nullptr,
+                        int32_t *merge_count = nullptr) {
     B2R_REQUIRE(nq >= 1 && q, "b2r_query: need at least one query");
     B2R_REQUIRE(k >= 1, "b2r_query: n_results must be a positive integer");
     B2R_REQUIRE(out_rows && out_dist && out_count, "b2r_query: NULL output");
@@ -1009,7 +1014,7 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
     if (h->rows == 0) path = 3;   // empty collection: Chroma returns empty lists; only the padding is written
 
     // ---- prepare queries (cosine: hnswlib normalisation; zero-pad to dp; bf16 copy for K3) ----
-    PushParams push;
+    FusedCall fc;
     if (path == 2 && (rc = ensure(h->q_bf16, (size_t)nq * h->dp * 2)) != B2R_OK) return rc;
     if (path == 2 && (rc = ensure(h->q_err, (size_t)nq * 4)) != B2R_OK) return rc;
     {
@@ -1025,10 +1030,18 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
         p.eps_rel = (float)(h->dp + 8) * 5.9604645e-8f * (path == 2 ? 4.f : 1.f) * 1.01f;
         // per-call shared state, cleared by the preparation: the fix-up work list control, ...
         p.wait_words = nullptr; p.wait_n = 0; p.wait_val = 0;
-        std::memset(&push, 0, sizeof push);
-        // fused exchange: take the next mailbox slot now (nothing after this point fails before the kernels are enqueued
-        // short of a CUDA error, which breaks the collective anyway)
-        if (push_to && (rc = xchg_begin_push(push_to, h->device, nq, k, &push, &p.wait_words, &p.wait_n, &p.wait_val)) != B2R_OK) return rc;
+        std::memset(&p.flags, 0, sizeof p.flags);
+        std::memset(&fc, 0, sizeof fc);
+        // fused exchange: take the next mailbox slot (and the rider) now -- nothing after this point fails before the kernels are
+        // enqueued short of a CUDA error, which breaks the collective anyway
+        if (push_to) {
+            B2R_REQUIRE(!merge_rows || (merge_dist && merge_count && is_device_ptr(merge_rows) && is_device_ptr(merge_dist) &&
+                                        is_device_ptr(merge_count)), "b2r_query_push: the merge outputs must be device pointers");
+            if ((rc = xchg_begin_fused(push_to, h->device, nq, k, &fc, merge_rows, merge_dist, merge_count,
+                                       exact_smem_limit(epl_exact(k), h->dp))) != B2R_OK) return rc;
+            p.wait_words = fc.wait_words; p.wait_n = fc.wait_n; p.wait_val = fc.wait_val;
+            p.flags = fc.flags;
+        }
         p.zero[0] = (unsigned *)h->need_ctl; p.zero_words[0] = 2;
         p.zero[1] = nullptr; p.zero_words[1] = 0;
         p.zero[2] = nullptr; p.zero_words[2] = 0;
@@ -1052,7 +1065,11 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
     fin.row_base = h->row_base; fin.out_rows = o_rows; fin.out_dist = o_dist; fin.out_dist64 = o_dist64;
     fin.out_count = o_count; fin.need_ctl = h->need_ctl; fin.need_list = (int *)h->need_list.p;
     fin.q_eps = (const double *)h->q_eps.p;
-    fin.push = push;
+    fin.push = fc.push;
+    // fused exchange: the merge of an earlier batch rides in this call's last kernel (the exact scan)
+    const XchgDev *rider_p = (push_to && fc.rider.nq && !fc.merge_after) ? &fc.rider : nullptr;
+    const size_t rider_smem = fc.rider_smem;
+    const bool merge_after = push_to && fc.merge_after;
 
     if (path == 1) {
         ScanParams sp;
@@ -1060,15 +1077,16 @@ static int query_locked(b2r_handle h, const float *q, int nq, int k, const b2r_f
         sp.type_mask = f.type_mask; sp.n = (unsigned)h->rows; sp.q0 = 0; sp.cta_lists = nullptr;
         sp.ticket = h->tickets; sp.fin = fin;
         if ((rc = launch_scan_batch(h, nq, epl_s, sp, s)) != B2R_OK) return rc;
-        if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
+        if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s, rider_p, rider_smem)) != B2R_OK) return rc;
     } else if (path == 2) {
         // candidates kept by the finalize: KP = 32 / 64 / 128 / 128 / 256 for k <= 8 / 16 / 32 / 64 / 128 (>= 2k beyond 8)
         if ((rc = launch_gemm_batch(h, nq, k, k <= 8 ? 1 : k <= 16 ? 2 : k <= 64 ? 4 : 8, fin, f, allow_dev, filter_key, s)) != B2R_OK) return rc;
-        if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s)) != B2R_OK) return rc;
+        if ((rc = launch_exact_batch(h, nq, k, 0, fin, f, allow_dev, s, rider_p, rider_smem)) != B2R_OK) return rc;
     } else {
-        if ((rc = launch_exact_batch(h, nq, k, 1, fin, f, allow_dev, s)) != B2R_OK) return rc;
+        if ((rc = launch_exact_batch(h, nq, k, 1, fin, f, allow_dev, s, rider_p, rider_smem)) != B2R_OK) return rc;
     }
     h->n_queries += nq;
+    if (merge_after && (rc = xchg_launch_merge(push_to, fc.rider, s)) != B2R_OK) return rc;
 
     if (!dev_out) {
         B2R_CUDA(cudaMemcpyAsync(h->o_host, h->o_pack.p, pack_bytes, cudaMemcpyDeviceToHost, s));
@@ -1093,10 +1111,11 @@ extern "C" int b2r_query_ex(b2r_handle h, const float *q, int nq, int k, const b
 }
 
 extern "C" int b2r_query_push(b2r_handle h, b2r_xchg_handle x, const float *q, int nq, int k, const b2r_filter *filter,
-                              int64_t *out_rows, float *out_dist, int32_t *out_count, void *stream) {
+                              int64_t *out_rows, float *out_dist, int32_t *out_count, int64_t *merge_rows, float *merge_dist,
+                              int32_t *merge_count, void *stream) {
     B2R_REQUIRE(h && x, "b2r_query_push: NULL handle");
     std::lock_guard<std::mutex> g(h->mu);
-    return query_locked(h, q, nq, k, filter, out_rows, out_dist, nullptr, out_count, stream, x);
+    return query_locked(h, q, nq, k, filter, out_rows, out_dist, nullptr, out_count, stream, x, merge_rows, merge_dist, merge_count);
 }
 
 extern "C" int b2r_query(b2r_handle h, const float *q, int nq, int k, const b2r_filter *filter,

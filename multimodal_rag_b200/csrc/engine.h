@@ -52,7 +52,8 @@ int scan_tile_rows(int dp);
 
 int exact_max_grid(int epl, int dp, int sm_count);
 int exact_group(int epl, int dp);   // queries K5 scores per corpus pass
-cudaError_t exact_launch(int epl, const ExactParams &p, int grid, cudaStream_t s);
+cudaError_t exact_launch(int epl, const ExactParams &p, int grid, cudaStream_t s, size_t rider_smem = 0);
+size_t exact_smem_limit(int epl, int dp);      // dynamic shared memory an exact-scan launch may ask for
 
 // K3 (gemm_kernels.cu): tcgen05 batched scoring
 struct GemmParams;
@@ -70,7 +71,17 @@ cudaError_t finalize_union_launch(int epl, const FinalizeParams &fin, const Unio
 
 // xchg.cu: reserves the next mailbox slot of `x` for a fused push of nq x k lists and fills what the kernels need; the acks the
 // first kernel must see before anything is stored are returned as (words, count, value)
-int xchg_begin_push(b2r_xchg *x, int device, int nq, int k, PushParams *out, const unsigned **wait_words, int *wait_n, unsigned *wait_val);
+struct FusedCall {
+    PushParams push;               // where this call's kernels store their lists
+    XchgFlags flags;               // flag words the previous fused call left for this call's first kernel
+    XchgDev rider;                 // the earlier batch merged inside this call's last kernel (nq = 0: none) ...
+    size_t rider_smem;
+    bool merge_after;              // ... or, when its lists do not fit there, by the stand-alone merge kernel behind the call
+    const unsigned *wait_words; int wait_n; unsigned wait_val;     // acks the first kernel must see before anything is stored
+};
+int xchg_begin_fused(b2r_xchg *x, int device, int nq, int k, FusedCall *c, int64_t *merge_rows, float *merge_dist,
+                     int32_t *merge_count, size_t rider_smem_limit);
+int xchg_launch_merge(b2r_xchg *x, XchgDev job, cudaStream_t s);
 
 struct DevBuf {
     void *p = nullptr;

@@ -13,6 +13,7 @@
 #pragma once
 #include "common.cuh"
 #include "finalize.cuh"
+#include "xchg.cuh"
 
 namespace b2r {
 
@@ -32,7 +33,8 @@ struct ExactParams {
     KeyD *cta_lists;              // [slots][G][gridDim.x][KP]
     unsigned *tickets;            // [EXACT_MAX_SLOTS] arrival tickets (0 between launches: the last CTA of a group resets its own)
     long long *n_fallbacks;       // device counter (may be nullptr)
-    int publish;                  // b2r_query_push, last launch of the call: the last CTA to leave publishes the arrival words
+    XchgDev rider;                // b2r_query_push, last launch of the call: the grid merges the batch pushed BEFORE this one on its way
+                                  // out (rider.nq = 0: none)
     FinalizeParams fin;
 };
 
@@ -180,7 +182,18 @@ __global__ void __launch_bounds__(EXACT_THREADS) exact_topk_kernel(const ExactPa
             }
         }
     }
-    if (p.publish) push_publish(p.fin.push);
+    // Rider: the cross-shard merge of the previous fused batch.  Its lists arrived a whole scan ago and this kernel is on the
+    // stream anyway (as the -- normally empty -- certificate fix-up): the exchange adds no launch to a step.  Neither this
+    // call's arrival nor the rider's "slot has been read" is published from here: the next kernel on the stream does both
+    // (XchgFlags), after this grid has completed, so no fence or exit ticket is needed.
+    if (p.rider.nq) {
+        __shared__ int s_valid;
+        xchg_wait_arrivals(p.rider);
+        for (int q = blockIdx.x; q < p.rider.nq; q += gridDim.x) {
+            __syncthreads();
+            xchg_merge_query(p.rider, q, smem_raw, &s_valid);
+        }
+    }
 }
 
 inline size_t exact_smem_bytes(int EPL, int G, int dp) {

@@ -1,4 +1,5 @@
 // Instantiations + launch table for K5 (exact.cuh).
+#include <algorithm>
 #include <map>
 #include <tuple>
 
@@ -59,11 +60,17 @@ int exact_max_grid(int epl, int dp, int sm_count) {
     return per_sm * sm_count;
 }
 
-cudaError_t exact_launch(int epl, const ExactParams &p, int grid, cudaStream_t s) {
+cudaError_t exact_launch(int epl, const ExactParams &p, int grid, cudaStream_t s, size_t rider_smem) {
     const int grp = exact_group(epl, p.fin.dp);
     exact_fn f = lookup(epl, grp);
     if (!f) return cudaErrorInvalidValue;
-    return launch_pdl(f, dim3(grid), dim3(EXACT_THREADS), exact_smem_bytes(epl, grp, p.fin.dp), s, p);
+    return launch_pdl(f, dim3(grid), dim3(EXACT_THREADS), std::max(exact_smem_bytes(epl, grp, p.fin.dp), rider_smem), s, p);
+}
+
+// what exact_max_grid raised the function attribute to
+size_t exact_smem_limit(int epl, int dp) {
+    const int grp = exact_group(epl, dp);
+    return grp > 1 ? exact_smem_bytes(epl, grp, 65536 / 8 / grp) : exact_smem_bytes(epl, 1, 8192);
 }
 
 }  // namespace b2r

@@ -29,11 +29,9 @@ struct FinCta {
 struct PushParams {
     char *box[8];                       // every rank's mailbox as mapped here (box[rank] = the local one)
     unsigned long long lists_off;       // this call's slot, this rank's block of lists: slot * slot_bytes + rank * nq_max * entry_bytes
-    unsigned long long arrive_off;      // the word (slot, this rank) of the arrival block -- written in EVERY mailbox once the call is complete
-    unsigned long long ticket_off;      // local exit ticket of the call's last kernel
     unsigned entry_bytes, k_max;        // one query's entry: rows[k_max] i64 | dist[k_max] f64 | count i32 (+pad)
-    unsigned seq;                       // this call's sequence number
-    int world, rank;                    // world = 0: no push
+    int world;                          // 0 = no push.  (The arrival words are written by the NEXT kernel on the stream -- xchg.cuh,
+                                        // XchgFlags -- once the grids that pushed have completed: no fence, no exit ticket here.)
 };
 
 struct FinalizeParams {
@@ -53,9 +51,7 @@ struct FinalizeParams {
     PushParams push;            // world = 0 unless the call is b2r_query_push
 };
 
-__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+
 
 // exact distance between prepared query and stored row, fp64 accumulation, whole warp
 __device__ __forceinline__ double exact_distance_warp(const FinalizeParams &p, const float *qv,
@@ -185,26 +181,6 @@ __device__ __forceinline__ void emit_sorted(const FinalizeParams &p, int qi, con
     if (tid == 0) p.out_count[qi] = cnt;
     if (p.push.world && tid < p.push.world)
         *reinterpret_cast<int *>(p.push.box[tid] + p.push.lists_off + (size_t)qi * p.push.entry_bytes + (size_t)p.push.k_max * 16) = cnt;
-}
-
-// Last kernel of a b2r_query_push call, every CTA on its way out: the last one to leave tells every rank that this rank's
-// lists of call `seq` are in place.  The lists were stored by CTAs of this grid (each fences at system scope before it
-// takes its ticket) or by grids that completed before this one started.
-__device__ __forceinline__ void push_publish(const PushParams &push) {
-    if (!push.world) return;
-    __shared__ unsigned s_exit;
-    __threadfence_system();
-    __syncthreads();
-    unsigned *ticket = reinterpret_cast<unsigned *>(push.box[push.rank] + push.ticket_off);
-    if (threadIdx.x == 0) s_exit = atomicAdd(ticket, 1u);
-    __syncthreads();
-    if (s_exit == gridDim.x - 1) {
-        if (threadIdx.x == 0) *ticket = 0u;              // ready for the next call on this stream
-        if ((int)threadIdx.x < push.world) {
-            __threadfence_system();
-            st_release_sys_u32(reinterpret_cast<unsigned *>(push.box[threadIdx.x] + push.arrive_off), push.seq);
-        }
-    }
 }
 
 // Stages shared by every scoring path once the candidate set is known (sm_keys: nvalid candidates,

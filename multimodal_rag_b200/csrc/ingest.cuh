@@ -4,6 +4,7 @@
 // certificate's error bound.  Also prepares query batches (same normalisation, no pack).
 #pragma once
 #include "common.cuh"
+#include "xchg.cuh"
 
 namespace b2r {
 
@@ -29,6 +30,7 @@ struct IngestParams {
     const unsigned *wait_words;    // b2r_query_push: the first kernel of the call holds the stream until every rank has read what
     int wait_n;                    // the mailbox slot held before (wait_words[0 .. wait_n) >= wait_val, written by the peers);
     unsigned wait_val;             // wait_n = 0 otherwise.  Normally true long before: the slot was used four calls ago.
+    XchgFlags flags;               // ... and writes the flag words the previous fused call left behind (world = 0: none)
 };
 
 // 1/(sqrt(s)+1e-30) exactly as hnswlib's normalize_vector does it in fp32
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(INGEST_THREADS) ingest_kernel(const IngestPara
     const int d = p.d, dp = p.dp, chunks = dp / 8;
     pdl_wait();          // query preparation overwrites buffers the previous query's kernels may still read
     pdl_trigger();
+    if (p.flags.world && blockIdx.x == gridDim.x - 1) xchg_publish_flags(p.flags, 32);
     if (p.wait_n && blockIdx.x == 0 && (int)threadIdx.x < p.wait_n) {
         unsigned v;
         const unsigned long long t0 = globaltimer_ns();

@@ -29,6 +29,7 @@
 #include <new>
 
 #include "engine.h"
+#include "xchg.cuh"
 
 using namespace b2r;
 
@@ -38,28 +39,6 @@ using namespace b2r;
     } while (0)
 
 namespace {
-
-constexpr int XCHG_MAX_WORLD = 8;
-constexpr int XCHG_THREADS = 256;
-constexpr int XCHG_SLOTS = 4;          // mailbox slots, used round-robin by sequence number
-
-struct XchgDev {
-    int rank, world, nq, k, slot;
-    int spin;                      // merge: wait for the arrival words inside the kernel (fused pushes) instead of on the stream
-    unsigned seq;
-    int nq_max, k_max;
-    size_t entry_bytes;            // one query's list in a mailbox: rows[k_max] i64 | dist[k_max] f64 | count i32 (+pad)
-    size_t slot_bytes;             // world * nq_max * entry_bytes
-    size_t flags_off;              // arrival words [SLOTS][world] u32, ack words [SLOTS][world] u32, three exit tickets
-    char *box[XCHG_MAX_WORLD];     // every rank's mailbox as mapped in this process (box[rank] = the local allocation)
-    const long long *rows; const double *d64; const int *cnt;      // push: this rank's local results
-    long long *out_rows; float *out_dist; int *out_cnt;            // merge: outputs
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned *flag_words(const XchgDev &p, int r) { return reinterpret_cast<unsigned *>(p.box[r] + p.flags_off); }
 
 // this rank's lists -> every mailbox (its own included), then the arrival word of (slot, this rank) on every rank
 __global__ void __launch_bounds__(XCHG_THREADS) xchg_push_kernel(const XchgDev p) {
@@ -86,7 +65,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_push_kernel(const XchgDev p
     }
     // the last CTA publishes: every store of this grid is ordered before its release (threadfence + ticket), and the release is
     // at system scope because the peers' streams read the word
-    unsigned *ticket = flag_words(p, p.rank) + 2 * XCHG_SLOTS * p.world;
+    unsigned *ticket = flag_words(p, p.rank) + 2 * XCHG_SLOTS * p.world + XCHG_TICKET_PUSH;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
@@ -100,75 +79,23 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_push_kernel(const XchgDev p
     }
 }
 
-// one CTA per query: rank every gathered candidate by counting (world * k <= 8192)
+// one CTA per query
 __global__ void __launch_bounds__(XCHG_THREADS) xchg_merge_kernel(const XchgDev p) {
     extern __shared__ __align__(16) unsigned char sm[];
-    const int total = p.world * p.k;
-    double *sd = reinterpret_cast<double *>(sm);
-    long long *sr = reinterpret_cast<long long *>(sd + total);
     __shared__ int s_valid;
     __shared__ unsigned s_ticket;
-    const int tid = threadIdx.x, q = blockIdx.x;
-    if (tid == 0) s_valid = 0;
     pdl_wait();
     pdl_trigger();
-    if (p.spin && tid < p.world) {      // fused pushes: the lists of every rank (this one included) must have arrived
-        const unsigned *w = flag_words(p, p.rank) + p.slot * p.world + tid;
-        const unsigned long long t0 = globaltimer_ns();
-        unsigned v;
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
-            if ((int)(v - p.seq) >= 0) break;
-            if (globaltimer_ns() - t0 > 4000000000ull) __trap();      // a peer that never pushed: fail, do not hang
-            __nanosleep(100);
-        }
-    }
-    __syncthreads();
-    const char *mine = p.box[p.rank] + (size_t)p.slot * p.slot_bytes;
-    int my_valid = 0;
-    for (int c = tid; c < total; c += XCHG_THREADS) {      // written by the peers: L2 loads
-        const int sh = c / p.k, i = c % p.k;
-        const char *e = mine + ((size_t)sh * p.nq_max + q) * p.entry_bytes;
-        const bool ok = i < __ldcg(reinterpret_cast<const int *>(e + (size_t)p.k_max * 16));
-        sd[c] = ok ? __ldcg(reinterpret_cast<const double *>(e + (size_t)p.k_max * 8) + i) : __longlong_as_double(0x7ff0000000000000ll);
-        sr[c] = ok ? __ldcg(reinterpret_cast<const long long *>(e) + i) : -1;
-        my_valid += ok ? 1 : 0;
-    }
-    if (my_valid) atomicAdd(&s_valid, my_valid);
-    __syncthreads();
-    const int n_out = min(s_valid, p.k);
-    for (int c = tid; c < total; c += XCHG_THREADS) {
-        const long long r = sr[c];
-        if (r < 0) continue;
-        const double d = sd[c];
-        int rank = 0;
-        for (int j = 0; j < total; ++j) {
-            const long long rj = sr[j];
-            const double dj = sd[j];
-            rank += (rj >= 0 && (dj < d || (dj == d && rj < r))) ? 1 : 0;
-        }
-        if (rank < p.k) {
-            p.out_rows[(size_t)q * p.k + rank] = r;
-            p.out_dist[(size_t)q * p.k + rank] = (float)d;
-        }
-    }
-    for (int t = n_out + tid; t < p.k; t += XCHG_THREADS) {
-        p.out_rows[(size_t)q * p.k + t] = -1;
-        p.out_dist[(size_t)q * p.k + t] = __int_as_float(0x7f800000);
-    }
-    if (tid == 0) p.out_cnt[q] = n_out;
-    // ---- the last CTA tells every peer that this rank has read the slot ----
-    unsigned *ticket = flag_words(p, p.rank) + 2 * XCHG_SLOTS * p.world + 1;
-    __syncthreads();
-    if (tid == 0) { __threadfence(); s_ticket = atomicAdd(ticket, 1u); }
-    __syncthreads();
-    if (s_ticket == gridDim.x - 1) {
-        if (tid == 0) *ticket = 0u;
-        if (tid < p.world) {
-            __threadfence_system();
-            st_release_sys(flag_words(p, tid) + XCHG_SLOTS * p.world + p.slot * p.world + p.rank, p.seq);
-        }
-    }
+    if (p.spin) xchg_wait_arrivals(p);      // fused pushes; otherwise the stream itself has waited (cuStreamWaitValue32)
+    xchg_merge_query(p, blockIdx.x, sm, &s_valid);
+    xchg_publish_ack(p, &s_ticket);
+}
+
+// the flag words a fused call left behind, when the next call on the stream is not another fused call
+__global__ void xchg_flush_kernel(const XchgFlags f) {
+    pdl_wait();
+    pdl_trigger();
+    xchg_publish_flags(f, 0);
 }
 
 typedef CUresult (*wait32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
@@ -198,17 +125,27 @@ struct b2r_xchg {
     bool opened = false;
     unsigned seq_push = 0, seq_merge = 0;
     bool fused[XCHG_SLOTS] = {};        // how the batch sitting in each slot was pushed
+    int nq_of[XCHG_SLOTS] = {}, k_of[XCHG_SLOTS] = {};   // ... and its shape
+    XchgFlags pending = {};             // flag words the last fused call left for the next kernel on its stream
     int sm_count = 0;
     std::mutex mu;
 };
 
 static void fill(const b2r_xchg *x, XchgDev &p, int nq, int k, unsigned seq) {
     p.rank = x->rank; p.world = x->world; p.nq = nq; p.k = k;
-    p.seq = seq; p.slot = (int)(seq % XCHG_SLOTS); p.spin = 0;
+    p.seq = seq; p.slot = (int)(seq % XCHG_SLOTS); p.spin = 0; p.ticket = XCHG_TICKET_MERGE;
     p.nq_max = x->nq_max; p.k_max = x->k_max;
     p.entry_bytes = x->entry_bytes; p.slot_bytes = x->slot_bytes; p.flags_off = x->flags_off;
     for (int r = 0; r < XCHG_MAX_WORLD; ++r) p.box[r] = x->box[r];
     p.rows = nullptr; p.d64 = nullptr; p.cnt = nullptr; p.out_rows = nullptr; p.out_dist = nullptr; p.out_cnt = nullptr;
+}
+
+// caller holds x->mu
+static int flush_pending(b2r_xchg *x, cudaStream_t s) {
+    if (!x->pending.arrive_seq && !x->pending.ack_seq) return B2R_OK;
+    B2R_CUDA(launch_pdl(xchg_flush_kernel, dim3(1), dim3(32), 0, s, x->pending));
+    x->pending.arrive_seq = 0; x->pending.ack_seq = 0;
+    return B2R_OK;
 }
 
 // make `stream` wait until word `index` of this rank's flag block has reached `value` (wrap-safe >=)
@@ -282,11 +219,12 @@ extern "C" int b2r_xchg_push(b2r_xchg_handle x, const int64_t *rows, const doubl
     std::lock_guard<std::mutex> g(x->mu);
     B2R_CUDA(cudaSetDevice(x->device));
     cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = flush_pending(x, s)) != B2R_OK) return rc;
     XchgDev p;
     fill(x, p, nq, k, ++x->seq_push);
-    x->fused[p.slot] = false;
+    x->fused[p.slot] = false; x->nq_of[p.slot] = nq; x->k_of[p.slot] = k;
     p.rows = (const long long *)rows; p.d64 = dist64; p.cnt = count;
-    int rc;
     if (p.seq > XCHG_SLOTS)   // the slot is free once every rank -- this one included: its merge may run on another stream -- has
                               // read what the slot held XCHG_SLOTS calls ago
         for (int r = 0; r < x->world; ++r)
@@ -306,10 +244,15 @@ extern "C" int b2r_xchg_merge(b2r_xchg_handle x, int nq, int k, int64_t *out_row
     XCHG_REQUIRE(x->seq_push - x->seq_merge <= XCHG_SLOTS, "b2r_xchg_merge: more batches pushed than the mailbox has slots");
     B2R_CUDA(cudaSetDevice(x->device));
     cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = flush_pending(x, s)) != B2R_OK) return rc;     // (the arrival of the last fused batch: this merge may be waiting for it)
     XchgDev p;
+    {
+        const int slot = (int)((x->seq_merge + 1) % XCHG_SLOTS);
+        XCHG_REQUIRE(x->nq_of[slot] == nq && x->k_of[slot] == k, "b2r_xchg_merge: nq / k differ from what the oldest unmerged batch was pushed with");
+    }
     fill(x, p, nq, k, ++x->seq_merge);
     p.out_rows = (long long *)out_rows; p.out_dist = out_dist; p.out_cnt = out_count;
-    int rc;
     p.spin = x->fused[p.slot] ? 1 : 0;
     if (!p.spin)
         for (int r = 0; r < x->world; ++r)      // own arrival word too: orders this merge after this rank's push when the streams differ
@@ -321,26 +264,61 @@ extern "C" int b2r_xchg_merge(b2r_xchg_handle x, int nq, int k, int64_t *out_row
     return B2R_OK;
 }
 
-int b2r::xchg_begin_push(b2r_xchg *x, int device, int nq, int k, PushParams *out, const unsigned **wait_words, int *wait_n,
-                         unsigned *wait_val) {
+// One fused call (b2r_query_push), everything decided under one lock so that a refused call changes nothing: the flag words the
+// previous fused call left to publish, the rider (the oldest unmerged batch, merged inside this call's last kernel when its lists
+// fit `rider_smem_limit` bytes of shared memory, by the stand-alone merge kernel behind the call otherwise), the next slot for this
+// call's lists, and the acks its first kernel must see.
+int b2r::xchg_begin_fused(b2r_xchg *x, int device, int nq, int k, FusedCall *c, int64_t *merge_rows, float *merge_dist,
+                          int32_t *merge_count, size_t rider_smem_limit) {
     XCHG_REQUIRE(x->opened, "b2r_query_push: the peers' mailboxes have not been opened (b2r_xchg_open)");
     XCHG_REQUIRE(x->device == device, "b2r_query_push: the exchange lives on another device than the shard");
     XCHG_REQUIRE(nq >= 1 && nq <= x->nq_max && k >= 1 && k <= x->k_max, "b2r_query_push: nq / k exceed what the exchange was created for");
     std::lock_guard<std::mutex> g(x->mu);
-    XCHG_REQUIRE(x->seq_push - x->seq_merge < XCHG_SLOTS, "b2r_query_push: every mailbox slot holds a batch that has not been merged (b2r_xchg_merge)");
+    const unsigned unmerged = x->seq_push - x->seq_merge;
+    XCHG_REQUIRE(!merge_rows || unmerged >= 1, "b2r_query_push: no earlier batch is waiting to be merged");
+    XCHG_REQUIRE(unmerged < (unsigned)XCHG_SLOTS, "b2r_query_push: every mailbox slot holds a batch that has not been merged (b2r_xchg_merge)");
+    c->flags = x->pending;                       // written by this call's first kernel
+    std::memset(&x->pending, 0, sizeof x->pending);
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) x->pending.box[r] = x->box[r];
+    x->pending.world = x->world;
+    c->rider.nq = 0; c->merge_after = false; c->rider_smem = 0;
+    if (merge_rows) {
+        const int slot = (int)((x->seq_merge + 1) % XCHG_SLOTS);
+        fill(x, c->rider, x->nq_of[slot], x->k_of[slot], ++x->seq_merge);
+        c->rider.spin = 1;
+        c->rider.out_rows = (long long *)merge_rows; c->rider.out_dist = merge_dist; c->rider.out_cnt = merge_count;
+        c->rider_smem = (size_t)x->world * c->rider.k * 16;
+        if (c->rider_smem <= rider_smem_limit) {
+            c->rider.ticket = XCHG_TICKET_RIDER;     // (unused: the next kernel on the stream publishes the ack)
+            x->pending.ack_seq = c->rider.seq;
+            x->pending.ack_off = x->flags_off + sizeof(unsigned) * ((size_t)XCHG_SLOTS * x->world + (size_t)slot * x->world + x->rank);
+        } else {
+            c->merge_after = true;                   // its own kernel, which also hands the slot back
+        }
+    }
     const unsigned seq = ++x->seq_push;
     const int slot = (int)(seq % XCHG_SLOTS);
-    x->fused[slot] = true;
-    for (int r = 0; r < XCHG_MAX_WORLD; ++r) out->box[r] = x->box[r];
-    out->lists_off = (size_t)slot * x->slot_bytes + (size_t)x->rank * x->nq_max * x->entry_bytes;
-    out->arrive_off = x->flags_off + sizeof(unsigned) * ((size_t)slot * x->world + x->rank);
-    out->ticket_off = x->flags_off + sizeof(unsigned) * ((size_t)2 * XCHG_SLOTS * x->world + 2);
-    out->entry_bytes = (unsigned)x->entry_bytes; out->k_max = (unsigned)x->k_max;
-    out->seq = seq; out->world = x->world; out->rank = x->rank;
+    x->fused[slot] = true; x->nq_of[slot] = nq; x->k_of[slot] = k;
+    x->pending.arrive_seq = seq;
+    x->pending.arrive_off = x->flags_off + sizeof(unsigned) * ((size_t)slot * x->world + x->rank);
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) c->push.box[r] = x->box[r];
+    c->push.lists_off = (size_t)slot * x->slot_bytes + (size_t)x->rank * x->nq_max * x->entry_bytes;
+    c->push.entry_bytes = (unsigned)x->entry_bytes; c->push.k_max = (unsigned)x->k_max;
+    c->push.world = x->world;
     // before the slot is written again every rank must have merged what it held XCHG_SLOTS calls ago (ack words, local memory)
-    *wait_words = reinterpret_cast<const unsigned *>(x->local + x->flags_off) + (size_t)XCHG_SLOTS * x->world + (size_t)slot * x->world;
-    *wait_n = seq > (unsigned)XCHG_SLOTS ? x->world : 0;
-    *wait_val = seq - XCHG_SLOTS;
+    c->wait_words = reinterpret_cast<const unsigned *>(x->local + x->flags_off) + (size_t)XCHG_SLOTS * x->world + (size_t)slot * x->world;
+    c->wait_n = seq > (unsigned)XCHG_SLOTS ? x->world : 0;
+    c->wait_val = seq - XCHG_SLOTS;
+    return B2R_OK;
+}
+
+// a rider whose lists did not fit the exact scan's shared memory: the stand-alone merge kernel (it hands the slot back itself)
+int b2r::xchg_launch_merge(b2r_xchg *x, XchgDev job, cudaStream_t s) {
+    B2R_CUDA(cudaSetDevice(x->device));
+    job.ticket = XCHG_TICKET_MERGE;
+    const size_t smem = (size_t)job.world * job.k * 16;
+    if (smem > 48 * 1024) B2R_CUDA(cudaFuncSetAttribute(xchg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2R_CUDA(launch_pdl(xchg_merge_kernel, dim3(job.nq), dim3(XCHG_THREADS), smem, s, job));
     return B2R_OK;
 }
 

@@ -341,8 +341,8 @@ class DeviceShard:
 
     def query_device_fused(self, q: torch.Tensor, k: int, o: dict):
         """Replicated queries, the exchange fused into the query's own kernels (b2r_query_push): the finalize stores each
-        list into every rank's mailbox over NVLink as it emits it, and the merge of the PREVIOUS batch is enqueued behind this
-        batch's kernels -- by then its lists have arrived, so nothing waits and no collective or exchange kernel stands
+        list into every rank's mailbox over NVLink as it emits it, and the merge of the PREVIOUS batch rides in this batch's
+        last kernel -- by then its lists have arrived, so nothing waits and no collective, exchange kernel or extra launch stands
         between two scans.  Needs enable_p2p_exchange().  Results of this batch (o['m_rows'|'m_dist'|'m_cnt']) are in place
         after the next call or after drain(); `o` must not be reused before then (alternate two output sets)."""
         nq = q.shape[0]
@@ -352,11 +352,12 @@ class DeviceShard:
         if not self._uses_xchg(nq, k, fused=True):
             raise ValueError("query_device_fused: enable_p2p_exchange(nq_max, k_max) must cover this batch")
         st = torch.cuda.current_stream().cuda_stream
-        _lib.check(self.lib.b2r_query_push(self.h, self._xchg, q.data_ptr(), nq, k, None, o["rows"].data_ptr(),
-                                           o["dist"].data_ptr(), o["cnt"].data_ptr(), st), "b2r_query_push")
         prev, self._fused_prev = self._fused_prev, (nq, k, o)
-        if prev is not None:
-            self._xchg_merge(*prev)
+        m = prev[2] if prev is not None else None       # the previous batch is merged inside this call's last kernel
+        _lib.check(self.lib.b2r_query_push(self.h, self._xchg, q.data_ptr(), nq, k, None, o["rows"].data_ptr(),
+                                           o["dist"].data_ptr(), o["cnt"].data_ptr(),
+                                           m["m_rows"].data_ptr() if m else None, m["m_dist"].data_ptr() if m else None,
+                                           m["m_cnt"].data_ptr() if m else None, st), "b2r_query_push")
 
     def _uses_xchg(self, nq, k, fused=False):
         return self._xchg is not None and (fused or self._xchg_default) and nq <= self._xchg_limits[0] and k <= self._xchg_limits[1]

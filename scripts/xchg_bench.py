@@ -35,7 +35,13 @@ def main():
     def v_p2p_pipe(i):
         sh_p.query_device_pipelined(Q[i % 4], k, op2[i % 2])
         if i == K - 1: sh_p.drain()
-    variants = [("local scan only", v_local), ("nccl all_gather + merge, one stream", v_nccl), ("b2r_xchg_merge, one stream", v_p2p),
+    sh_f = mk()                            # a third shard with mailboxes of its own for the fused form (b2r_query_push)
+    sh_f.enable_p2p_exchange(nq_max=max(nq, 256), k_max=max(k, 8), default=False)
+    of2 = [sh_f.alloc_out(nq, k) for _ in range(2)]
+    def v_fused(i):
+        sh_f.query_device_fused(Q[i % 4], k, of2[i % 2])
+        if i == K - 1: sh_f.drain()
+    variants = [("local scan only", v_local), ("fused into the query's kernels (b2r_query_push), merge behind the next batch", v_fused), ("nccl all_gather + merge, one stream", v_nccl), ("b2r_xchg_merge, one stream", v_p2p),
                 ("nccl, side stream (pipelined)", v_nccl_pipe), ("b2r_xchg_merge, side stream (pipelined)", v_p2p_pipe)]
     times = {name: [] for name, _ in variants}
     for rnd in range(8):
@@ -52,8 +58,8 @@ def main():
         base = sorted(times["local scan only"])[len(times["local scan only"]) // 2]
         for name, _ in variants:
             ts = sorted(times[name]); med = ts[len(ts) // 2]
-            print(f"N={world} nq={nq} k={k}: {name:45s} median {med * 1e3:7.1f} us/step  min {ts[0] * 1e3:7.1f}  (+{(med - base) * 1e3:5.1f} us over the local scan)", flush=True)
-    sh_n.close(); sh_p.close()
+            print(f"N={world} nq={nq} k={k}: {name:80s} median {med * 1e3:7.1f} us/step  min {ts[0] * 1e3:7.1f}  (+{(med - base) * 1e3:5.1f} us over the local scan)", flush=True)
+    sh_n.close(); sh_p.close(); sh_f.close()
     dist.destroy_process_group()
 
 if __name__ == "__main__":

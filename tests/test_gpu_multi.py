@@ -143,7 +143,8 @@ def test_two_gpu_row_sharded_matches_oracle(tmp_path):
 
 def test_fused_exchange_with_a_world_of_one():
     """b2r_query_push on one GPU (a world of one rank: the mailbox is local): the pushed lists, merged, are the query's own
-    answer -- through K3's finalize, through the batch-1 path, through forced exact fix-ups, 10 batches (every slot, the acks)."""
+    answer -- through K3's finalize, through the batch-1 scan, through forced exact scans; merged as a rider of the next call's
+    last kernel or by b2r_xchg_merge; 13 batches of three shapes (every slot several times, the acks)."""
     import ctypes
     import torch
     from multimodal_rag_b200 import _lib
@@ -155,37 +156,53 @@ def test_fused_exchange_with_a_world_of_one():
     x = ctypes.c_void_p()
     _lib.check(lib.b2r_xchg_create(0, 0, 1, 64, 32, ctypes.byref(x)))
     st = torch.cuda.current_stream().cuda_stream
-    pending = []
-    for i in range(10):
+    pending, checked = [], 0
+
+    def check(o_, want_):
+        torch.cuda.synchronize()
+        assert torch.equal(o_["m_rows"], want_[0]) and torch.equal(o_["m_dist"], want_[1]) and torch.equal(o_["m_cnt"], want_[2])
+        assert torch.equal(o_["rows"], want_[0])                   # the local outputs are written as before
+
+    def merge_oldest():
+        nq_, k_, o_, want_ = pending.pop(0)
+        _lib.check(lib.b2r_xchg_merge(x, nq_, k_, o_["m_rows"].data_ptr(), o_["m_dist"].data_ptr(), o_["m_cnt"].data_ptr(), st))
+        check(o_, want_)
+
+    for i in range(13):
         nq, k = (1, 5) if i % 3 == 0 else (40, 10) if i % 3 == 1 else (64, 32)
         Q = torch.from_numpy(make_unit(nq, d, 30 + i)).cuda()
         o = sh.alloc_out(nq, k)
-        sh.query_local(Q, k, o)                                   # the plain answer
+        sh.query_local(Q, k, o)                                    # the plain answer
         want = (o["rows"].clone(), o["dist"].clone(), o["cnt"].clone())
         o2 = sh.alloc_out(nq, k)
-        if i == 4:
-            lib.b2r_set_path(sh.h, 3)
+        if i in (4, 8):
+            lib.b2r_set_path(sh.h, 3)                              # the exact scan emits (and pushes) every list
+        ride = pending[0] if (pending and i % 4 != 2) else None    # most calls carry the oldest unmerged batch as a rider
+        m = ride[2] if ride else None
         _lib.check(lib.b2r_query_push(sh.h, x, Q.data_ptr(), nq, k, None, o2["rows"].data_ptr(), o2["dist"].data_ptr(),
-                                      o2["cnt"].data_ptr(), st), "b2r_query_push")
+                                      o2["cnt"].data_ptr(), m["m_rows"].data_ptr() if m else None, m["m_dist"].data_ptr() if m else None,
+                                      m["m_cnt"].data_ptr() if m else None, st), "b2r_query_push")
         lib.b2r_set_path(sh.h, 0)
+        if ride:
+            pending.pop(0)
+            check(ride[2], ride[3])
+            checked += 1
         pending.append((nq, k, o2, want))
-        if len(pending) == 3:                                     # up to three batches pushed and not merged
-            for nq_, k_, o_, want_ in pending[:2]:
-                _lib.check(lib.b2r_xchg_merge(x, nq_, k_, o_["m_rows"].data_ptr(), o_["m_dist"].data_ptr(), o_["m_cnt"].data_ptr(), st))
-                torch.cuda.synchronize()
-                assert torch.equal(o_["m_rows"], want_[0]) and torch.equal(o_["m_dist"], want_[1]) and torch.equal(o_["m_cnt"], want_[2])
-                assert torch.equal(o_["rows"], want_[0])           # the local outputs are written as before
-            pending = pending[2:]
-    for nq_, k_, o_, want_ in pending:
-        _lib.check(lib.b2r_xchg_merge(x, nq_, k_, o_["m_rows"].data_ptr(), o_["m_dist"].data_ptr(), o_["m_cnt"].data_ptr(), st))
-        torch.cuda.synchronize()
-        assert torch.equal(o_["m_rows"], want_[0]) and torch.equal(o_["m_dist"], want_[1])
-    # a fourth unmerged batch is refused, not deadlocked
+        if len(pending) == 3:
+            merge_oldest()
+    while pending:
+        merge_oldest()
+    assert checked >= 8
+    # a wrong shape for the oldest batch is refused; so is a fifth unmerged batch (no deadlock) and a rider when nothing older waits
     Q = torch.from_numpy(make_unit(8, d, 99)).cuda()
     outs = [sh.alloc_out(8, 5) for _ in range(5)]
-    rcs = [lib.b2r_query_push(sh.h, x, Q.data_ptr(), 8, 5, None, o_["rows"].data_ptr(), o_["dist"].data_ptr(), o_["cnt"].data_ptr(), st)
-           for o_ in outs]
-    assert rcs == [0, 0, 0, 0, _lib.B2R_EINVAL] or rcs[:3] == [0, 0, 0] and rcs[3] == _lib.B2R_EINVAL
+    push = lambda o_, m=None: lib.b2r_query_push(sh.h, x, Q.data_ptr(), 8, 5, None, o_["rows"].data_ptr(), o_["dist"].data_ptr(),
+                                                 o_["cnt"].data_ptr(), m["m_rows"].data_ptr() if m else None,
+                                                 m["m_dist"].data_ptr() if m else None, m["m_cnt"].data_ptr() if m else None, st)
+    assert push(outs[0], outs[4]) == _lib.B2R_EINVAL               # nothing older to carry
+    assert [push(o_) for o_ in outs] == [0, 0, 0, 0, _lib.B2R_EINVAL]
+    o_ = outs[0]
+    assert lib.b2r_xchg_merge(x, 9, 5, o_["m_rows"].data_ptr(), o_["m_dist"].data_ptr(), o_["m_cnt"].data_ptr(), st) == _lib.B2R_EINVAL
     torch.cuda.synchronize()
     lib.b2r_xchg_destroy(x)
     sh.close()
