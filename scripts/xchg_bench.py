@@ -41,7 +41,7 @@ def main():
     def v_fused(i):
         sh_f.query_device_fused(Q[i % 4], k, of2[i % 2])
         if i == K - 1: sh_f.drain()
-    variants = [("local scan only", v_local), ("fused into the query's kernels (b2r_query_push), merge behind the next batch", v_fused), ("nccl all_gather + merge, one stream", v_nccl), ("b2r_xchg_merge, one stream", v_p2p),
+    variants = [("local scan only", v_local), ("fused into the query's kernels (b2r_query_push), merge rides in the next call", v_fused), ("nccl all_gather + merge, one stream", v_nccl), ("b2r_xchg_merge, one stream", v_p2p),
                 ("nccl, side stream (pipelined)", v_nccl_pipe), ("b2r_xchg_merge, side stream (pipelined)", v_p2p_pipe)]
     times = {name: [] for name, _ in variants}
     for rnd in range(8):
