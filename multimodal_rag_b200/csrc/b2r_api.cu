@@ -895,9 +895,14 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
                 gp.n_slices = std::max(1, std::min(gp.n_slices, max_pairs / (gp.n_qblocks / 2)));
             }
         }
-        {   // seeding tiles per CTA: >= 128 tiles (32k rows) over the block's slices, more on long slices (<= 1/64 extra work)
+        {   // seeding tiles per CTA: >= 128 tiles (32k rows) over the block's slices, more on long slices (<= 1/64 extra work).
+            // The pair form samples >= 192 tiles (3 per pair at 74 pairs): a tighter bound shortens the candidate pools the
+            // finalize sorts (105 -> 70 entries per query at 1M rows) by more than the extra tile costs -- 2 / 3 / 4 / 6 tiles
+            // per pair, A/B on one box, sustained: 191.9 / 189.4 / 192.5 / 199.5 us per batch-256 step (gpurun_out/seed_tiles2.log)
             const int tiles_per_cta = tiles_total / gp.n_slices;
-            const int want = std::max((128 + gp.n_slices - 1) / gp.n_slices, std::min(tiles_per_cta / 64, 8));
+            const int want128 = std::max((128 + gp.n_slices - 1) / gp.n_slices, std::min(tiles_per_cta / 64, 8));
+            const int want192 = std::max((192 + gp.n_slices - 1) / gp.n_slices, std::min(tiles_per_cta / 64, 8));
+            const int want = (pair && tiles_per_cta >= 8 * want192) ? want192 : want128;     // short slices keep the smaller sample
             gp.seed_stride = 1;
             if (pool_mode) {   // whenever there is anything to sample: max(4 tiles, 1/32 of the shard) spread over the slices, so
                                // that the 32nd best sample leaves ~1024 candidates per query -- far more than k, or the
