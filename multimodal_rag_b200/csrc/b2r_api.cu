@@ -168,6 +168,7 @@ extern "C" int b2r_create(int dim, int space, int64_t capacity_rows, int device,
     if (const char *e = getenv("B2R_POOL_SAMPLE_DIV")) h->pool_sample_div = std::max(0, atoi(e));
     if (const char *e = getenv("B2R_TRACE")) { h->trace_on = atoi(e) != 0; h->trace_mode = atoi(e); }
     if (const char *e = getenv("B2R_NO_PAIR")) h->no_pair = atoi(e) != 0;
+    if (const char *e = getenv("B2R_SEED_RANK_L")) h->seed_rank_l = atoi(e) != 0;
     if (const char *e = getenv("B2R_NO_DYN")) h->no_dyn = atoi(e) != 0;
     if (const char *e = getenv("B2R_NO_BM64")) h->no_bm64 = atoi(e) != 0;
     int rc = B2R_OK;
@@ -877,6 +878,10 @@ int launch_gemm_batch(b2r_index *h, int nq, int k, int epl, const FinalizeParams
         gp.samples = (unsigned *)h->gemm_samples.p; gp.seeded = gp.cnt + (size_t)qblocks_total * GEMM_BM; gp.arrive = gp.seeded + (size_t)qblocks_total * GEMM_BM;
         gp.tile_counter = nullptr;
         gp.seed_tiles = 0;
+        // the bound is seeded from the k-th best sampled score where that was measured to pay (launches of >= 2 query blocks:
+        // pools 144 -> 87 entries per query at k = 5, 286 -> 178 at k = 10, -1..4 % per step, -3..5 % at 512 dims / k = 10:
+        // the finalize sorts less); single-block launches keep the L-th best (batch 1: no gain measured)
+        gp.seed_rank = pool_mode ? GEMM_POOL_SAMPLE_RANK : ((h->seed_rank_l || k > L || gp.n_qblocks < 2) ? L : k);
         gp.seed_wait_ns = h->seed_wait_ns; gp.delay_us = h->delay_us;
         gp.trace = h->trace_on ? (unsigned long long *)h->trace.p : nullptr; gp.trace_mode = h->trace_mode;
         UnionParams un;

@@ -139,6 +139,7 @@ struct b2r_index {
     unsigned long long seed_wait_ns = 0;
     int delay_us = 0, pool_sample_div = 0;     // 0 = by shard size (1/32, 1/64 from 8M rows on)
     bool no_pair = false;
+    bool seed_rank_l = false;       // B2R_SEED_RANK_L=1: the L-th best sample seeds K3's bound (the form before the k-th best was used)
     bool no_dyn = false;
     bool no_bm64 = false;           // B2R_NO_BM64=1: 128-query blocks even for batches of at most 64            // B2R_NO_DYN=1: static slices only (no dynamic tile hand-out)           // B2R_NO_PAIR=1: never use the cta_group::2 form of K3
     b2r::DevBuf trace;

@@ -83,6 +83,8 @@ struct GemmParams {
     int seed_stride;             // slices 0, stride, 2*stride, ... sample; the others post nothing (small shards in pool mode)
     unsigned *samples;           // [launch queries (padded to 128)][n_slices*2][2 .. L] ordered score keys, 0 = empty
     unsigned *seeded;            // [all queries] 0 = not seeded yet, 1 = seeded without a bound, else the seed (= gthr[q] then)
+    int seed_rank;               // which of the posted scores becomes the bound: the k-th best (list mode; any rank in [k, L] is a
+                                 // valid lower bound of the k-th best overall, the k-th is the tightest), the 32nd (pool mode)
     unsigned *arrive;            // [all q-blocks] CTAs that have posted (0 between calls: the query preparation clears it)
     unsigned *tile_counter;      // nullptr: every CTA scans its static slice.  Else (one query block per launch, no pairs): the next
                                  // tile of the shard nobody has taken yet (0 at launch: cleared by the preparation); CTAs take tiles
@@ -712,8 +714,9 @@ __device__ __forceinline__ void epi_bar_sync() {       // the 8 epilogue warps o
 // One warp: the L-th largest of vals[0..n) (ordered score keys of DISTINCT rows, 0 = empty), 0 when fewer than
 // L are set.  Every lane keeps the L best of its strided share in registers, then the warp pops the
 // maximum L times.
+// `rank` <= L: the rank-th largest instead (the lanes still keep L each).
 template <int L>
-__device__ __forceinline__ unsigned warp_lth_largest(const unsigned *vals, int n, int lane) {
+__device__ __forceinline__ unsigned warp_lth_largest(const unsigned *vals, int n, int lane, int rank = L) {
     unsigned top[L];
 #pragma unroll
     for (int i = 0; i < L; ++i) top[i] = 0u;
@@ -736,7 +739,7 @@ __device__ __forceinline__ unsigned warp_lth_largest(const unsigned *vals, int n
     }
     unsigned res = 0u;
 #pragma unroll 1
-    for (int r = 0; r < L; ++r) {
+    for (int r = 0; r < rank; ++r) {
         res = __reduce_max_sync(FULL_MASK, top[0]);
         const unsigned who = __ballot_sync(FULL_MASK, top[0] == res);
         if (lane == __ffs(who) - 1) {                    // the winning lane advances to its next best
@@ -969,7 +972,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             for (; lq_next < lq1; lq_next += GEMM_EPI_WARPS) {
                 const int qs = qb * BM + lq_next;
                 if (qs >= p.nq) break;
-                const unsigned v = warp_lth_largest<LS>(p.samples + (size_t)(qs - p.qblock0 * BM) * per_q, per_q, lane);
+                const unsigned v = warp_lth_largest<LS>(p.samples + (size_t)(qs - p.qblock0 * BM) * per_q, per_q, lane, p.seed_rank);
                 if (lane == 0) {
                     atomicExch(p.seeded + qs, v != 0u ? v : 1u);  // flag and seed in one word (1 = no seed: too few rows pass): the waiting threads take it from here
                     if (v != 0u) atomicMax(p.gthr + qs, v);       // the finalize (and every later tile) reads the bound from gthr[q]
