@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from .idtable import IdTable, IdsByRow, RowOfId, encode_ids
-from .where import MetaTable, pack_bits
+from .where import MetaTable, doc_mask, pack_bits
 
 logger = logging.getLogger(__name__)
 
@@ -269,12 +269,10 @@ class B200Collection:
     def delete(self, ids=None, where=None, where_document=None):
         """Chroma ``Collection.delete``: by ids and / or a where clause.  With neither, chromadb 0.4.22 raises instead of
         wiping the collection (the reference empties a collection through delete_collection, embedder.py:669-678)."""
-        if where_document:
-            raise NotImplementedError("where_document ($contains) is not part of the reference's hot path")
-        if (ids is None or (not isinstance(ids, str) and len(ids) == 0)) and not where:
+        if (ids is None or (not isinstance(ids, str) and len(ids) == 0)) and not where and not where_document:
             raise ValueError("You must provide either ids, where, or where_document to delete.")
         with self._lock:
-            rows = self._select_rows(ids, where)
+            rows = self._select_rows(ids, where, where_document)
             self._kill_rows(rows)
             return self._idtab.ids_of(rows)
 
@@ -297,14 +295,14 @@ class B200Collection:
             return n
 
     # ---- reads -----------------------------------------------------------------------
-    def _where_mask(self, where) -> np.ndarray:
-        """bool per row: live AND matching `where`.  The clause runs on the device columns (b2r_filter_eval) like a
-        query's would; clauses the device cannot run fall back to the host tables inside `_filter`."""
+    def _where_mask(self, where, where_document=None) -> np.ndarray:
+        """bool per row: live AND matching `where` (AND `where_document`).  The clause runs on the device columns
+        (b2r_filter_eval) like a query's would; clauses the device cannot run fall back to the host tables inside `_filter`."""
         if self._h is None or not self._nrows:
             return np.zeros(self._nrows, dtype=bool)
-        return self.filter_bits(where)
+        return self.filter_bits(where, where_document)
 
-    def _select_rows(self, ids, where):
+    def _select_rows(self, ids, where, where_document=None):
         if ids is not None:
             if isinstance(ids, str):
                 ids = [ids]
@@ -313,12 +311,12 @@ class B200Collection:
             except TypeError:
                 raise ValueError("Expected ids to be a list of str") from None
             rows = np.unique(found[found >= 0]).tolist()
-            if where and rows:
-                mask = self._where_mask(where)
+            if (where or where_document) and rows:
+                mask = self._where_mask(where, where_document)
                 rows = [r for r in rows if mask[r]]
             return rows
-        if where:
-            mask = self._where_mask(where)
+        if where or where_document:
+            mask = self._where_mask(where, where_document)
         else:
             mask = self._alive
         return np.flatnonzero(mask).tolist()
@@ -339,10 +337,10 @@ class B200Collection:
                 raise ValueError(f"Expected include item to be one of {sorted(allowed)}, got {key}")
         return include
 
-    def get(self, ids=None, where=None, limit=None, offset=None, include=_INCLUDE_GET):
+    def get(self, ids=None, where=None, limit=None, offset=None, include=_INCLUDE_GET, where_document=None):
         include = self._check_include(include, {"metadatas", "documents", "embeddings"})
         with self._lock:
-            rows = self._select_rows(ids, where)
+            rows = self._select_rows(ids, where, where_document)
             if offset:
                 rows = rows[offset:]
             if limit is not None:
@@ -356,15 +354,19 @@ class B200Collection:
                 out["documents"] = [self._docs[r] for r in rows]
             return out
 
-    def _filter(self, where):
-        """where -> (B2RFilter, keep-alive object).  None when nothing can match."""
+    def _filter(self, where, where_document=None):
+        """where (+ where_document) -> (B2RFilter, keep-alive object)."""
         f = _lib.B2RFilter(type_mask=(1 << 64) - 1, allow_bits=None, where=None)
+        doc_bits = None
+        if where_document:                    # host pass over the documents -> allow bitmap, ANDed on the device with the rest
+            doc_bits = pack_bits(doc_mask(self._docs, where_document))
+            f.allow_bits = doc_bits.ctypes.data
         if not where:
-            return f, None
+            return f, doc_bits
         tm = self._meta.type_only_mask(where)
         if tm is not None:
             f.type_mask = tm
-            return f, None
+            return f, doc_bits
         if self.device_where:                # the clause runs on the device against the metadata columns
             # compiled clauses are kept while the table does not grow (a chat session repeats its filter; the device
             # side recognises the repeat by the clause's hash and re-uses its bitmaps)
@@ -387,8 +389,11 @@ class B200Collection:
                         self._where_cache[key] = hit
             if hit is not None:
                 f.where = ctypes.pointer(hit[0])
-                return f, hit
-        bits = pack_bits(self._meta.mask(where))      # clause the device cannot run: host-evaluated bitmap
+                return f, (hit, doc_bits)
+        mask = self._meta.mask(where)                 # clause the device cannot run: host-evaluated bitmap
+        if where_document:
+            mask = mask & doc_mask(self._docs, where_document)
+        bits = pack_bits(mask)
         f.allow_bits = bits.ctypes.data
         return f, bits
 
@@ -399,18 +404,18 @@ class B200Collection:
         with self._lock:
             return self._filter(where)
 
-    def filter_bits(self, where=None) -> np.ndarray:
-        """The pass bitmap the device derives for `where` (bool per row: live AND matching) -- b2r_filter_eval."""
+    def filter_bits(self, where=None, where_document=None) -> np.ndarray:
+        """The pass bitmap the device derives for `where` / `where_document` (bool per row: live AND matching) -- b2r_filter_eval."""
         with self._lock:
             n = self._nrows
             words = np.zeros((n + 31) // 32, dtype=np.uint32)
             if self._h is not None and n:
-                f, keep = self._filter(where)
+                f, keep = self._filter(where, where_document)
                 _lib.check(self._lib.b2r_filter_eval(self._h, ctypes.byref(f), words.ctypes.data, 0), "b2r_filter_eval")
                 del keep
             return np.unpackbits(words.view(np.uint8), bitorder="little")[:n].astype(bool)
 
-    def query_rows(self, query_embeddings, n_results=10, where=None, want_dist64=False):
+    def query_rows(self, query_embeddings, n_results=10, where=None, want_dist64=False, where_document=None):
         """Device query returning numpy arrays: rows [nq,k] int64 (-1 pad), dist [nq,k] fp32,
         count [nq] int32 (and fp64 distances when asked)."""
         with self._lock:
@@ -428,7 +433,7 @@ class B200Collection:
             d64 = np.full((m.n, k), np.inf, dtype=np.float64) if want_dist64 else None
             if self._h is None or not self._idtab.live:
                 return (rows, dist, cnt, d64) if want_dist64 else (rows, dist, cnt)
-            f, keep = self._filter(where)
+            f, keep = self._filter(where, where_document)
             _lib.check(self._lib.b2r_query_ex(self._h, m.ptr, m.n, k, ctypes.byref(f), rows.ctypes.data,
                                               dist.ctypes.data, None if d64 is None else d64.ctypes.data,
                                               cnt.ctypes.data, m.stream), "b2r_query")
@@ -473,11 +478,9 @@ class B200Collection:
         distance; keys not in ``include`` are None."""
         if query_texts is not None and query_embeddings is None:
             raise ValueError("query_texts needs an embedding function; pass query_embeddings")
-        if where_document:
-            raise NotImplementedError("where_document ($contains) is not part of the reference's hot path")
         include = self._check_include(include, _VALID_INCLUDE)
         with self._lock:
-            rows, dist, cnt = self.query_rows(query_embeddings, n_results, where)
+            rows, dist, cnt = self.query_rows(query_embeddings, n_results, where, where_document=where_document)
             nq = rows.shape[0]
             live = self._idtab.live
             if n_results > live:

@@ -305,6 +305,33 @@ class MetaTable:
         return m
 
 
+def doc_mask(docs: list, where_document: dict) -> np.ndarray:
+    """bool[len(docs)] of rows whose DOCUMENT satisfies a Chroma ``where_document`` clause (chromadb 0.4.22:
+    ``{"$contains": s}``, ``{"$not_contains": s}``, ``{"$and": [...]}``, ``{"$or": [...]}``).  Chroma answers these from its
+    sqlite full-text table before the vector search; here it is a pass over the host's document list that ends as an allow
+    bitmap for the device (the reference never passes where_document -- app/utils/embedder.py:595-601 -- so this is a
+    compatibility path, not a hot one).  A row without a document matches neither operator."""
+    if not isinstance(where_document, dict) or len(where_document) != 1:
+        raise ValueError(f"Expected where document to have exactly one operator, got {where_document}")
+    (op, val), = where_document.items()
+    if op in ("$and", "$or"):
+        if not isinstance(val, (list, tuple)) or len(val) < 1:
+            raise ValueError(f"Expected where document value for {op} to be a non-empty list")
+        parts = [doc_mask(docs, w) for w in val]
+        out = parts[0]
+        for p in parts[1:]:
+            out = (out & p) if op == "$and" else (out | p)
+        return out
+    if op not in ("$contains", "$not_contains"):
+        raise ValueError(f"Expected where document operator to be one of $contains, $not_contains, $and, $or, got {op}")
+    if not isinstance(val, str) or not val:
+        raise ValueError(f"Expected where document operand value for operator {op} to be a non-empty str")
+    has = np.fromiter((d is not None and val in d for d in docs), dtype=bool, count=len(docs))
+    if op == "$contains":
+        return has
+    return ~has & np.fromiter((d is not None for d in docs), dtype=bool, count=len(docs))
+
+
 def pack_bits(mask: np.ndarray) -> np.ndarray:
     """bool[n] -> uint32[ceil(n/32)], bit (r & 31) of word r >> 5 (include/b2r.h b2r_filter)."""
     n = mask.shape[0]

@@ -159,6 +159,27 @@ def where_match(meta: dict | None, where: dict | None) -> bool:
     return bool(_CMP[op](have, val))
 
 
+def where_document_match(doc, where_document) -> bool:
+    """Chroma ``where_document`` (chromadb 0.4.22 validate_where_document / the sqlite full-text filter, restated from
+    memory like the rest of this file): $contains, $not_contains, $and, $or; a row without a document matches neither."""
+    if not where_document:
+        return True
+    if len(where_document) != 1:
+        raise ValueError(f"Expected where document to have exactly one operator, got {where_document}")
+    (op, val), = where_document.items()
+    if op == "$and":
+        return all(where_document_match(doc, w) for w in val)
+    if op == "$or":
+        return any(where_document_match(doc, w) for w in val)
+    if op not in ("$contains", "$not_contains"):
+        raise ValueError(f"unknown where document operator {op}")
+    if not isinstance(val, str) or not val:
+        raise ValueError("where document operand must be a non-empty str")
+    if doc is None:
+        return False
+    return (val in doc) if op == "$contains" else (val not in doc)
+
+
 # --------------------------------------------------------------------------
 # Collection with Chroma's add/upsert/query/get/delete/count semantics
 # --------------------------------------------------------------------------
@@ -235,8 +256,8 @@ class ExactCollection:
             self._append(id_, e[i], None if metadatas is None else metadatas[i],
                          None if documents is None else documents[i])
 
-    def delete(self, ids=None, where=None):
-        rows = self._select_rows(ids, where)
+    def delete(self, ids=None, where=None, where_document=None):
+        rows = self._select_rows(ids, where, where_document)
         for r in rows:
             self._alive[r] = False
             self._row_of.pop(self._ids[r], None)
@@ -248,7 +269,7 @@ class ExactCollection:
     def _live_rows(self):
         return [r for r, a in enumerate(self._alive) if a]
 
-    def _select_rows(self, ids, where):
+    def _select_rows(self, ids, where, where_document=None):
         if ids is not None:
             rows = [self._row_of[i] for i in ids if i in self._row_of]
             rows.sort()
@@ -256,10 +277,12 @@ class ExactCollection:
             rows = self._live_rows()
         if where:
             rows = [r for r in rows if where_match(self._meta[r], where)]
+        if where_document:
+            rows = [r for r in rows if where_document_match(self._doc[r], where_document)]
         return rows
 
-    def get(self, ids=None, where=None, include=("metadatas", "documents")):
-        rows = self._select_rows(ids, where)
+    def get(self, ids=None, where=None, include=("metadatas", "documents"), where_document=None):
+        rows = self._select_rows(ids, where, where_document)
         out = {"ids": [self._ids[r] for r in rows], "embeddings": None,
                "metadatas": None, "documents": None}
         if "embeddings" in include:
@@ -271,7 +294,7 @@ class ExactCollection:
         return out
 
     def query(self, query_embeddings, n_results=10, where=None,
-              include=("metadatas", "documents", "distances")):
+              include=("metadatas", "documents", "distances"), where_document=None):
         q = np.asarray(query_embeddings, dtype=np.float32)
         if q.ndim == 1:
             q = q[None]
@@ -280,7 +303,7 @@ class ExactCollection:
         if n_results <= 0:
             raise ValueError("n_results must be a positive integer")
         nq = q.shape[0]
-        rows = self._select_rows(None, where)
+        rows = self._select_rows(None, where, where_document)
         res = {"ids": [], "distances": None, "metadatas": None, "documents": None, "embeddings": None}
         for key in ("distances", "metadatas", "documents", "embeddings"):
             if key in include:

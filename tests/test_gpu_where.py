@@ -187,3 +187,40 @@ def test_sparse_keys_that_end_before_the_batch_does():
     r = c.query(query_embeddings=X[5:6].tolist(), n_results=3, where={"first": 1})
     assert r["ids"] == [["a0"]]
     c.close()
+
+
+def test_where_document_on_query_get_delete():
+    """Chroma's where_document ($contains / $not_contains, alone, beside a type filter, beside a compiled clause): query, get and
+    delete select what the oracle's collection selects."""
+    from multimodal_rag_b200 import B200Collection
+    from oracle import exact_oracle as eo
+    n, d = 3000, 128
+    X = make_unit(n, d, 14)
+    metas = _metas(n, seed=3)
+    docs = [None if i % 13 == 0 else f"{('text on page', 'table row', 'image of Figure')[i % 3]} {i % 29} / {i}" for i in range(n)]
+    ids = [f"id{i}" for i in range(n)]
+    c = B200Collection("wd", {"hnsw:space": "cosine"})
+    o = eo.ExactCollection("wd", {"hnsw:space": "cosine"})
+    for col in (c, o):
+        col.add(ids=ids, embeddings=X, metadatas=metas, documents=docs)
+        col.delete(ids=ids[::11])
+    Q = make_unit(6, d, 15)
+    cases = [({"$contains": "table row"}, None), ({"$not_contains": "page"}, {"type": "image"}),
+             ({"$or": [{"$contains": "Figure 3"}, {"$contains": "row 12"}]}, {"$and": [{"page": {"$gte": 2}}, {"type": {"$ne": "text"}}]}),
+             ({"$contains": "never there"}, None)]
+    for wd, where in cases:
+        got = c.query(query_embeddings=Q, n_results=7, where=where, where_document=wd)
+        want = o.query(Q, n_results=7, where=where, where_document=wd)
+        assert got["ids"] == want["ids"] and got["documents"] == want["documents"]
+        for a, b in zip(got["distances"], want["distances"]):
+            np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-7)
+        assert c.get(where=where, where_document=wd)["ids"] == o.get(where=where, where_document=wd)["ids"]
+    gone = c.delete(where_document={"$contains": "image of"})
+    before = set(o._row_of)
+    o.delete(where_document={"$contains": "image of"})
+    assert sorted(gone) == sorted(before - set(o._row_of)) and len(gone) > 500
+    assert c.count() == o.count()
+    assert c.query(query_embeddings=Q, n_results=5)["ids"] == o.query(Q, n_results=5)["ids"]
+    with pytest.raises(ValueError):
+        c.query(query_embeddings=Q, n_results=5, where_document={"$contains": ""})
+    c.close()

@@ -116,3 +116,37 @@ def test_compile_gives_up_on_host_only_columns_and_long_clauses():
     assert t.compile({"$or": [{"k1": i} for i in range(16)]}) is not None
     with pytest.raises(ValueError):
         t.compile({"k1": {"$gt": "a"}})
+
+
+DOC_CLAUSES = [
+    {"$contains": "table"}, {"$not_contains": "table"}, {"$contains": "Figure 3"}, {"$contains": "é"},
+    {"$and": [{"$contains": "page"}, {"$not_contains": "7"}]},
+    {"$or": [{"$contains": "image of"}, {"$and": [{"$contains": "row"}, {"$contains": "12"}]}]},
+    {"$contains": "never there"},
+]
+
+
+def _docs(n=400):
+    docs = []
+    for i in range(n):
+        kind = ("text on page", "table row", "image of Figure", "résumé é")[i % 4]
+        docs.append(None if i % 13 == 0 else f"{kind} {i % 29} / {i}")
+    return docs
+
+
+@pytest.mark.parametrize("wd", DOC_CLAUSES)
+def test_doc_mask_matches_oracle(wd):
+    """where_document ($contains / $not_contains / $and / $or): the product's pass over the document list against the oracle's
+    per-row restatement; a row without a document matches neither operator."""
+    from multimodal_rag_b200.where import doc_mask
+    from oracle.exact_oracle import where_document_match
+    docs = _docs()
+    want = np.asarray([where_document_match(d, wd) for d in docs])
+    np.testing.assert_array_equal(doc_mask(docs, wd), want)
+
+
+def test_doc_mask_rejects_malformed_clauses():
+    from multimodal_rag_b200.where import doc_mask
+    for bad in ({"$contains": ""}, {"$contains": 3}, {"$like": "x"}, {"$and": []}, {"$contains": "a", "$not_contains": "b"}, "table"):
+        with pytest.raises(ValueError):
+            doc_mask(["a"], bad)
