@@ -289,7 +289,6 @@ int b2r::xchg_begin_fused(b2r_xchg *x, int device, int nq, int k, FusedCall *c, 
         c->rider.out_rows = (long long *)merge_rows; c->rider.out_dist = merge_dist; c->rider.out_cnt = merge_count;
         c->rider_smem = (size_t)x->world * c->rider.k * 16;
         if (c->rider_smem <= rider_smem_limit) {
-            c->rider.ticket = XCHG_TICKET_RIDER;     // (unused: the next kernel on the stream publishes the ack)
             x->pending.ack_seq = c->rider.seq;
             x->pending.ack_off = x->flags_off + sizeof(unsigned) * ((size_t)XCHG_SLOTS * x->world + (size_t)slot * x->world + x->rank);
         } else {

@@ -9,13 +9,14 @@ namespace b2r {
 constexpr int XCHG_MAX_WORLD = 8;
 constexpr int XCHG_THREADS = 256;
 constexpr int XCHG_SLOTS = 4;          // mailbox slots, used round-robin by sequence number
-// flag block of a mailbox (u32 words): arrival [SLOTS][world], ack [SLOTS][world], then four exit tickets
-constexpr int XCHG_TICKET_PUSH = 0, XCHG_TICKET_MERGE = 1, XCHG_TICKET_PUBLISH = 2, XCHG_TICKET_RIDER = 3;
+// flag block of a mailbox (u32 words): arrival [SLOTS][world], ack [SLOTS][world], then the exit tickets of the push and the
+// merge kernel (the fused form needs none: its flag words are written by the next kernel on the stream)
+constexpr int XCHG_TICKET_PUSH = 0, XCHG_TICKET_MERGE = 1;
 
 struct XchgDev {
     int rank, world, nq, k, slot;
     int spin;                      // merge: wait for the arrival words inside the kernel (fused pushes) instead of on the stream
-    int ticket;                    // which exit ticket the merging grid uses (stand-alone kernel / rider of the exact scan)
+    int ticket;                    // exit ticket of the stand-alone merge kernel (a rider takes none)
     unsigned seq;
     int nq_max, k_max;
     size_t entry_bytes;            // one query's list in a mailbox: rows[k_max] i64 | dist[k_max] f64 | count i32 (+pad)
