@@ -205,8 +205,8 @@ int b2r_merge_shards_packed(const void *packed, int64_t shard_stride, int64_t of
  * allocated by this library, mapped into the other processes with CUDA IPC).  b2r_xchg_push (enqueue on the stream of the
  * scan) stores this rank's lists straight into every peer's mailbox over NVLink and publishes a sequence number there;
  * b2r_xchg_merge (same stream, or another one so that the exchange of batch i overlaps the scan of batch i+1) makes its stream
- * wait for the peers' sequence numbers with stream memory operations -- no SM spins while a peer is late -- and merges.  Two
- * mailbox slots alternate; a slot is rewritten only after every rank has read it.  Collective: every rank makes the same
+ * wait for the peers' sequence numbers with stream memory operations -- no SM spins while a peer is late -- and merges.  Four
+ * mailbox slots rotate; a slot is rewritten only after every rank has read it.  Collective: every rank makes the same
  * sequence of push / merge calls (same nq, k).  Setup: b2r_xchg_create on every rank, exchange the 64-byte handles by any
  * means (torch.distributed all_gather_object), b2r_xchg_open with all of them in rank order, then a barrier.  world <= 8.
  * No reference counterpart: the reference is single-process.                                                              */

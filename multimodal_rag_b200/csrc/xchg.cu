@@ -11,8 +11,8 @@
 //          have reached the sequence number (cuStreamWaitValue32: a stream memory operation, no SM is occupied while waiting),
 //          then one CTA per query merges the world x k candidates on (fp64 distance, global row) -- the order a single shard
 //          uses -- and the last CTA tells every peer that the slot has been read.
-// Two mailbox slots alternate by sequence number; before a slot is written again the pushing stream waits (again a stream memory
-// operation) until every peer has reported having read what the slot held two calls ago.  Why no spinning: the scoring kernel
+// Four mailbox slots are used round-robin by sequence number; before a slot is written again the pushing stream waits (again a
+// stream memory operation) until every peer has reported having read what the slot held four calls ago.  Why no spinning: the scoring kernel
 // of the NEXT batch owns every SM's shared memory; a kernel that waits inside an SM either keeps that SM from starting its slice or
 // cannot start itself (measured: a fused spin-wait version cost +31 us per batch on one stream and up to +50 us with outliers on a
 // side stream, NCCL's all_gather + a merge launch +26 us / +8 us).  Calls are collective: every rank makes the same sequence of
