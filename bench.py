@@ -584,9 +584,35 @@ def run_gpu(args):
         except Exception as e:                        # no peer access between these GPUs: the NCCL forms remain
             sys.stderr.write(f"[bench] fused exchange unavailable: {e}\n")
             fused_ok = False
-        t_ok = torch.tensor([1 if fused_ok else 0], device=dev)
-        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        fused_ok = bool(int(t_ok.item()))
+        # (enable_p2p_exchange agrees on a failure across the ranks before it raises: fused_ok is the same everywhere)
+
+        union = {}
+
+        def check_form(which):
+            """Collective: one batch through exchange form `which`; True when its merged rows / distances equal a single-GPU answer
+            over the union of the shards (rank 0 builds the union once)."""
+            if which == "fused":
+                sh2.query_device_fused(Q2[0], k, o2)
+                sh2.drain()
+            else:
+                sh2.query_device(Q2[0], k, o2)
+            torch.cuda.synchronize()
+            good = True
+            if rank == 0:
+                if not union:
+                    un = DeviceShard(DIM, "cosine", capacity=world * N_ROWS, row_base=0, device=local_rank, group=None, world=1)
+                    for r in range(world):
+                        fill_shard(un, N_ROWS, DIM, 0xC0FFEE + 1 + r)
+                    ou = un.alloc_out(nq, k)
+                    un.query_local(Q2[0], k, ou)
+                    torch.cuda.synchronize()
+                    union["rows"], union["dist"] = ou["rows"].clone(), ou["dist"].clone()
+                    un.close()
+                good = (bool(torch.equal(union["rows"], o2["m_rows"])) and int(o2["m_cnt"].min()) == k and
+                        bool(torch.allclose(union["dist"], o2["m_dist"], rtol=1e-6, atol=0)))
+            flag = torch.tensor([1 if good else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            return int(flag.item()) == 1
 
         def step_sharded_fused(i):
             # the finalize of batch i stores its lists into every rank's mailbox; the merge of batch i rides in the last kernel
@@ -616,13 +642,18 @@ def run_gpu(args):
             step_sharded_serial(i)
         trial = {"pipelined": summarize(timed(step_sharded_pipelined, K, min_s=0.1), K)["ms_per_step"],
                  "serial": summarize(timed(step_sharded_serial, K, min_s=0.1), K)["ms_per_step"]}
+        fused_rejected = False
         if fused_ok:
             for i in range(W):
                 step_sharded_fused(i)
             sh2.drain()
-            trial["fused"] = summarize(timed(step_sharded_fused, K, min_s=0.1), K)["ms_per_step"]
+            if check_form("fused"):                   # a form that answers wrongly is never a candidate
+                trial["fused"] = summarize(timed(step_sharded_fused, K, min_s=0.1), K)["ms_per_step"]
+            else:
+                fused_ok, fused_rejected = False, True
+                sys.stderr.write("[bench] the fused exchange's merged rows differ from the single-GPU answer: form dropped\n")
         forms = sorted(trial)
-        pick = torch.tensor([forms.index(min(trial, key=trial.get))], device=dev)
+        pick = torch.tensor([forms.index(min(forms, key=trial.get))], device=dev)
         dist.broadcast(pick, 0)
         form = forms[int(pick.item())]
         use_pipelined = form == "pipelined"
@@ -646,29 +677,9 @@ def run_gpu(args):
 
         # self-check: the merged rows of batch 0 == a single-GPU answer over the union of the shards (rank 0 builds it),
         # through the form that was timed
-        if form == "fused":
-            sh2.query_device_fused(Q2[0], k, o2)
-            sh2.drain()
-        else:
-            sh2.query_device(Q2[0], k, o2)
-        torch.cuda.synchronize()
-        verified, detail = None, None
-        if rank == 0:
-            un = DeviceShard(DIM, "cosine", capacity=world * N_ROWS, row_base=0, device=local_rank, group=None, world=1)
-            for r in range(world):
-                fill_shard(un, N_ROWS, DIM, 0xC0FFEE + 1 + r)
-            ou = un.alloc_out(nq, k)
-            un.query_local(Q2[0], k, ou)
-            torch.cuda.synchronize()
-            same_rows = bool(torch.equal(ou["rows"], o2["m_rows"]))
-            same_dist = bool(torch.allclose(ou["dist"], o2["m_dist"], rtol=1e-6, atol=0))
-            verified = same_rows and same_dist and int(o2["m_cnt"].min()) == k
-            detail = f"merged rows/distances of one {nq}-query batch == single-GPU answer over the {world * N_ROWS}-row union"
-            un.close()
-        vflag = torch.tensor([1 if (verified or rank != 0) else 0], device=dev)
-        dist.all_reduce(vflag, op=dist.ReduceOp.MIN)
-        if int(vflag.item()) != 1:
+        if not check_form(form):
             raise SystemExit("bench: row-sharded result differs from the single-GPU answer over the union")
+        detail = f"merged rows/distances of one {nq}-query batch == single-GPU answer over the {world * N_ROWS}-row union"
         bytes_per_rank = o2["layout"][0]
         if form == "fused":
             comm_backend = "nccl for setup and timing reductions only; data path: peer-to-peer stores over NVLink from the query's own kernels"
@@ -690,7 +701,7 @@ def run_gpu(args):
                                            "(DeviceShard.query_device_fused)") if form == "fused" else
                                           sh2.exchange_mode + ("; issued on a side stream behind an event so that it overlaps the scan of the next batch "
                                                                "(DeviceShard.query_device_pipelined)" if use_pipelined else "; on the scan's stream (DeviceShard.query_device)"),
-                              "form_timed": form, "trial_ms_per_step": trial,
+                              "form_timed": form, "trial_ms_per_step": trial, "fused_rejected": fused_rejected,
                               "trial_note": "every form is timed for 0.1 s and the fastest one is measured in full",
                               "nccl_all_gather_ms_per_step": shd_nccl["ms_per_step"],
                               "nccl_note": "the same step with torch.distributed all_gather_into_tensor + b2r_merge_shards_packed on one stream"},

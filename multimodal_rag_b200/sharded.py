@@ -323,14 +323,32 @@ class DeviceShard:
                 self._xchg_default = True
                 self.exchange_mode = self._P2P_MODE
             return
+        # Every rank walks the same collectives whatever fails locally (a rank that raised half way would leave the others
+        # waiting in a different collective): failures are agreed on first, then raised on every rank.
         rank = dist.get_rank(self.group)
-        x = ctypes.c_void_p()
-        _lib.check(self.lib.b2r_xchg_create(self.device, rank, self.world, nq_max, k_max, ctypes.byref(x)), "b2r_xchg_create")
+        x, err = ctypes.c_void_p(), None
         buf = ctypes.create_string_buffer(64)
-        _lib.check(self.lib.b2r_xchg_ipc_handle(x, buf), "b2r_xchg_ipc_handle")
+        try:
+            _lib.check(self.lib.b2r_xchg_create(self.device, rank, self.world, nq_max, k_max, ctypes.byref(x)), "b2r_xchg_create")
+            _lib.check(self.lib.b2r_xchg_ipc_handle(x, buf), "b2r_xchg_ipc_handle")
+        except Exception as e:                       # noqa: BLE001 -- re-raised below, on every rank
+            err = e
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(buf.raw), group=self.group)
-        _lib.check(self.lib.b2r_xchg_open(x, b"".join(handles)), "b2r_xchg_open")
+        dist.all_gather_object(handles, bytes(buf.raw) if err is None else b"", group=self.group)
+        if err is None and all(len(h_) == 64 for h_ in handles):
+            try:
+                _lib.check(self.lib.b2r_xchg_open(x, b"".join(handles)), "b2r_xchg_open")
+            except Exception as e:                   # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer could not create its mailbox")
+        dev = torch.device("cuda", self.device)
+        ok = torch.tensor([0 if err is not None else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) != 1:
+            if x:
+                self.lib.b2r_xchg_destroy(x)
+            raise RuntimeError(f"peer-to-peer exchange unavailable on this node: {err or 'a peer failed to map the mailboxes'}")
         dist.barrier(group=self.group)
         self._xchg = x
         self._xchg_limits = (nq_max, k_max)
