@@ -58,6 +58,35 @@ def _compile(name, src, defs, verbose):
     return out, r.stderr
 
 
+def build_asan() -> str:
+    """The same library with its HOST code instrumented by AddressSanitizer + UBSan (device code is untouched): the CPU tests that
+    drive the host layer without a GPU -- the id table, argument validation, shard-file parsing -- run against it with
+        LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 B2R_LIB=multimodal_rag_b200/build_asan/libb2r_asan.so \
+            python -m pytest tests/test_abi.py tests/test_idtable.py tests/test_host_tables.py -q
+    (compute-sanitizer is closed on the GPU pool; this covers the half of the library that is plain C++)."""
+    out_dir = os.path.join(HERE, "build_asan")
+    os.makedirs(out_dir, exist_ok=True)
+    san = "-fsanitize=address,-fsanitize=undefined"          # (-Xcompiler splits at commas)
+    flags = ARCH + ["-O1", "-g", "-std=c++17", "-lineinfo", "-Xcompiler", f"-fPIC,-fno-omit-frame-pointer,{san}", "-ccbin", "/usr/bin/g++"]
+
+    def one(u):
+        name, src, defs = u
+        out = os.path.join(out_dir, name + ".o")
+        r = subprocess.run([NVCC, *flags, *defs, "-c", os.path.join(CSRC, src), "-o", out], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {name}:\n{r.stdout}\n{r.stderr}")
+        return out
+
+    units = _units()
+    with cf.ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(one, units))
+    lib = os.path.join(out_dir, "libb2r_asan.so")
+    r = subprocess.run([NVCC, *ARCH, "-shared", "-o", lib, *objs, "-ccbin", "/usr/bin/g++", "-Xcompiler", san], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "digest.txt")
@@ -84,5 +113,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--asan", action="store_true", help="build build_asan/libb2r_asan.so (host code under ASan + UBSan) instead")
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build_asan() if a.asan else build(a.force, a.verbose))
