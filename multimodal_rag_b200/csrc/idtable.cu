@@ -121,9 +121,24 @@ struct b2r_idtab {
     // The probe loops run PREFETCH_AHEAD ids behind a prefetch of the home slot: the cache (and TLB) misses of a batch
     // overlap instead of queueing.  Measured on a 10M-id table, 8192-id batch: 0.18 ms against 0.24 ms unprefetched and
     // 0.31 ms when the whole batch is prefetched up front (that floods the fill buffers).
-    static constexpr int64_t PREFETCH_AHEAD = 24;
+    // A HIT costs two more dependent misses -- the row's arena offset, then its id bytes, for the byte comparison that confirms
+    // it -- so the same window looks twice more at the ids it is about to probe: 16 ahead the (by then cached) home slot is
+    // read and, when its hash matches, the row's offset is prefetched; 8 ahead the offset is read and the id bytes are
+    // prefetched.  (Hints only: an entry displaced from its home slot simply misses them.)  8192-id upsert batch with 10 % known
+    // ids on a 10M-id table (build box, medians of 56 batches): lookup 0.88 -> 0.54-0.71 ms, append 0.65 -> 0.38-0.47 ms.
+    static constexpr int64_t PREFETCH_AHEAD = 24, PEEK_OFFSET = 16, PEEK_BYTES = 8;
     void prefetch_home(int64_t i, int64_t n) const {
         if (i + PREFETCH_AHEAD < n) __builtin_prefetch(&slots[scratch[(size_t)(i + PREFETCH_AHEAD)] & mask]);
+        if (i + PEEK_OFFSET < n) {
+            const uint64_t h = scratch[(size_t)(i + PEEK_OFFSET)];
+            const Slot &sl = slots[h & mask];
+            if (sl.v != 0 && sl.h == h) __builtin_prefetch(&row_off[(size_t)(sl.v - 1)]);
+        }
+        if (i + PEEK_BYTES < n) {
+            const uint64_t h = scratch[(size_t)(i + PEEK_BYTES)];
+            const Slot &sl = slots[h & mask];
+            if (sl.v != 0 && sl.h == h) __builtin_prefetch(arena.data() + row_off[(size_t)(sl.v - 1)]);
+        }
     }
     void erase_slot(uint64_t i) {
         uint64_t j = i;
