@@ -89,13 +89,26 @@ def numpy_merge(rows, d64, cnt, k):
     return o_rows, o_dist, o_cnt
 
 
-def _worker(rank, world, port, q):
+def _real_collection_on_the_fake_device(space):
+    """The product's B200Collection (native id table, metadata columns, compiled clauses, result assembly) with
+    tests/fake_device.py answering the device entry points: sharded.py and collection.py are exercised TOGETHER on CPU."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from multimodal_rag_b200 import _lib, B200Collection
+    from fake_device import FakeLib
+    if not isinstance(_lib.load(), FakeLib):
+        lib = FakeLib()
+        _lib.load = lambda: lib
+    return B200Collection("shard", {"hnsw:space": space})
+
+
+def _worker(rank, world, port, q, kind="oracle"):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from multimodal_rag_b200.sharded import ShardedCollection
         from oracle import exact_oracle as eo
+        make_shard = (lambda: OracleShard("cosine")) if kind == "oracle" else (lambda: _real_collection_on_the_fake_device("cosine"))
         rng = np.random.default_rng(5)
         n, d = 300, 32
         X = rng.standard_normal((n, d), dtype=np.float32)
@@ -103,8 +116,7 @@ def _worker(rank, world, port, q):
         ids = [f"doc_{i // 9:03d}_text_{i}" for i in range(n)]
         metas = [{"type": "image" if i % 4 == 0 else "text", "doc_id": f"doc_{i // 9:03d}"} for i in range(n)]
         docs = [f"summary {i}" for i in range(n)]
-        sc = ShardedCollection("c", {"hnsw:space": "cosine"}, shard_factory=lambda: OracleShard("cosine"),
-                               merge_fn=numpy_merge)
+        sc = ShardedCollection("c", {"hnsw:space": "cosine"}, shard_factory=make_shard, merge_fn=numpy_merge)
         ref = eo.ExactCollection("c", {"hnsw:space": "cosine"})
         for lo in range(0, n, 77):                            # several ragged batches
             sl = slice(lo, min(n, lo + 77))
@@ -161,11 +173,14 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(180)
-def test_sharded_collection_world2_gloo():
+@pytest.mark.parametrize("kind", ["oracle", "b200_collection_on_fake_device"])
+def test_sharded_collection_world2_gloo(kind):
+    from multimodal_rag_b200 import build as b2r_build
+    b2r_build.build()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + (7 if kind == "oracle" else 13)) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, kind)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=150) for _ in procs]
