@@ -82,7 +82,8 @@ def headline_config(world, nq):
         cfg["parallelism"] = "single GPU"
     else:
         cfg["parallelism"] = (f"row-sharded: {world} shards of {N_ROWS}x{DIM} ({world * N_ROWS} rows in all), one per GPU; queries "
-                              f"replicated; ONE NCCL all_gather of the per-rank [batch, top_k] lists + merge kernel per batch; value "
+                              f"replicated; ONE exchange of the per-rank [batch, top_k] lists + merge per batch (NCCL all_gather + merge kernel, or the "
+                              f"library's fused peer-to-peer form: comm.form_timed says which was measured); value "
                               f"counts {world} x batch shard-queries per step (weak scaling: fixed work per GPU), the merged answers "
                               f"over all rows come out at value / {world}")
         cfg["rows_total"] = world * N_ROWS
