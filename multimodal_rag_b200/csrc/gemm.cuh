@@ -23,7 +23,7 @@
 // What leaves the kernel: per query a compact pool of the admitted rows that still reach the published bound
 // (KeyS: score, local row) and the final gthr[q].  Invariant used by the certificate (finalize_union_kernel):
 // a row that is not in the pool was rejected by, evicted below, or filtered against a value that was
-// published to gthr[q] -- a real row's L-th-best score, or some list's L-th best -- so its bf16 score is
+// published to gthr[q] -- the seed_rank-th best of the sampled rows' scores (k-th or L-th), or some list's L-th best -- so its bf16 score is
 // <= the final gthr[q].
 #pragma once
 #include <cuda.h>
