@@ -257,6 +257,9 @@ class ExactCollection:
                          None if documents is None else documents[i])
 
     def delete(self, ids=None, where=None, where_document=None):
+        if (ids is None or len(ids) == 0) and not where and not where_document:
+            # chromadb 0.4.22 refuses a delete without ids or a clause instead of wiping the collection
+            raise ValueError("You must provide either ids, where, or where_document to delete.")
         rows = self._select_rows(ids, where, where_document)
         for r in rows:
             self._alive[r] = False
