@@ -173,8 +173,7 @@ class B200Collection:
             if lst is not None and len(lst) != n:
                 raise ValueError(f"Number of {name} {len(lst)} must match number of ids {n}")
         if metadatas is not None:
-            for md in metadatas:
-                MetaTable.validate(md)
+            MetaTable.validate_batch(metadatas)
         if n and self._dim is not None and m.d != self._dim:
             raise ValueError(f"Embedding dimension {m.d} does not match collection dimensionality {self._dim}")
         return ids, enc, found, m
@@ -216,8 +215,7 @@ class B200Collection:
         if metas is None:
             self._meta.append_none(n)
         else:
-            for md in metas:
-                self._meta.append(md)
+            self._meta.append_batch(metas)
             self._push_columns(first.value, n, {k for md in metas if md for k in md}, m.stream)
         del keep
 
@@ -545,8 +543,7 @@ class B200Collection:
         c._idtab.append(encode_ids(t["ids"]), 0)         # an id stored more than once ends at its last row ...
         c._meta.type_codes = {k: int(v) for k, v in t["type_codes"].items()}
         c._meta.type_overflow = bool(t["type_overflow"])
-        for md in t["metadatas"]:
-            c._meta.append(md)
+        c._meta.append_batch(t["metadatas"])
         c._alive_buf = np.ones(max(c._nrows, 1024), dtype=bool)
         dead = np.asarray(t["dead_rows"], dtype=np.int64)
         c._alive_buf[dead] = False

@@ -97,8 +97,7 @@ class ShardedCollection:
                 raise ValueError(f"Number of {name} {len(lst)} must match number of ids {n}")
         if metadatas is not None:
             from .where import MetaTable
-            for md in metadatas:
-                MetaTable.validate(md)
+            MetaTable.validate_batch(metadatas)
         have_local = self._held(ids)
         have = set().union(*self._all_gather_obj(have_local))
         if upsert:

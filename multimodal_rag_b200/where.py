@@ -36,6 +36,14 @@ def _kind(v) -> int:
     raise ValueError(f"metadata values must be str, int, float or bool, got {type(v).__name__}")
 
 
+class _Missing:
+    """the key is absent from this row's metadata (batch ingestion)"""
+
+
+_MISSING = _Missing()
+_EXACT_KIND = {str: 0, int: 1, float: 1, bool: 2}
+
+
 class _Column:
     """Dictionary-encoded column: codes[row] = index into values, -1 = key absent."""
 
@@ -44,7 +52,7 @@ class _Column:
         self.n = nrows
         self.values: list = []
         self.kinds: list[int] = []
-        self.index: dict = {}
+        self.by_kind: tuple = ({}, {}, {})   # raw value -> code, per kind (1 == 1.0 == True as dict keys: kinds keep them apart)
         self.kinds_np = None       # cache of `kinds` as an array (compiled $ne leaves)
 
     def _grow(self, n):
@@ -56,14 +64,60 @@ class _Column:
     def set(self, row: int, v):
         self._grow(row + 1)
         self.n = max(self.n, row + 1)
-        key = (_kind(v), v)
-        c = self.index.get(key)
+        kd = _kind(v)
+        c = self.by_kind[kd].get(v)
         if c is None:
-            c = len(self.values)
-            self.index[key] = c
-            self.values.append(v)
-            self.kinds.append(key[0])
+            c = self._new_code(kd, v)
         self.codes[row] = c
+
+    def code_of(self, v):
+        """the code of value v in this column's dictionary, or None"""
+        return self.by_kind[_kind(v)].get(v)
+
+    def _new_code(self, kd: int, v) -> int:
+        c = len(self.values)
+        self.by_kind[kd][v] = c
+        self.values.append(v)
+        self.kinds.append(kd)
+        return c
+
+    def set_batch(self, first: int, vals: list):
+        """rows first .. first + len(vals) - 1 at once (vals[i] = the row's value or _MISSING).  A batch whose values are of one
+        kind -- the usual case -- costs one dict probe per row at C speed; only values never seen before (and absent keys) take
+        a second, interpreted pass.  Same codes, in the same order, as `set` row by row."""
+        n = len(vals)
+        types = set(map(type, vals))
+        types.discard(_Missing)
+        if not types:
+            return                                        # the key is absent from the whole batch
+        kds = {_EXACT_KIND.get(t, -1) for t in types}
+        self._grow(first + n)
+        if len(kds) != 1 or -1 in kds:                    # mixed kinds / subclasses (numpy scalars ...): row by row
+            for i, v in enumerate(vals):
+                if v is not _MISSING:
+                    self.set(first + i, v)
+            return
+        kd = kds.pop()
+        d = self.by_kind[kd]
+        get = d.get
+        codes = np.asarray([get(v, -2) for v in vals], dtype=np.int32)      # -2: not seen before, or absent
+        todo = np.flatnonzero(codes == -2)
+        if todo.size:
+            # the distinct unseen values, in order of first appearance, take the next codes (what `set` row by row would give);
+            # then the unseen rows are probed once more
+            unseen = vals if todo.size == n else [vals[i] for i in todo.tolist()]
+            fresh = dict.fromkeys(unseen)
+            fresh.pop(_MISSING, None)
+            base = len(self.values)
+            d.update(zip(fresh, range(base, base + len(fresh))))
+            self.values.extend(fresh)
+            self.kinds.extend([kd] * len(fresh))
+            codes[todo] = [get(v, -1) for v in unseen]
+        last = n - 1
+        while last >= 0 and codes[last] < 0:
+            last -= 1
+        self.codes[first: first + n] = codes
+        self.n = max(self.n, first + last + 1)
 
     def lut_mask(self, nrows: int, pred) -> np.ndarray:
         lut = np.zeros(len(self.values) + 1, dtype=bool)       # last slot = absent key
@@ -125,6 +179,41 @@ class MetaTable:
                     col = self.cols[k] = _Column(0)
                 col.set(row, v)
         return self.type_code_of(meta)
+
+    @staticmethod
+    def validate_batch(metas) -> None:
+        """`validate` for a whole batch: the types of all keys and values are collected at C speed and only looked at once"""
+        key_types, val_types = set(), set()
+        for md in metas:
+            if md is None:
+                continue
+            if type(md) is not dict:
+                MetaTable.validate(md)                    # subclasses pass, anything else raises with the row's message
+            key_types.update(map(type, md))
+            val_types.update(map(type, md.values()))
+        if key_types - {str} or val_types - set(_EXACT_KIND):
+            for md in metas:                              # an unusual type somewhere: the per-row check decides (and words the error)
+                MetaTable.validate(md)
+
+    def append_batch(self, metas: list) -> None:
+        """`append` for a whole batch, column by column (same tables as row by row; type codes are NOT returned: see
+        type_code_of)."""
+        first, n = self.nrows, len(metas)
+        self.nrows += n
+        self.meta.extend(metas)
+        # the distinct key tuples of the batch, in order of first appearance (a handful, usually one), give the keys in the order
+        # a row-by-row pass would meet them -- that order numbers the device columns
+        shapes = dict.fromkeys(map(tuple, filter(None, metas)))
+        keys = dict.fromkeys(k for shape in shapes for k in shape)
+        if len(shapes) == 1 and None not in metas and all(metas):
+            columns = dict(zip(keys, zip(*map(dict.values, metas))))       # every row has the same keys in the same order: transpose
+        else:
+            columns = {k: [md.get(k, _MISSING) if md else _MISSING for md in metas] for k in keys}
+        for k in keys:
+            col = self.cols.get(k)
+            if col is None:
+                col = self.cols[k] = _Column(0)
+            col.set_batch(first, columns[k])
 
     def append_none(self, n: int) -> None:
         """n rows without metadata (bulk adds of bare vectors): no per-row work"""
@@ -224,7 +313,7 @@ class MetaTable:
         (op, val), = cond.items()
         if op in ("$eq", "$in", "$nin"):
             for v in ([val] if op == "$eq" else val):
-                c = col.index.get((_kind(v), v))
+                c = col.code_of(v)
                 if c is not None:
                     bits[c] = True
             if op == "$nin":
@@ -233,7 +322,7 @@ class MetaTable:
             if col.kinds_np is None or col.kinds_np.shape[0] != nv:
                 col.kinds_np = np.asarray(col.kinds, dtype=np.int8)
             bits[:nv] = col.kinds_np == _kind(val)
-            c = col.index.get((_kind(val), val))
+            c = col.code_of(val)
             if c is not None:
                 bits[c] = False
         else:

@@ -150,3 +150,41 @@ def test_doc_mask_rejects_malformed_clauses():
     for bad in ({"$contains": ""}, {"$contains": 3}, {"$like": "x"}, {"$and": []}, {"$contains": "a", "$not_contains": "b"}, "table"):
         with pytest.raises(ValueError):
             doc_mask(["a"], bad)
+
+
+def test_batch_ingestion_builds_the_same_tables_as_row_by_row():
+    """MetaTable.append_batch / validate_batch (what B200Collection.add uses) against append / validate row by row: same
+    dictionaries, codes, column order (= device column numbers) and masks -- with absent keys, rows without metadata, values of
+    mixed kinds in one column (4 / 4.0 / "4" / True), numpy scalars, several batches."""
+    rng = np.random.default_rng(8)
+    metas = []
+    for i in range(3000):
+        m = {"doc_id": f"doc_{i % 41:03d}", "type": str(rng.choice(["text", "table", "image"]))}
+        if i % 3:
+            m["page"] = [4, 4.0, "4", True, 7, 2.5][i % 6]
+        if i % 5 == 0:
+            m["score"] = np.float64(i) / 3 if i % 10 else float(i)
+        if i > 1500 and i % 7 == 0:
+            m["late_key"] = f"v{i % 4}"
+        metas.append(None if i % 29 == 0 else ({} if i % 31 == 0 else m))
+    a, b = MetaTable(), MetaTable()
+    for md in metas:
+        MetaTable.validate(md)
+        a.append(md)
+    for lo in (0, 700, 701, 2000):
+        hi = {0: 700, 700: 701, 701: 2000, 2000: 3000}[lo]
+        MetaTable.validate_batch(metas[lo:hi])
+        b.append_batch(metas[lo:hi])
+    assert a.nrows == b.nrows and a.meta == b.meta and list(a.cols) == list(b.cols)
+    for k in a.cols:
+        ca, cb = a.cols[k], b.cols[k]
+        assert ca.values == cb.values and ca.kinds == cb.kinds and ca.n == cb.n, k
+        np.testing.assert_array_equal(ca.codes[: ca.n], cb.codes[: cb.n])
+    for where in ({"page": 4}, {"page": {"$ne": "4"}}, {"page": True}, {"score": {"$gt": 100.0}}, {"late_key": {"$in": ["v1", "v3"]}},
+                  {"$or": [{"type": "image"}, {"doc_id": "doc_007"}]}):
+        np.testing.assert_array_equal(a.mask(where), b.mask(where))
+        want = np.asarray([where_match(m, where) for m in metas])
+        np.testing.assert_array_equal(b.mask(where), want)
+    for bad in ([{"k": [1]}], [{3: "x"}], ["not a dict"], [{"k": None}]):
+        with pytest.raises(ValueError):
+            MetaTable.validate_batch(bad)
